@@ -1,0 +1,146 @@
+"""Record golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tools/make_golden.py            # rewrites tests/golden/*.npz
+
+Outputs (all small, committed):
+  tests/golden/env_traces.npz  -- per-step traces of Maze.reset/step + Agent.get_observations under several
+                                  mask-legal action policies and maze configurations (ref_harness.run_trace)
+  tests/golden/gen_kats.npz    -- mazes produced by Maze.build_maze for given random.seed values
+The GPU box has no /root/reference: tests only ever read these files.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# (name, maze_seed, action_seed, steps, policy, maze kwargs overriding main.py:20)
+TRACES = [
+    ("kat2_uniform", 0, 7, 5000, "uniform", {}),  # SURVEY 8c KAT(2); sha256 recorded below
+    ("guided_a", 100, 0, 2500, "guided", {}),
+    ("guided_b", 101, 1, 2500, "guided", {}),
+    ("slow_a", 200, 0, 2500, "guided_slow", {}),
+    ("slow_b", 203, 3, 2500, "guided_slow", {}),
+    ("nomark", 303, 3, 1500, "nomark", {}),
+    ("tiny7", 5, 1, 1500, "guided", dict(default_size=[4, 4], rand_sizes=False, rand_start=False, max_timestep=60)),
+    ("mixed_sizes_d3", 6, 1, 2000, "guided", dict(rand_range=[3, 9], difficulty=3, max_timestep=200)),
+    ("s49_d2", 7, 2, 2500, "guided_slow", dict(rand_range=[25, 25], difficulty=2, max_timestep=800)),
+    ("s49_guided", 8, 3, 2000, "guided", dict(rand_range=[25, 25], max_timestep=1200)),
+]
+
+MAXS = 64
+
+
+def pack_trace(tr):
+    n = len(tr["actions"])
+    mz = tr["mazes"]
+    K = len(mz)
+    lay = np.ones((K, MAXS, MAXS), np.uint8)
+    hdr = np.zeros((K, 11), np.int32)
+    for k, m in enumerate(mz):
+        a = np.asarray(m["layout"], np.uint8)
+        lay[k, :a.shape[0], :a.shape[1]] = a
+        hdr[k] = [m["width"], m["height"], m["path0"][0], m["path0"][1], m["path1"][0], m["path1"][1],
+                  m["end"][0], m["end"][1], m["key"][0], m["key"][1], m["shortest_path_len"]]
+    # obs the policy sees after each reset (episode k), i.e. emit_obs at the first step of episode k
+    first = [0] + [i + 1 for i in range(n) if tr["done"][i]]
+    reset_obs = np.zeros((K, 2, 65), np.float32)
+    reset_masks = np.zeros((K, 2, 6), np.uint8)
+    reset_agents = np.zeros((K, 2, 18), np.int32)
+    for k, i in enumerate(first):
+        if i < n:
+            reset_obs[k] = tr["emit_obs"][i]; reset_masks[k] = tr["emit_masks"][i]; reset_agents[k] = tr["agents_emit"][i]
+        else:
+            reset_obs[k] = tr["final_obs"]; reset_masks[k] = tr["final_masks"]
+    return dict(
+        maze_layout=np.packbits(lay == 1, axis=-1),  # walls only; the reference's fresh layout is 0/1
+        maze_hdr=hdr,
+        actions=np.asarray(tr["actions"], np.uint8),
+        step_obs=np.asarray(tr["step_obs"], np.float32),
+        step_masks=np.asarray(tr["step_masks"], np.uint8),
+        reward=np.asarray(tr["reward"], np.float32),
+        done=np.asarray(tr["done"], np.uint8),
+        agents_after=np.asarray(tr["agents_after"], np.int32),
+        reset_obs=reset_obs, reset_masks=reset_masks, reset_agents=reset_agents,
+        max_timestep=np.int32(tr["max_timestep"]), final_t=np.int32(tr["final_t"]),
+    )
+
+
+def kat2_hash(tr):
+    """SHA-256 of SURVEY 8c KAT(2), computed from the recorded trace."""
+    h = hashlib.sha256()
+    n = len(tr["actions"])
+
+    def emit(o, m, r, d):
+        h.update(np.asarray(o, np.float32).tobytes()); h.update(np.asarray(m, np.uint8).tobytes())
+        h.update(np.float32(r).tobytes()); h.update(bytes([int(d)]))
+    emit(tr["emit_obs"][0], tr["emit_masks"][0], 0, False)
+    for i in range(n):
+        emit(tr["step_obs"][i], tr["step_masks"][i], tr["reward"][i], tr["done"][i])
+        if tr["done"][i]:
+            emit(tr["emit_obs"][i + 1] if i + 1 < n else tr["final_obs"], tr["emit_masks"][i + 1] if i + 1 < n else tr["final_masks"], 0, False)
+    return h.hexdigest()
+
+
+def main():
+    import random
+    os.makedirs(OUT, exist_ok=True)
+    blob = {}
+    names = []
+    for name, ms, as_, n, pol, kw in TRACES:
+        tr = rh.run_trace(ms, as_, n, maze_kw=kw, policy=pol)
+        for k, v in pack_trace(tr).items():
+            blob[f"{name}/{k}"] = v
+        cfg = dict(rh.MAIN_PY_KW); cfg.update(kw)
+        blob[f"{name}/cfg"] = np.asarray([ms, as_, n, cfg["max_timestep"], cfg["difficulty"], int(cfg["rand_start"]), int(cfg["rand_sizes"]),
+                                          cfg["rand_range"][0], cfg["rand_range"][1], cfg["default_size"][0], cfg["default_size"][1]], np.int64)
+        names.append(name)
+        nd = int(np.sum(tr["done"])); print(f"{name}: steps={n} episodes={len(tr['mazes'])} dones={nd} reward_sum={sum(tr['reward'])}")
+        if name == "kat2_uniform":
+            hx = kat2_hash(tr); print("kat2 sha256", hx)
+            assert hx == "4809ce85defd322829727dd95048c32b7d522acc9a7d29685b8b4d9d489325ef"
+            blob["kat2_sha256"] = np.frombuffer(bytes.fromhex(hx), np.uint8)
+    blob["names"] = np.asarray(names)
+    np.savez_compressed(os.path.join(OUT, "env_traces.npz"), **blob)
+
+    # generator KATs: random.seed(s); Maze(**cfg).build_maze() x3 consecutive mazes per seed
+    import contextlib, io
+    g = {}
+    cfgs = [("main", {}), ("tiny7", dict(default_size=[4, 4], rand_sizes=False, rand_start=False)),
+            ("d3", dict(rand_range=[3, 9], difficulty=3)), ("s49", dict(rand_range=[25, 25], difficulty=2)),
+            ("fixed17", dict(default_size=[9, 9], rand_sizes=False, rand_start=True))]
+    for cname, kw in cfgs:
+        for seed in (0, 1, 5, 1234567, 2**40 + 17):
+            with contextlib.redirect_stdout(io.StringIO()):
+                env = rh.make_env(**kw)
+                random.seed(seed)
+                hdrs, lays, paths = [], [], []
+                for _ in range(3):
+                    env.build_maze()
+                    m = rh.maze_snapshot(env)
+                    lay = np.ones((MAXS, MAXS), np.uint8); a = np.asarray(m["layout"], np.uint8); lay[:a.shape[0], :a.shape[1]] = a
+                    lays.append(np.packbits(lay == 1, axis=-1))
+                    hdrs.append([m["width"], m["height"], m["start"][0], m["start"][1], m["end"][0], m["end"][1], m["key"][0], m["key"][1],
+                                 m["shortest_path_len"], m["path1"][0], m["path1"][1]])
+                    paths.append(hashlib.sha256(np.asarray(env.shortest_path, np.int32).tobytes()).digest())
+            cfg = dict(rh.MAIN_PY_KW); cfg.update(kw)
+            key = f"{cname}/{seed}"
+            g[key + "/hdr"] = np.asarray(hdrs, np.int32); g[key + "/layout"] = np.asarray(lays)
+            g[key + "/path_sha"] = np.frombuffer(b"".join(paths), np.uint8)
+            g[key + "/cfg"] = np.asarray([cfg["difficulty"], int(cfg["rand_start"]), int(cfg["rand_sizes"]), cfg["rand_range"][0], cfg["rand_range"][1],
+                                          cfg["default_size"][0], cfg["default_size"][1]], np.int64)
+    g["keys"] = np.asarray(sorted({k.rsplit("/", 1)[0] for k in g}))
+    np.savez_compressed(os.path.join(OUT, "gen_kats.npz"), **g)
+    for f in os.listdir(OUT):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
