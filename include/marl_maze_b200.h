@@ -1,0 +1,137 @@
+/*
+ * marl_maze_b200.h -- C ABI of libmarl_maze_b200.so (hand-written sm_100a kernels for the MARL-Maze hot path).
+ *
+ * The reference (rhuangr/MARL-Maze) is pure Python and has no FFI of its own; its hot path is reached through
+ * plain method calls.  This header is the boundary a maintainer would bind underneath those methods
+ * (ctypes stubs are shown in INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, none allocates memory;
+ *   - return value: 0 = MM_OK, otherwise an MM_ERR_* code (mm_error_string() names it); nothing throws;
+ *   - the caller (PyTorch on the host side) owns every buffer; sizes are given by the mm_sizeof_* helpers.
+ *
+ * HBM layout
+ *   maze pool (read-only while stepping), P mazes of side <= smax, rows = smax + 10:
+ *     pool_grid [P][rows][2] u64   bit planes (lo, hi) of the 2-bit cell value, bit (x+5) of row (y+5);
+ *                                  0 path, 1 wall, 2/3 marks; everything outside W x H is wall
+ *     pool_d2e  [P][smax][2] u64   bit planes of the direction-to-exit field (0 N, 1 E, 2 S, 3 W), bit (x+5) of row y
+ *     pool_hdr  [P] 4 x u32        W | H<<8 | p0x<<16 | p0y<<24,  p1x | p1y<<8 | ex<<16 | ey<<24,  kx | ky<<8 | spl<<16,  id
+ *   environments (E of them, two agents each):
+ *     env_grid  [E][rows][2] u64   working copy of the pool grid plus the agents' marks
+ *     env_hdr   [E] 4 x u32        t,  ex | ey<<8 | kx<<16 | ky<<24,  key_present | err<<1 | W<<8 | H<<16,  pool index
+ *     env_episode [E] u32          episodes started so far; the next episode of env e uses pool maze (e + episode*E) mod P
+ *     agent_a   [2E] 4 x u32, agent_b [2E] u32   packed per-agent state (mm_env.cuh)
+ */
+#ifndef MARL_MAZE_B200_H
+#define MARL_MAZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_OK 0
+#define MM_ERR_BAD_ARG 1
+#define MM_ERR_CUDA 2
+#define MM_ERR_UNSUPPORTED 3
+
+#define MM_OBS_DIM 65   /* networks.py:11 OBS_SPACE */
+#define MM_MASK_DIM 6   /* maze_agent.py:131-140 */
+#define MM_PAD 5        /* wall border kept around every stored grid */
+#define MM_MAX_SIDE 54  /* side + 2*MM_PAD <= 64 bit columns */
+#define MM_AGENT_FIELDS 18
+
+typedef struct mm_state {
+    /* pool */
+    const void *pool_grid, *pool_d2e, *pool_hdr;
+    /* environments */
+    void *env_grid, *env_hdr, *env_episode, *agent_a, *agent_b;
+    int32_t n_envs, n_pool, smax, max_timestep;
+    int32_t env_offset;   /* global id of env 0 of this shard (keys the per-env random streams; 0 on one GPU) */
+    int32_t reserved;
+} mm_state;
+
+int mm_abi_version(void);
+const char *mm_error_string(int code);
+/* last CUDA error text seen by this library on the calling thread ("" if none) */
+const char *mm_last_cuda_error(void);
+
+/* allocation sizes in bytes */
+size_t mm_sizeof_pool_grid(int n_pool, int smax);
+size_t mm_sizeof_pool_d2e(int n_pool, int smax);
+size_t mm_sizeof_pool_hdr(int n_pool);
+size_t mm_sizeof_env_grid(int n_envs, int smax);
+size_t mm_sizeof_env_hdr(int n_envs);
+size_t mm_sizeof_env_episode(int n_envs);
+size_t mm_sizeof_agent_a(int n_envs);
+size_t mm_sizeof_agent_b(int n_envs);
+size_t mm_sizeof_finalize_scratch(int n, int smax);
+size_t mm_sizeof_generate_scratch(int n, int smax);
+
+/* Agent.__init__ state for every agent (maze_agent.py:16-57): x=y=0, facing south, exit_len=-1, empty memory. */
+int mm_init_state(const mm_state *st, void *stream);
+
+/*
+ * Parity injection: pack byte layouts recorded from the reference into pool entries [first, first+n).
+ * Replaces nothing in the reference (it exists so that identical mazes can be replayed); computes the
+ * dir-to-exit field by a tree walk from the exit (the closed form of Agent.exit_route, maze.py:148-154,
+ * maze_agent.py:227-260).   layouts: [n][smax][smax] u8 (0 path / 1 wall, row-major, top-left W x H used)
+ * hdr: [n][11] i32 = W,H,p0x,p0y,p1x,p1y,ex,ey,kx,ky,shortest_path_len.   scratch: mm_sizeof_finalize_scratch.
+ */
+int mm_load_layouts(const mm_state *st, int first, int n, const uint8_t *layouts, const int32_t *hdr, void *scratch, void *stream);
+
+/*
+ * K1 -- batched maze generator.  Replaces Maze.build_maze/get_neighbors/set_start/set_end/set_key/
+ * get_shortest_path (maze.py:170-273): randomized DFS carve with the corridor-length bias, exit on the left or
+ * right edge (best of `difficulty` candidates), key by rejection sampling off the start->exit path.
+ * Random stream: Philox4x32-10 keyed by (seed, maze id = id_base + index) -- see DESIGN.md for the draw mapping.
+ * side_lo..side_hi: the maze side is (randint(side_lo, side_hi))*2-1 like rand_range (maze.py:172).
+ */
+int mm_generate(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
+                uint64_t seed, uint32_t id_base, void *scratch, void *stream);
+
+/*
+ * Maze.reset() (maze.py:55-72) + Agent.reset() (maze_agent.py:59-79) for every env with reset_mask[e] != 0
+ * (all envs when reset_mask == NULL): takes the next pool maze, places agent i on shortest_path[i], emits the
+ * first observations/masks.   obs: [E][2][65] f32, masks: [E][2][6] u8.
+ */
+int mm_reset(const mm_state *st, const uint8_t *reset_mask, float *obs, uint8_t *masks, void *stream);
+
+/*
+ * K2 -- fused step + observation.  Replaces Maze.step / single_agent_step (maze.py:74-163) and
+ * Agent.get_observations with all helpers (maze_agent.py:89-358).
+ *   actions [E][2][2] u8 (move 0..4 relative to facing, mark 0/1)
+ *   obs [E][2][65] f32, masks [E][2][6] u8, reward [E] f32, done [E] u8
+ *   auto_reset != 0: a finished env is reset in the same launch and obs/masks are those of the new episode
+ *   (the PPO.get_batch loop, PPO.py:120-130); reward/done always describe the step just taken.
+ *   actions_out (may be NULL): when actions == NULL the kernel draws uniform mask-legal actions itself
+ *   (Philox keyed by seed, env, agent, step) from the masks it emitted last step and records them here.
+ */
+int mm_step_obs(const mm_state *st, const uint8_t *actions, float *obs, uint8_t *masks, float *reward, uint8_t *done,
+                int auto_reset, uint64_t action_seed, uint8_t *actions_out, void *stream);
+
+/* Debug/test readback of the packed agent state as the fields of tools/ref_harness.py AGENT_FIELDS: out [E][2][18] i32 */
+int mm_unpack_agents(const mm_state *st, int32_t *out, void *stream);
+/* out [E][8] i32 = t, key_x, key_y (-1 if taken), pool index, W, H, err, episode */
+int mm_unpack_envs(const mm_state *st, int32_t *out, void *stream);
+/* byte layout of env e's working grid (marks included): out [smax][smax] u8 */
+int mm_unpack_layout(const mm_state *st, int env, uint8_t *out, void *stream);
+/* byte layout + dir-to-exit of pool maze p: out_layout [smax][smax] u8, out_d2e [smax][smax] u8, out_hdr [11] i32 */
+int mm_unpack_pool(const mm_state *st, int p, uint8_t *out_layout, uint8_t *out_d2e, int32_t *out_hdr, void *stream);
+
+/*
+ * K3 -- GAE reverse scan.  Replaces PPO.get_GAEs (PPO.py:193-203) over fixed-horizon [T][E] buffers with
+ * episode boundaries marked by done[t][e]; v_boot[e] = V(s_T) bootstraps episodes still open at t = T-1
+ * (extension).  adv [T][E] f32; rtg (may be NULL) = adv + value (PPO.py:46).  gamma/lam are doubles
+ * because the reference multiplies them as python floats before the product meets an fp32 tensor (PPO.py:201).
+ */
+int mm_gae(const float *reward, const float *value, const uint8_t *done, const float *v_boot, float *adv, float *rtg,
+           int T, int E, double gamma, double lam, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

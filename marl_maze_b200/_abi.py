@@ -1,0 +1,82 @@
+"""ctypes binding of include/marl_maze_b200.h.  There is NO CPU fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+EXPORTS = [
+    "mm_abi_version", "mm_error_string", "mm_last_cuda_error",
+    "mm_sizeof_pool_grid", "mm_sizeof_pool_d2e", "mm_sizeof_pool_hdr", "mm_sizeof_env_grid", "mm_sizeof_env_hdr",
+    "mm_sizeof_env_episode", "mm_sizeof_agent_a", "mm_sizeof_agent_b", "mm_sizeof_finalize_scratch", "mm_sizeof_generate_scratch",
+    "mm_init_state", "mm_load_layouts", "mm_generate", "mm_reset", "mm_step_obs",
+    "mm_unpack_agents", "mm_unpack_envs", "mm_unpack_layout", "mm_unpack_pool", "mm_gae",
+]
+
+
+class MMState(C.Structure):
+    """struct mm_state of include/marl_maze_b200.h"""
+    _fields_ = [("pool_grid", C.c_void_p), ("pool_d2e", C.c_void_p), ("pool_hdr", C.c_void_p),
+                ("env_grid", C.c_void_p), ("env_hdr", C.c_void_p), ("env_episode", C.c_void_p),
+                ("agent_a", C.c_void_p), ("agent_b", C.c_void_p),
+                ("n_envs", C.c_int32), ("n_pool", C.c_int32), ("smax", C.c_int32), ("max_timestep", C.c_int32),
+                ("env_offset", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MMError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        # sources present (a checkout): build in-tree; otherwise fail loudly -- there is no other code path
+        try:
+            path = _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise MMError(f"libmarl_maze_b200.so is missing and could not be built ({e}); "
+                          "run `python -m marl_maze_b200.build` (needs nvcc). There is no CPU fallback.") from e
+    L = C.CDLL(path)
+    vp, i32, u64, u32, sz = C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_size_t
+    st = C.POINTER(MMState)
+    sig = {
+        "mm_abi_version": (i32, []),
+        "mm_error_string": (C.c_char_p, [i32]),
+        "mm_last_cuda_error": (C.c_char_p, []),
+        "mm_sizeof_pool_grid": (sz, [i32, i32]), "mm_sizeof_pool_d2e": (sz, [i32, i32]), "mm_sizeof_pool_hdr": (sz, [i32]),
+        "mm_sizeof_env_grid": (sz, [i32, i32]), "mm_sizeof_env_hdr": (sz, [i32]), "mm_sizeof_env_episode": (sz, [i32]),
+        "mm_sizeof_agent_a": (sz, [i32]), "mm_sizeof_agent_b": (sz, [i32]),
+        "mm_sizeof_finalize_scratch": (sz, [i32, i32]), "mm_sizeof_generate_scratch": (sz, [i32, i32]),
+        "mm_init_state": (i32, [st, vp]),
+        "mm_load_layouts": (i32, [st, i32, i32, vp, vp, vp, vp]),
+        "mm_generate": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, vp, vp]),
+        "mm_reset": (i32, [st, vp, vp, vp, vp]),
+        "mm_step_obs": (i32, [st, vp, vp, vp, vp, vp, i32, u64, vp, vp]),
+        "mm_unpack_agents": (i32, [st, vp, vp]),
+        "mm_unpack_envs": (i32, [st, vp, vp]),
+        "mm_unpack_layout": (i32, [st, i32, vp, vp]),
+        "mm_unpack_pool": (i32, [st, i32, vp, vp, vp, vp]),
+        "mm_gae": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp]),
+    }
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise MMError(f"{path} does not export {name}")
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def check(code: int, what: str):
+    if code != 0:
+        L = lib()
+        raise MMError(f"{what}: {L.mm_error_string(code).decode()} {L.mm_last_cuda_error().decode()}")

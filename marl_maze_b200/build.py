@@ -1,0 +1,57 @@
+"""Build libmarl_maze_b200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+    python -m marl_maze_b200.build        # or __graft_entry__.build()
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmarl_maze_b200.so")
+SOURCES = ["mm_abi.cu", "mm_step_obs.cu", "mm_pool.cu", "mm_gae.cu", "mm_generate.cu", "mm_policy.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC"]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: marl_maze_b200 has no CPU fallback and cannot be built without the CUDA toolkit")
+
+
+def sources():
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(os.path.dirname(HERE), "include", "marl_maze_b200.h")]
+    return srcs, hdrs
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    srcs, hdrs = sources()
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in srcs + hdrs)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    srcs, _ = sources()
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [_nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

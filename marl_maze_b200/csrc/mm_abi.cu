@@ -1,0 +1,140 @@
+// mm_abi.cu -- the C ABI declared in include/marl_maze_b200.h.  Thin argument checking + kernel launches; no torch types.
+#include <stdio.h>
+#include <string.h>
+#include "mm_env.cuh"
+
+namespace mm {
+cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream);
+cudaError_t launch_gae(const float*, const float*, const uint8_t*, const float*, float*, float*, int, int, double, double, cudaStream_t);
+cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
+                            uint64_t seed, uint32_t id_base, void* scratch, cudaStream_t stream);
+__global__ void k_load_layouts(ulonglong2*, ulonglong2*, uint4*, int, int, int, int, const uint8_t*, const int32_t*, uint16_t*);
+__global__ void k_init_state(uint4*, uint32_t*, uint4*, uint32_t*, int);
+__global__ void k_unpack_agents(const uint4*, const uint32_t*, const uint4*, const ulonglong2*, int, int, int32_t*);
+__global__ void k_unpack_envs(const uint4*, const uint32_t*, int, int32_t*);
+__global__ void k_unpack_grid(const ulonglong2*, const ulonglong2*, int, uint8_t*, uint8_t*);
+__global__ void k_unpack_pool_hdr(const uint4*, int, int32_t*);
+}  // namespace mm
+
+using namespace mm;
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_status(cudaError_t e) {
+    if (e == cudaSuccess) return MM_OK;
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return MM_ERR_CUDA;
+}
+static bool state_ok(const mm_state* st) {
+    return st && st->n_envs > 0 && st->n_pool > 0 && st->smax >= 3 && st->smax <= MM_MAX_SIDE && st->max_timestep > 0 && st->pool_grid && st->pool_d2e &&
+           st->pool_hdr && st->env_grid && st->env_hdr && st->env_episode && st->agent_a && st->agent_b;
+}
+static StepParams make_params(const mm_state* st) {
+    StepParams p{};
+    p.pool_grid = (const ulonglong2*)st->pool_grid; p.pool_d2e = (const ulonglong2*)st->pool_d2e; p.pool_hdr = (const uint4*)st->pool_hdr;
+    p.env_grid = (ulonglong2*)st->env_grid; p.env_hdr = (uint4*)st->env_hdr; p.env_episode = (uint32_t*)st->env_episode;
+    p.agent_a = (uint4*)st->agent_a; p.agent_b = (uint32_t*)st->agent_b;
+    p.E = st->n_envs; p.P = st->n_pool; p.rows = st->smax + 2 * MM_PAD; p.smax = st->smax; p.max_t = st->max_timestep; p.env_offset = st->env_offset;
+    return p;
+}
+
+extern "C" {
+
+int mm_abi_version(void) { return 1; }
+const char* mm_error_string(int code) {
+    switch (code) {
+        case MM_OK: return "ok";
+        case MM_ERR_BAD_ARG: return "bad argument";
+        case MM_ERR_CUDA: return "CUDA error (see mm_last_cuda_error)";
+        case MM_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown";
+    }
+}
+const char* mm_last_cuda_error(void) { return g_cuda_err; }
+
+size_t mm_sizeof_pool_grid(int n_pool, int smax) { return (size_t)n_pool * (smax + 2 * MM_PAD) * 16; }
+size_t mm_sizeof_pool_d2e(int n_pool, int smax) { return (size_t)n_pool * smax * 16; }
+size_t mm_sizeof_pool_hdr(int n_pool) { return (size_t)n_pool * 16; }
+size_t mm_sizeof_env_grid(int n_envs, int smax) { return (size_t)n_envs * (smax + 2 * MM_PAD) * 16; }
+size_t mm_sizeof_env_hdr(int n_envs) { return (size_t)n_envs * 16; }
+size_t mm_sizeof_env_episode(int n_envs) { return (size_t)n_envs * 4; }
+size_t mm_sizeof_agent_a(int n_envs) { return (size_t)n_envs * 2 * 16; }
+size_t mm_sizeof_agent_b(int n_envs) { return (size_t)n_envs * 2 * 4; }
+size_t mm_sizeof_finalize_scratch(int n, int smax) { return (size_t)n * smax * smax * 2; }
+size_t mm_sizeof_generate_scratch(int n, int smax) { return (size_t)n * smax * smax * 2; }
+
+int mm_init_state(const mm_state* st, void* stream) {
+    if (!state_ok(st)) return MM_ERR_BAD_ARG;
+    const int n = 2 * st->n_envs;
+    k_init_state<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint4*)st->env_hdr, (uint32_t*)st->env_episode, (uint4*)st->agent_a, (uint32_t*)st->agent_b, st->n_envs);
+    return cuda_status(cudaGetLastError());
+}
+
+int mm_load_layouts(const mm_state* st, int first, int n, const uint8_t* layouts, const int32_t* hdr, void* scratch, void* stream) {
+    if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || (n && (!layouts || !hdr || !scratch))) return MM_ERR_BAD_ARG;
+    if (n == 0) return MM_OK;
+    k_load_layouts<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>((ulonglong2*)st->pool_grid, (ulonglong2*)st->pool_d2e, (uint4*)st->pool_hdr, first, n,
+                                                                  st->smax + 2 * MM_PAD, st->smax, layouts, hdr, (uint16_t*)scratch);
+    return cuda_status(cudaGetLastError());
+}
+
+int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
+                void* scratch, void* stream) {
+    if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 2 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
+        (n && !scratch))
+        return MM_ERR_BAD_ARG;
+    if (n == 0) return MM_OK;
+    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, scratch, (cudaStream_t)stream));
+}
+
+int mm_reset(const mm_state* st, const uint8_t* reset_mask, float* obs, uint8_t* masks, void* stream) {
+    if (!state_ok(st) || !obs || !masks) return MM_ERR_BAD_ARG;
+    StepParams p = make_params(st);
+    p.reset_mask = reset_mask; p.obs = obs; p.masks = masks;
+    return cuda_status(launch_step_obs(p, true, (cudaStream_t)stream));
+}
+
+int mm_step_obs(const mm_state* st, const uint8_t* actions, float* obs, uint8_t* masks, float* reward, uint8_t* done, int auto_reset,
+                uint64_t action_seed, uint8_t* actions_out, void* stream) {
+    if (!state_ok(st) || !obs || !masks || !reward || !done) return MM_ERR_BAD_ARG;
+    if (((uintptr_t)obs & 15) || ((uintptr_t)masks & 1) || ((uintptr_t)actions & 1) || ((uintptr_t)actions_out & 1)) return MM_ERR_BAD_ARG;
+    StepParams p = make_params(st);
+    p.actions = actions; p.actions_out = actions_out; p.obs = obs; p.masks = masks; p.reward = reward; p.done = done;
+    p.auto_reset = auto_reset; p.action_seed = action_seed;
+    return cuda_status(launch_step_obs(p, false, (cudaStream_t)stream));
+}
+
+int mm_unpack_agents(const mm_state* st, int32_t* out, void* stream) {
+    if (!state_ok(st) || !out) return MM_ERR_BAD_ARG;
+    const int n = 2 * st->n_envs;
+    k_unpack_agents<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const uint4*)st->agent_a, (const uint32_t*)st->agent_b, (const uint4*)st->env_hdr,
+                                                                      (const ulonglong2*)st->pool_d2e, st->smax, st->n_envs, out);
+    return cuda_status(cudaGetLastError());
+}
+int mm_unpack_envs(const mm_state* st, int32_t* out, void* stream) {
+    if (!state_ok(st) || !out) return MM_ERR_BAD_ARG;
+    k_unpack_envs<<<(st->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const uint4*)st->env_hdr, (const uint32_t*)st->env_episode, st->n_envs, out);
+    return cuda_status(cudaGetLastError());
+}
+int mm_unpack_layout(const mm_state* st, int env, uint8_t* out, void* stream) {
+    if (!state_ok(st) || !out || env < 0 || env >= st->n_envs) return MM_ERR_BAD_ARG;
+    const int n = st->smax * st->smax, rows = st->smax + 2 * MM_PAD;
+    k_unpack_grid<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const ulonglong2*)st->env_grid + (size_t)env * rows, nullptr, st->smax, out, nullptr);
+    return cuda_status(cudaGetLastError());
+}
+int mm_unpack_pool(const mm_state* st, int p, uint8_t* out_layout, uint8_t* out_d2e, int32_t* out_hdr, void* stream) {
+    if (!state_ok(st) || !out_layout || !out_d2e || !out_hdr || p < 0 || p >= st->n_pool) return MM_ERR_BAD_ARG;
+    const int n = st->smax * st->smax, rows = st->smax + 2 * MM_PAD;
+    k_unpack_grid<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const ulonglong2*)st->pool_grid + (size_t)p * rows,
+                                                                    (const ulonglong2*)st->pool_d2e + (size_t)p * st->smax, st->smax, out_layout, out_d2e);
+    k_unpack_pool_hdr<<<1, 1, 0, (cudaStream_t)stream>>>((const uint4*)st->pool_hdr, p, out_hdr);
+    return cuda_status(cudaGetLastError());
+}
+
+int mm_gae(const float* reward, const float* value, const uint8_t* done, const float* v_boot, float* adv, float* rtg, int T, int E, double gamma,
+           double lam, void* stream) {
+    if (!reward || !value || !done || !adv || T < 0 || E < 0) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_gae(reward, value, done, v_boot, adv, rtg, T, E, gamma, lam, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// mm_step_obs.cu -- K2: fused environment step + observation (+ in-launch auto-reset), sm_100a.
+//
+// Replaces Maze.step / Maze.single_agent_step (maze.py:74-163), Maze.reset's agent placement (maze.py:55-72),
+// Agent.reset (maze_agent.py:59-79) and Agent.get_observations with every helper (maze_agent.py:89-358).
+//
+// Mapping: one lane per AGENT, the two agents of an environment sit in adjacent lanes (2e, 2e+1), a warp owns
+// 16 environments.  Everything that is a function of one agent's own position and the grid (rays, marks,
+// dead ends, key / exit / other-agent sightings, bounding box) runs on both lanes at once; the reference's
+// sequential coupling (agent 0 stepped and observed before agent 1, route sharing mutating the other agent,
+// key pickup priority, mark overwrite order) is resolved with a handful of warp shuffles between the pair.
+//
+// Memory: per-agent 11-row window of the bit-plane grid is read straight from HBM (rows y-5..y+5, one 16-byte
+// (lo,hi) pair per row); marks are applied in registers and the marked row written back; observations are
+// staged in shared memory ([lane][65] floats, stride 65 = conflict-free) and leave as one coalesced
+// 8320-byte stream per warp directly into the caller's rollout buffer.
+#include "mm_env.cuh"
+
+namespace mm {
+
+constexpr int kThreads = 128;
+
+// One axis ray seen from the agent.  cw: bit j-1 = wall (or out of bounds) at distance j, j = 1..5.
+// latopen: bit j-1 = a cell left or right of the ray cell at distance j is open, j = 1..4.
+// Returns n = number of visible cells (maze_agent.py:218-225) and the dead-end code de in quarters
+// (get_dead_ends, maze_agent.py:143-181: 4 = wall adjacent, 4-j = dead end seen at distance j, 0 = none).
+__device__ __forceinline__ void ray_eval(uint32_t cw, uint32_t latopen, uint32_t own_open, int& n, int& de) {
+    n = __ffs(cw | 0x10u) - 1;
+    const uint32_t open = ~cw;
+    const uint32_t FWD = (open >> 1) & 0xfu;                // neighbour ahead of cell j is open
+    const uint32_t BACK = ((open << 1) | own_open) & 0xfu;  // neighbour behind cell j is open
+    const uint32_t LAT = latopen & 0xfu;
+    const uint32_t CNT1 = ~LAT & (BACK ^ FWD) & 0xfu;        // exactly one open neighbour
+    const uint32_t BRK0 = (LAT | (~CNT1 & ~FWD)) & 0xfu;     // a turn, or a wall ahead without being a dead end
+    const uint32_t ev = BRK0 | CNT1;
+    const int j = __ffs(ev);                                // first event along the ray (0 = none within 4)
+    int d = (j && ((CNT1 >> (j - 1)) & 1u)) ? 4 - j : 0;
+    de = (cw & 1u) ? 4 : d;
+}
+
+// Where does (dx,dy) lie relative to the agent: j = 0 same cell, 1.. distance along axis ray `dir`, 99 = off-axis.
+__device__ __forceinline__ void locate(int dx, int dy, int& dir, int& j) {
+    const int adx = abs(dx), ady = abs(dy);
+    if (dx == 0) { dir = dy < 0 ? 0 : 2; j = ady; }
+    else if (dy == 0) { dir = dx > 0 ? 1 : 3; j = adx; }
+    else { dir = 0; j = 99; }
+}
+
+__device__ __forceinline__ uint32_t rev5(uint32_t v) { return __brev(v & 0x1fu) >> 27; }
+__device__ __forceinline__ uint32_t rot4r(uint32_t m, int f) { return ((m | (m << 4)) >> f) & 0xfu; }  // abs-direction bits -> relative
+__device__ __forceinline__ float fdiv(int a, int b) { return __fdiv_rn((float)a, (float)b); }
+
+template <bool kResetOnly>
+__global__ void __launch_bounds__(kThreads) k_step_obs(const StepParams p) {
+    extern __shared__ __align__(16) float s_obs[];  // [kThreads][65]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long g = (long long)blockIdx.x * kThreads + tid;  // global agent index
+    const int e = (int)(g >> 1);
+    const int a = (int)(g & 1);  // 0 = tag 2 (RED), 1 = tag 3 (BLUE), main.py:18-19
+    const bool valid = e < p.E;
+
+    uint4 H = make_uint4(0, 0, 0, 0), A = make_uint4(0, 0, 0, 0);
+    uint32_t B = 0;
+    if (valid) { H = p.env_hdr[e]; A = p.agent_a[g]; B = p.agent_b[g]; }
+    Agent me = unpack_agent(A, B);
+    uint32_t t = H.x, keyp = H.z & 1u, err = (H.z >> 1) & 1u, pidx = H.w;
+    int W = (H.z >> 8) & 0xff, Hh = (H.z >> 16) & 0xff;
+    int ex = H.y & 0xff, ey = (H.y >> 8) & 0xff, kx = (H.y >> 16) & 0xff, ky = H.y >> 24;
+
+    float reward = 0.f;
+    uint32_t done = 0;
+    bool mk = false;      // this agent marked its (pre-move) cell this step
+    int px = 0, py = 0;   // pre-move cell
+    bool want_reset = false;
+
+    if (kResetOnly) {
+        want_reset = valid && (p.reset_mask == nullptr || p.reset_mask[e] != 0);
+    } else {
+        // ---------------------------------------------------------------- S1: Maze.step / single_agent_step
+        int move, mark;
+        if (p.actions != nullptr) {
+            const uint32_t aw = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(p.actions)[g] : 4u;
+            move = aw & 0xff; mark = (aw >> 8) & 0xff;
+        } else {  // uniform mask-legal action from the masks emitted by the previous launch
+            uint32_t r[4];
+            philox4x32_10(t, (uint32_t)(p.env_offset + e) * 2u + (uint32_t)a, 0x4d415a45u, 0u, (uint32_t)p.action_seed, (uint32_t)(p.action_seed >> 32), r);
+            uint32_t legal = me.last_mask & 0x1fu;
+            const int n = __popc(legal);
+            move = 4;
+            if (n) {
+                int k = (int)(((uint64_t)r[0] * (uint32_t)n) >> 32);
+                for (int i = 0; i < 4; i++) if (i < k) legal &= legal - 1;
+                move = __ffs(legal) - 1;
+            }
+            mark = ((me.last_mask >> 5) & 1u) ? (int)(r[1] & 1u) : 0;
+            if (valid && p.actions_out != nullptr) reinterpret_cast<uint16_t*>(p.actions_out)[g] = (uint16_t)(move | (mark << 8));
+        }
+        t += 1;  // maze.py:75
+        px = me.x; py = me.y;
+        if (mark == 1) { mk = true; me.lmx = px; me.lmy = py; me.mkv = 1; }  // maze.py:132-134 (grid write below)
+        uint32_t cand_key = 0;
+        if (move < 4) {  // maze.py:137-162
+            const int nd = (move + me.dir) & 3;
+            const int nx = me.x + (nd == 1) - (nd == 3), ny = me.y + (nd == 2) - (nd == 0);
+            if (nx < 0 || nx >= W || ny < 0 || ny >= Hh) {
+                err = 1;  // the reference prints and then indexes out of range (maze.py:141-145): treated as `stop` + error flag
+            } else {
+                if (me.ke) {  // exit_route pop/push == walking along / against the tree path to the exit (maze.py:148-154)
+                    const bool at_end_pre = (me.x == ex && me.y == ey);
+                    me.exit_len += (!at_end_pre && nd == me.d2e) ? -1 : 1;
+                }
+                me.x = nx; me.y = ny; me.dir = nd;
+                cand_key = keyp && nx == kx && ny == ky;
+                me.mem = (me.mem >> 3) | ((uint32_t)(move + 1) << 9);
+            }
+        } else if (move > 4) {
+            err = 1;
+        }
+        // key pickup: agent 0 is stepped first and takes the key if both arrive together (maze.py:157-161)
+        const uint32_t c0 = __shfl_sync(kFull, cand_key, lane & ~1), c1 = __shfl_sync(kFull, cand_key, lane | 1);
+        const uint32_t got = a == 0 ? c0 : (c1 & ~c0 & 1u);
+        if (got) { me.has = 1; me.team = 1; }
+        const uint32_t got_any = c0 | c1;
+        keyp &= ~got_any & 1u;
+        err |= __shfl_xor_sync(kFull, err, 1);
+        // reward / done (maze.py:115-121): needs only post-move positions and has_key
+        const uint32_t ohas = __shfl_xor_sync(kFull, me.has, 1);
+        const int oxp = __shfl_xor_sync(kFull, me.x, 1), oyp = __shfl_xor_sync(kFull, me.y, 1);
+        reward = got_any ? 0.5f : 0.f;
+        if ((me.has | ohas) && oxp == me.x && oyp == me.y && me.x == ex && me.y == ey) { reward = 1.f; done = 1; }
+        else if ((int)t >= p.max_t) done = 1;
+        want_reset = valid && done && p.auto_reset;
+    }
+
+    bool wrote = false;
+#pragma unroll 1
+    for (int pass = kResetOnly ? 1 : 0; pass < 2; ++pass) {
+        const bool act = valid && (pass == 0 || want_reset);
+        if (pass == 1 && !__any_sync(kFull, act)) break;
+
+        // What the partner sees of me.  In the reset pass agent 0 is observed while agent 1 still holds the
+        // PREVIOUS episode's x, y, direction, has_key, knows_end (maze.py:64-71): lane 1 keeps
+        // presenting its stale fields, lane 0 presents its freshly reset ones.
+        int pres_x = me.x, pres_y = me.y, pres_dir = me.dir;
+        uint32_t pres_has = me.has, pres_ke = me.ke;
+
+        if (pass == 1) {
+            uint32_t ep = (act && a == 0) ? p.env_episode[e] : 0u;
+            ep = __shfl_sync(kFull, ep, lane & ~1);
+            if (act) {
+                pidx = (uint32_t)(((unsigned long long)e + (unsigned long long)ep * (unsigned)p.E) % (unsigned)p.P);
+                if (a == 0) p.env_episode[e] = ep + 1;
+                const uint4 ph = p.pool_hdr[pidx];
+                W = ph.x & 0xff; Hh = (ph.x >> 8) & 0xff;
+                const int sx = a ? (int)(ph.y & 0xff) : (int)((ph.x >> 16) & 0xff);
+                const int sy = a ? (int)((ph.y >> 8) & 0xff) : (int)(ph.x >> 24);
+                ex = (ph.y >> 16) & 0xff; ey = ph.y >> 24; kx = ph.z & 0xff; ky = (ph.z >> 8) & 0xff;
+                keyp = 1; t = 0;  // maze.py:56
+                // Agent.reset (maze_agent.py:59-79); time_from_last_seen is deliberately kept
+                me.x = sx; me.y = sy; me.olsx = sx; me.olsy = sy;
+                me.minx = me.maxx = sx; me.miny = me.maxy = sy;
+                me.dir = 2; me.mkv = 0; me.mem = 0; me.ke = me.oke = 0; me.exit_len = -1; me.has = me.team = 0;
+                if (a == 0) { pres_x = me.x; pres_y = me.y; pres_dir = me.dir; pres_has = 0; pres_ke = 0; }
+                // fresh working copy of the grid (no marks yet); the two lanes interleave rows
+                const ulonglong2* src = p.pool_grid + (size_t)pidx * p.rows;
+                ulonglong2* dst = p.env_grid + (size_t)e * p.rows;
+                for (int r = a; r < p.rows; r += 2) dst[r] = src[r];
+            }
+        }
+
+        // ------------------------------------------------------------ window: rows y-5..y+5 of both bit planes
+        const int x = me.x, y = me.y, f = me.dir;
+        ulonglong2 w[11];
+        ulonglong2 dd = make_ulonglong2(0, 0);
+        if (act) {
+            const ulonglong2* grid = pass == 0 ? (const ulonglong2*)(p.env_grid + (size_t)e * p.rows) : (p.pool_grid + (size_t)pidx * p.rows);
+#pragma unroll
+            for (int r = 0; r < 11; r++) w[r] = __ldcg(&grid[y + r]);
+            dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 11; r++) w[r] = make_ulonglong2(~0ull, 0ull);
+        }
+        const int d2e_here = (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
+
+        // ------------------------------------------------------------ marks of this step (agent 0's first, maze.py:80-90,132-133)
+        if (pass == 0) {
+            const uint32_t omk = __shfl_xor_sync(kFull, (uint32_t)mk, 1);
+            const int opx = __shfl_xor_sync(kFull, px, 1), opy = __shfl_xor_sync(kFull, py, 1);
+            const bool m0 = a ? (omk != 0) : mk, m1 = a ? mk : (omk != 0);
+            const int m0x = a ? opx : px, m0y = a ? opy : py, m1x = a ? px : opx, m1y = a ? py : opy;
+            if (m0) {  // tag 2: hi=1, lo=0
+                const int rr = m0y - y + kPad; const unsigned long long bit = 1ull << (m0x + kPad);
+#pragma unroll
+                for (int r = 0; r < 11; r++) if (rr == r) { w[r].y |= bit; w[r].x &= ~bit; }
+            }
+            if (m1) {  // tag 3: hi=1, lo=1
+                const int rr = m1y - y + kPad; const unsigned long long bit = 1ull << (m1x + kPad);
+#pragma unroll
+                for (int r = 0; r < 11; r++) if (rr == r) { w[r].y |= bit; w[r].x |= bit; }
+            }
+            if (mk && act) {  // the marked row (pre-move cell: window row 4, 5 or 6) goes back to HBM with both marks applied
+                const int rr = py - y + kPad;
+                const ulonglong2 row = rr == 4 ? w[4] : (rr == 6 ? w[6] : w[5]);
+                p.env_grid[(size_t)e * p.rows + py + kPad] = row;
+            }
+        }
+
+        // ------------------------------------------------------------ per-direction bit masks (abs 0 N, 1 E, 2 S, 3 W)
+        uint32_t l5, h5, wl4, wl5, wl6;
+        uint32_t cw[4] = {0, 0, 0, 0}, lat[4] = {0, 0, 0, 0}, ownm[4] = {0, 0, 0, 0}, othm[4] = {0, 0, 0, 0};
+        const uint32_t ua = (uint32_t)a;
+        {
+            uint32_t l[11], h[11];
+#pragma unroll
+            for (int r = 0; r < 11; r++) { l[r] = (uint32_t)(w[r].x >> x); h[r] = (uint32_t)(w[r].y >> x); }
+            l5 = l[5]; h5 = h[5]; wl4 = l[4] & ~h[4]; wl5 = l5 & ~h5; wl6 = l[6] & ~h[6];
+#pragma unroll
+            for (int j = 1; j <= 5; j++) {
+                const int rn = 5 - j, rs = 5 + j;
+                const uint32_t wn = l[rn] & ~h[rn], ws = l[rs] & ~h[rs];
+                cw[0] |= ((wn >> 5) & 1u) << (j - 1);
+                cw[2] |= ((ws >> 5) & 1u) << (j - 1);
+                if (j <= 4) {
+                    lat[0] |= (((~wn >> 4) | (~wn >> 6)) & 1u) << (j - 1);
+                    lat[2] |= (((~ws >> 4) | (~ws >> 6)) & 1u) << (j - 1);
+                    const uint32_t hn = (h[rn] >> 5) & 1u, ln = (l[rn] >> 5) & 1u, hs = (h[rs] >> 5) & 1u, ls = (l[rs] >> 5) & 1u;
+                    ownm[0] |= (hn & (ln ^ ua ^ 1u)) << (j - 1); othm[0] |= (hn & (ln ^ ua)) << (j - 1);
+                    ownm[2] |= (hs & (ls ^ ua ^ 1u)) << (j - 1); othm[2] |= (hs & (ls ^ ua)) << (j - 1);
+                }
+            }
+        }
+        const uint32_t own5 = h5 & (a ? l5 : ~l5), oth5 = h5 & ~own5;
+        const uint32_t lat5 = ~wl4 | ~wl6;
+        cw[1] = (wl5 >> 6) & 0x1fu; lat[1] = (lat5 >> 6) & 0xfu; ownm[1] = (own5 >> 6) & 0xfu; othm[1] = (oth5 >> 6) & 0xfu;
+        cw[3] = rev5(wl5); lat[3] = rev5(lat5) & 0xfu; ownm[3] = rev5(own5) & 0xfu; othm[3] = rev5(oth5) & 0xfu;
+        const uint32_t own_open = ((wl5 >> 5) & 1u) ^ 1u;
+        const uint32_t cell_is_own = ((h5 >> 5) & 1u) & ((((l5 >> 5) & 1u) ^ ua) ^ 1u);  // layout[y][x] == tag
+
+        int n[4], de[4];
+        uint32_t N32 = 0, DE32 = 0, OWN32 = 0, OTH32 = 0, NB = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            ray_eval(cw[d], lat[d], own_open, n[d], de[d]);
+            const uint32_t vm = (1u << n[d]) - 1u;
+            N32 |= (uint32_t)n[d] << (8 * d);
+            DE32 |= (uint32_t)de[d] << (8 * d);
+            OWN32 |= (uint32_t)__popc(ownm[d] & vm) << (8 * d);
+            OTH32 |= (uint32_t)__popc(othm[d] & vm) << (8 * d);
+            NB |= ((cw[d] & 1u) ^ 1u) << d;
+        }
+        // bounding box of seen cells, update_maze_minmax (maze_agent.py:269,313-328)
+        if (act) {
+            me.miny = min(me.miny, y - n[0]); me.maxx = max(me.maxx, x + n[1]);
+            me.maxy = max(me.maxy, y + n[2]); me.minx = min(me.minx, x - n[3]);
+            me.d2e = d2e_here;
+        }
+
+        // ------------------------------------------------------------ sightings: exit, key, other agent
+        const int ox = __shfl_xor_sync(kFull, pres_x, 1), oy = __shfl_xor_sync(kFull, pres_y, 1), odir = __shfl_xor_sync(kFull, pres_dir, 1);
+        int dE, jE, dK, jK, dO, jO;
+        locate(ex - x, ey - y, dE, jE);
+        locate(kx - x, ky - y, dK, jK);
+        locate(ox - x, oy - y, dO, jO);
+        const uint32_t at_end = jE == 0;
+        const uint32_t visE = jE >= 1 && jE <= (int)((N32 >> (8 * dE)) & 0xffu);
+        const uint32_t visK = keyp && jK >= 1 && jK <= (int)((N32 >> (8 * dK)) & 0xffu);
+        const uint32_t sc = jO == 0;                                           // same cell (live x,y; maze_agent.py:202)
+        const bool in_map = !(pass == 1 && a == 0);                            // agent_positions holds only agent 0 during its reset obs
+        const uint32_t visO = in_map && jO >= 1 && jO <= (int)((N32 >> (8 * dO)) & 0xffu);
+        const int rE = (dE - f) & 3, rK = (dK - f) & 3, rO = (dO - f) & 3;
+
+        // ------------------------------------------------------------ sequential flag logic: obs(agent 0) then obs(agent 1)
+        uint32_t s_ke = 0, s_oke = 0, s_team = 0, s_se = 0, s_vr = 0, s_od = 0;  // values as of this agent's own observation
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            const uint32_t o_ke = __shfl_xor_sync(kFull, a ? pres_ke : me.ke, 1);
+            const uint32_t o_has = __shfl_xor_sync(kFull, a ? pres_has : me.has, 1);
+            uint32_t ke = me.ke, oke = me.oke, team = me.team, time = me.time + 1;  // maze_agent.py:195
+            int olsx = me.olsx, olsy = me.olsy, el = me.exit_len;
+            uint32_t se = at_end, vr = 0, od = 0, share = 0;
+            if (sc) {  // maze_agent.py:202-213
+                time = 0; vr = 0xfu; olsx = ox; olsy = oy; team |= o_has; oke |= o_ke; od = 1u << odir;
+                if (ke && !o_ke) { oke = 1; share = 1; }
+            }
+            const uint32_t ke_before = ke;
+            if (visE) { ke = 1; se = 1; if (el == -1) el = jE; }  // maze_agent.py:227-233
+            if (visO) {                                            // maze_agent.py:239-260
+                time = 0; olsx = ox; olsy = oy; oke |= o_ke; team |= o_has; od |= 1u << odir; vr = 1u << rO;
+                const uint32_t ke_at = ke_before | (visE && (rE < rO || (rE == rO && jE <= 1)));
+                if (jO == 1 && ke_at && !o_ke) { oke = 1; share = 1; }
+            }
+            const bool mine = (a == rnd);
+            if (pass == 1 && rnd == 0) share = 0;  // nothing observed during agent 0's reset obs reaches the (about to be reset) agent 1
+            if (mine && act) {
+                me.ke = ke; me.oke = oke; me.team = team; me.time = time; me.olsx = olsx; me.olsy = olsy; me.exit_len = el;
+                s_ke = ke; s_oke = oke; s_team = team; s_se = se; s_vr = vr; s_od = od;
+            }
+            const uint32_t sh = __shfl_xor_sync(kFull, mine ? share : 0u, 1);
+            if (!mine && sh && act) { me.ke = 1; me.oke = 1; }  // route shared with me: agent.knows_end = agent.other_knows_end = True
+        }
+
+        // next_move_to_exit (maze_agent.py:113-118): exit_route[-1] == dir-to-exit of the current cell
+        const uint32_t nm = (s_ke && !at_end) ? (1u << ((d2e_here - f) & 3)) : 0xfu;
+        // exit_ready (maze.py:100-106): each term sampled right after that agent's own observation
+        const uint32_t term = s_team & s_ke;
+        const uint32_t exit_ready = (pass == 0) ? (term & __shfl_xor_sync(kFull, term, 1)) : 0u;
+
+        // ------------------------------------------------------------ action mask (maze_agent.py:131-139, maze.py:107-113)
+        const uint32_t DEr = __funnelshift_r(DE32, DE32, 8 * f);
+        const uint32_t NBr = rot4r(NB, f);
+        uint32_t mm;
+        if (!s_se && !visK) {
+            mm = ((DEr & 0xffu) == 0) | (((DEr >> 8) & 0xffu) == 0) << 1 | (((DEr >> 16) & 0xffu) == 0) << 2 | ((DEr >> 24) == 0) << 3;
+        } else {
+            mm = NBr;
+        }
+        if (visK) mm = 1u << rK;
+        uint32_t stop = (s_vr != 0) && (x == ex) && (x == ey);  // (self.x, self.x) == maze.end -- sic, maze_agent.py:136
+        if (exit_ready) {
+            if (!at_end) mm = nm & (0u - nm);  // np.argmax of the one-hot / all-ones next_move_to_exit
+            else { mm = 0; stop = 1; }
+        }
+        const uint32_t mask6 = mm | (stop << 4) | ((cell_is_own ^ 1u) << 5);
+
+        if (act) {
+            me.last_mask = mask6;
+            // -------------------------------------------------------- observation vector (maze_agent.py:92-130)
+            float* so = s_obs + tid * kObs;
+            const uint32_t OWNr = __funnelshift_r(OWN32, OWN32, 8 * f), OTHr = __funnelshift_r(OTH32, OTH32, 8 * f);
+            const uint32_t keyr = visK ? (1u << rK) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                so[i] = (f == i) ? 1.f : 0.f;
+                so[4 + i] = 0.25f * (float)((DEr >> (8 * i)) & 0xffu);
+                so[8 + i] = 0.25f * (float)((OWNr >> (8 * i)) & 0xffu);
+                so[12 + i] = 0.25f * (float)((OTHr >> (8 * i)) & 0xffu);
+                so[16 + i] = (float)((s_vr >> i) & 1u);
+                so[20 + i] = (float)((s_od >> i) & 1u);
+                so[24 + i] = (float)((keyr >> i) & 1u);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {  // get_memory: oldest first, one-hot over moves 0..3
+                const uint32_t mv = (me.mem >> (3 * i)) & 7u;
+#pragma unroll
+                for (int q = 0; q < 4; q++) so[28 + 4 * i + q] = (mv == (uint32_t)(q + 1)) ? 1.f : 0.f;
+            }
+            uint32_t lmr = 0;  // get_direction_from(last_mark_pos), maze_agent.py:297-311
+            if (me.mkv) {
+                if (me.lmx == x && me.lmy == y) lmr = 0xfu;
+                else {
+                    const uint32_t ab = (uint32_t)(me.lmy < y) | (uint32_t)(me.lmx > x) << 1 | (uint32_t)(me.lmy > y) << 2 | (uint32_t)(me.lmx < x) << 3;
+                    lmr = rot4r(ab, f);
+                }
+            }
+            const int we = (me.maxx - me.minx) ? (me.maxx - me.minx) : 1, he = (me.maxy - me.miny) ? (me.maxy - me.miny) : 1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { so[44 + i] = (float)((lmr >> i) & 1u); so[53 + i] = (float)((nm >> i) & 1u); }
+            so[48] = fdiv(x - me.minx, we);
+            so[49] = fdiv(me.maxy - y, he);
+            so[50] = fdiv(me.olsx - me.minx, we);
+            so[51] = fdiv(me.maxy - me.olsy, he);
+            so[52] = (float)s_se;
+            so[57] = me.exit_len < 40 ? fdiv(me.exit_len, 40) : 1.f;
+            so[58] = (float)s_oke;
+            so[59] = (float)me.has;
+            so[60] = (float)s_team;
+            so[61] = me.time < 40u ? fdiv((int)me.time, 40) : 1.f;
+            so[62] = fdiv((int)t, p.max_t);
+            so[63] = a ? 0.f : 1.f;
+            so[64] = a ? 1.f : 0.f;
+            uint16_t* mo = reinterpret_cast<uint16_t*>(p.masks) + g * 3;
+            mo[0] = (uint16_t)((mask6 & 1u) | ((mask6 >> 1) & 1u) << 8);
+            mo[1] = (uint16_t)(((mask6 >> 2) & 1u) | ((mask6 >> 3) & 1u) << 8);
+            mo[2] = (uint16_t)(((mask6 >> 4) & 1u) | ((mask6 >> 5) & 1u) << 8);
+            wrote = true;
+        }
+    }
+
+    // ---------------------------------------------------------------- state write-back
+    if (valid && (!kResetOnly || want_reset)) {
+        p.agent_a[g] = pack_agent(me);
+        p.agent_b[g] = me.time;
+        if (a == 0) {
+            p.env_hdr[e] = make_uint4(t, (uint32_t)ex | ((uint32_t)ey << 8) | ((uint32_t)kx << 16) | ((uint32_t)ky << 24),
+                                      keyp | (err << 1) | ((uint32_t)W << 8) | ((uint32_t)Hh << 16), pidx);
+            if (!kResetOnly) { p.reward[e] = reward; p.done[e] = (uint8_t)done; }
+        }
+    }
+
+    // ---------------------------------------------------------------- observations: shared memory -> HBM, coalesced per warp
+    __syncwarp();
+    const uint32_t wmask = __ballot_sync(kFull, wrote);
+    const int wbase = tid & ~31;
+    const long long gbase = g - lane;
+    if (wmask == kFull) {
+        const float4* s4 = reinterpret_cast<const float4*>(s_obs + wbase * kObs);
+        float4* o4 = reinterpret_cast<float4*>(p.obs + gbase * kObs);
+#pragma unroll 4
+        for (int i = lane; i < 32 * kObs / 4; i += 32) __stcs(&o4[i], s4[i]);
+    } else {
+        for (uint32_t m = wmask; m; m &= m - 1) {
+            const int L = __ffs(m) - 1;
+            const float* s = s_obs + (wbase + L) * kObs;
+            float* o = p.obs + (gbase + L) * kObs;
+            for (int i = lane; i < kObs; i += 32) o[i] = s[i];
+        }
+    }
+}
+
+cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream) {
+    const long long agents = 2ll * p.E;
+    const int blocks = (int)((agents + kThreads - 1) / kThreads);
+    const size_t smem = (size_t)kThreads * kObs * sizeof(float);
+    if (blocks == 0) return cudaSuccess;
+    if (reset_only) k_step_obs<true><<<blocks, kThreads, smem, stream>>>(p);
+    else k_step_obs<false><<<blocks, kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace mm

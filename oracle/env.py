@@ -62,6 +62,7 @@ def load_lib():
         "obatch_env": (vp, [vp, i32]),
         "obatch_errors": (i32, [vp]),
         "obatch_random_actions": (None, [vp, pu8, pu8, C.POINTER(C.c_uint64)]),
+        "obatch_guided_actions": (None, [vp, pu8, pu8, C.POINTER(C.c_uint64), i32, i32, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -204,4 +205,11 @@ class OracleBatch:
     def random_actions(self, rng_state: np.ndarray) -> np.ndarray:
         act = np.zeros((self.E, 2, 2), np.uint8)
         self.lib.obatch_random_actions(self.h, _p(self.masks, C.c_uint8), _p(act, C.c_uint8), _p(rng_state, C.c_uint64))
+        return act
+
+    def guided_actions(self, rng_state: np.ndarray, p_follow: float = 0.8, p_mark: float = 0.3) -> np.ndarray:
+        """Test-driver helper (privileged BFS towards key then exit); see maze_oracle.c obatch_guided_actions."""
+        act = np.zeros((self.E, 2, 2), np.uint8)
+        self.lib.obatch_guided_actions(self.h, _p(self.masks, C.c_uint8), _p(act, C.c_uint8), _p(rng_state, C.c_uint64),
+                                       int(p_follow * 1024), int(p_mark * 1024), self.threads)
         return act

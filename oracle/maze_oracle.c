@@ -590,6 +590,7 @@ typedef struct {
 } OPoolMaze;
 typedef struct {
     int E, P; OMaze **envs; OPoolMaze *pool; int *episode; int *maze_idx;
+    int8_t **dkey, **dexit; int *dir_episode; /* guided-action driver cache (test helper, not reference code) */
 } OBatch;
 
 OBatch *obatch_new(int E, int P, int max_timestep) {
@@ -599,12 +600,16 @@ OBatch *obatch_new(int E, int P, int max_timestep) {
     for (int e = 0; e < E; e++) b->envs[e] = omaze_new(max_timestep, 1, 1, 0, 0, 0, 4, 4);
     b->pool = (OPoolMaze *)calloc(P, sizeof(OPoolMaze));
     b->episode = (int *)calloc(E, sizeof(int)); b->maze_idx = (int *)calloc(E, sizeof(int));
+    b->dkey = (int8_t **)calloc(E, sizeof(int8_t *)); b->dexit = (int8_t **)calloc(E, sizeof(int8_t *));
+    b->dir_episode = (int *)calloc(E, sizeof(int));
     return b;
 }
 void obatch_free(OBatch *b) {
     if (!b) return;
     for (int e = 0; e < b->E; e++) omaze_free(b->envs[e]);
     for (int p = 0; p < b->P; p++) free(b->pool[p].layout);
+    for (int e = 0; e < b->E; e++) { free(b->dkey[e]); free(b->dexit[e]); }
+    free(b->dkey); free(b->dexit); free(b->dir_episode);
     free(b->envs); free(b->pool); free(b->episode); free(b->maze_idx); free(b);
 }
 void obatch_set_pool_maze(OBatch *b, int p, int width, int height, const uint8_t *layout, int p0x, int p0y, int p1x, int p1y,
@@ -668,6 +673,52 @@ void obatch_random_actions(const OBatch *b, const uint8_t *masks, uint8_t *actio
             s ^= s << 13; s ^= s >> 7; s ^= s << 17;
             actions[4 * e + 2 * a] = (uint8_t)(n ? legal[(s >> 33) % (uint64_t)n] : 4);
             actions[4 * e + 2 * a + 1] = (uint8_t)(mk[5] ? ((s >> 11) & 1) : 0);
+        }
+        rng_state[e] = s;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Test-driver helper, NOT part of the restated reference: mask-legal actions biased towards the key and then
+ * the exit (privileged BFS over the maze), so that batched parity runs exercise key pickup, route sharing, the
+ * exit_ready mask override and reward-1 terminations.  Mirrors tools/ref_harness.py guided_action in spirit.
+ * ------------------------------------------------------------------------------------------------ */
+static void bfs_dirs(const OMaze *m, int tx, int ty, int8_t *out) {
+    int n = m->width * m->height; int *q = (int *)malloc(sizeof(int) * n); int head = 0, tail = 0;
+    for (int i = 0; i < n; i++) out[i] = -2;
+    out[ty * m->width + tx] = -1; q[tail++] = ty * m->width + tx;
+    while (head < tail) {
+        int c = q[head++], x = c % m->width, y = c / m->width;
+        for (int k = 0; k < 4; k++) {
+            int nx = x + DELTAS[k][0], ny = y + DELTAS[k][1];
+            if (is_valid_cell(m, nx, ny) && LAY(m, nx, ny) != 1 && out[ny * m->width + nx] == -2) { out[ny * m->width + nx] = (int8_t)((k + 2) % 4); q[tail++] = ny * m->width + nx; }
+        }
+    }
+    free(q);
+}
+void obatch_guided_actions(OBatch *b, const uint8_t *masks, uint8_t *actions, uint64_t *rng_state, int p_follow_1024, int p_mark_1024, int threads) {
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+    for (int e = 0; e < b->E; e++) {
+        OMaze *m = b->envs[e];
+        if (!b->dkey[e] || b->dir_episode[e] != b->episode[e]) {
+            b->dkey[e] = (int8_t *)realloc(b->dkey[e], 64 * 64); b->dexit[e] = (int8_t *)realloc(b->dexit[e], 64 * 64);
+            bfs_dirs(m, m->key_x, m->key_y, b->dkey[e]); bfs_dirs(m, m->end_x, m->end_y, b->dexit[e]);
+            b->dir_episode[e] = b->episode[e];
+        }
+        uint64_t s = rng_state[e];
+        for (int a = 0; a < 2; a++) {
+            const uint8_t *mk = masks + (size_t)e * 12 + a * 6; const OAgent *ag = &m->agents[a];
+            int legal[5], n = 0; for (int k = 0; k < 5; k++) if (mk[k]) legal[n++] = k;
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            int move = -1;
+            if ((int)((s >> 40) & 1023) < p_follow_1024) {
+                const int8_t *d = m->key_present ? b->dkey[e] : b->dexit[e];
+                int ad = d[ag->y * m->width + ag->x];
+                if (ad >= 0) { int rel = ((ad - ag->direction) % 4 + 4) % 4; if (mk[rel]) move = rel; }
+            }
+            if (move < 0) move = n ? legal[(s >> 20) % (uint64_t)n] : 4;
+            actions[4 * e + 2 * a] = (uint8_t)move;
+            actions[4 * e + 2 * a + 1] = (uint8_t)(mk[5] ? ((int)((s >> 5) & 1023) < p_mark_1024) : 0);
         }
         rng_state[e] = s;
     }
