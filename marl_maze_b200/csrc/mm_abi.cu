@@ -90,17 +90,18 @@ int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, 
 int mm_reset(const mm_state* st, const uint8_t* reset_mask, float* obs, uint8_t* masks, void* stream) {
     if (!state_ok(st) || !obs || !masks) return MM_ERR_BAD_ARG;
     StepParams p = make_params(st);
-    p.reset_mask = reset_mask; p.obs = obs; p.masks = masks;
+    if (((uintptr_t)obs & 3) || ((uintptr_t)masks & 1)) return MM_ERR_BAD_ARG;
+    p.reset_mask = reset_mask; p.obs = obs; p.masks = masks; p.obs_vec4 = ((uintptr_t)obs & 15) == 0;
     return cuda_status(launch_step_obs(p, true, (cudaStream_t)stream));
 }
 
 int mm_step_obs(const mm_state* st, const uint8_t* actions, float* obs, uint8_t* masks, float* reward, uint8_t* done, int auto_reset,
                 uint64_t action_seed, uint8_t* actions_out, void* stream) {
     if (!state_ok(st) || !obs || !masks || !reward || !done) return MM_ERR_BAD_ARG;
-    if (((uintptr_t)obs & 15) || ((uintptr_t)masks & 1) || ((uintptr_t)actions & 1) || ((uintptr_t)actions_out & 1)) return MM_ERR_BAD_ARG;
+    if (((uintptr_t)obs & 3) || ((uintptr_t)masks & 1) || ((uintptr_t)actions & 1) || ((uintptr_t)actions_out & 1)) return MM_ERR_BAD_ARG;
     StepParams p = make_params(st);
     p.actions = actions; p.actions_out = actions_out; p.obs = obs; p.masks = masks; p.reward = reward; p.done = done;
-    p.auto_reset = auto_reset; p.action_seed = action_seed;
+    p.auto_reset = auto_reset; p.action_seed = action_seed; p.obs_vec4 = ((uintptr_t)obs & 15) == 0;
     return cuda_status(launch_step_obs(p, false, (cudaStream_t)stream));
 }
 

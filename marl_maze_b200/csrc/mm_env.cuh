@@ -37,6 +37,7 @@ struct StepParams {
     float* reward;                         // [E]
     uint8_t* done;                         // [E]
     int E, P, rows, smax, max_t, auto_reset, env_offset;
+    int obs_vec4;                          // obs pointer is 16-byte aligned: whole-warp float4 copy-out allowed
     uint64_t action_seed;
 };
 

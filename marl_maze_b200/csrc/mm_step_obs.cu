@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kThreads) k_step_obs(const StepParams p) {
     const uint32_t wmask = __ballot_sync(kFull, wrote);
     const int wbase = tid & ~31;
     const long long gbase = g - lane;
-    if (wmask == kFull) {
+    if (wmask == kFull && p.obs_vec4) {
         const float4* s4 = reinterpret_cast<const float4*>(s_obs + wbase * kObs);
         float4* o4 = reinterpret_cast<float4*>(p.obs + gbase * kObs);
 #pragma unroll 4
