@@ -88,7 +88,8 @@ int mm_load_layouts(const mm_state *st, int first, int n, const uint8_t *layouts
  * get_shortest_path (maze.py:170-273): randomized DFS carve with the corridor-length bias, exit on the left or
  * right edge (best of `difficulty` candidates), key by rejection sampling off the start->exit path.
  * Random stream: Philox4x32-10 keyed by (seed, maze id = id_base + index) -- see DESIGN.md for the draw mapping.
- * side_lo..side_hi: the maze side is (randint(side_lo, side_hi))*2-1 like rand_range (maze.py:172).
+ * side_lo..side_hi: the maze side is (randint(side_lo, side_hi))*2-1 like rand_range (maze.py:172); side_lo >= 4 (7x7), the
+ * smallest size on which the reference's rejection loops for exit and key are guaranteed to terminate.
  */
 int mm_generate(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
                 uint64_t seed, uint32_t id_base, void *scratch, void *stream);

@@ -80,7 +80,7 @@ int mm_load_layouts(const mm_state* st, int first, int n, const uint8_t* layouts
 
 int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
                 void* scratch, void* stream) {
-    if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 2 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
+    if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 4 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
         (n && !scratch))
         return MM_ERR_BAD_ARG;
     if (n == 0) return MM_OK;

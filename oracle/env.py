@@ -62,6 +62,7 @@ def load_lib():
         "obatch_env": (vp, [vp, i32]),
         "obatch_errors": (i32, [vp]),
         "obatch_random_actions": (None, [vp, pu8, pu8, C.POINTER(C.c_uint64)]),
+        "obatch_run_random": (C.c_long, [vp, i32, i32, u64, pf, pu8, C.POINTER(C.c_double)]),
         "obatch_guided_actions": (None, [vp, pu8, pu8, C.POINTER(C.c_uint64), i32, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -213,3 +214,8 @@ class OracleBatch:
         self.lib.obatch_guided_actions(self.h, _p(self.masks, C.c_uint8), _p(act, C.c_uint8), _p(rng_state, C.c_uint64),
                                        int(p_follow * 1024), int(p_mark * 1024), self.threads)
         return act
+
+    def run_random(self, steps: int, seed: int = 0) -> int:
+        """CPU-baseline driver: `steps` uniform-legal-random steps per env with auto-reset, env-major, OpenMP over envs."""
+        rs = C.c_double()
+        return int(self.lib.obatch_run_random(self.h, int(steps), self.threads, seed, _p(self.obs, C.c_float), _p(self.masks, C.c_uint8), C.byref(rs)))

@@ -209,7 +209,9 @@ static void set_start(OMaze *m) { /* maze.py:229-237 */
 static void set_end(OMaze *m) { /* maze.py:239-250 */
     int coin = rng_randint(&m->rng, 0, 1);
     int x = coin == 0 ? 0 : m->width - 1;
-    for (;;) {
+    for (long tries = 0;; tries++) {
+        /* the reference loops forever on a maze with no eligible cell on that edge; the oracle gives up loudly */
+        if (tries > 1000000) { m->error |= 2; m->end_x = x; m->end_y = 0; break; }
         int y = rng_randint(&m->rng, 0, m->height - 1);
         if (x == m->start_x && y == m->start_y) continue;
         if (LAY(m, x, y) == 0) { m->end_x = x; m->end_y = y; break; }
@@ -247,7 +249,8 @@ static int in_path(const OMaze *m, int x, int y) {
     return 0;
 }
 static void set_key(OMaze *m) { /* maze.py:252-259 */
-    for (;;) {
+    for (long tries = 0;; tries++) {
+        if (tries > 1000000) { m->error |= 4; m->key_x = m->start_x; m->key_y = m->start_y; m->key_present = 1; break; } /* reference: infinite loop */
         int x = rng_randint(&m->rng, 0, m->width - 1), y = rng_randint(&m->rng, 0, m->height - 1);
         if (LAY(m, x, y) == 1 || (x == m->end_x && y == m->end_y) || (x == m->start_x && y == m->start_y) || in_path(m, x, y)) continue;
         m->key_x = x; m->key_y = y; m->key_present = 1; break;
@@ -722,4 +725,34 @@ void obatch_guided_actions(OBatch *b, const uint8_t *masks, uint8_t *actions, ui
         }
         rng_state[e] = s;
     }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU-baseline driver (bench.py cpu_baseline / --impl reference): every env runs `steps` steps of uniform mask-legal
+ * random actions with auto-reset, env-major (each thread keeps one env hot in cache for all its steps -- the best
+ * case for the CPU), OpenMP over envs.  Observations are produced every step exactly as the reference does and
+ * left in the per-env slot of `obs`.  Returns the number of env-steps executed.
+ * ------------------------------------------------------------------------------------------------ */
+long obatch_run_random(OBatch *b, int steps, int threads, uint64_t seed, float *obs, uint8_t *masks, double *reward_sum) {
+    double rs = 0.0;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 8) reduction(+ : rs)
+    for (int e = 0; e < b->E; e++) {
+        uint64_t s = (seed + (uint64_t)e + 1) * 0x9E3779B97F4A7C15ull;
+        float *o = obs + (size_t)e * 2 * OBS_DIM; uint8_t *mk = masks + (size_t)e * 12;
+        for (int t = 0; t < steps; t++) {
+            int act[4];
+            for (int a = 0; a < 2; a++) {
+                int legal[5], n = 0; for (int k = 0; k < 5; k++) if (mk[a * 6 + k]) legal[n++] = k;
+                s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+                act[2 * a] = n ? legal[(s >> 33) % (uint64_t)n] : 4;
+                act[2 * a + 1] = mk[a * 6 + 5] ? (int)((s >> 11) & 1) : 0;
+            }
+            float r; uint8_t d;
+            omaze_step(b->envs[e], act, o, mk, &r, &d);
+            rs += r;
+            if (d) obatch_reset_env(b, e, obs, masks);
+        }
+    }
+    if (reward_sum) *reward_sum = rs;
+    return (long)b->E * steps;
 }

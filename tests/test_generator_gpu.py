@@ -1,0 +1,69 @@
+"""K1 (mm_generate) against the oracle's generator under the same Philox stream, plus structural properties."""
+import numpy as np
+import pytest
+
+from oracle import OracleMaze
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_tree_properties(m):
+    lay = np.asarray(m["layout"]); H, W = lay.shape
+    open_ = lay == 0
+    n_open = int(open_.sum())
+    edges = int((open_[:, :-1] & open_[:, 1:]).sum() + (open_[:-1, :] & open_[1:, :]).sum())
+    assert edges == n_open - 1, "open cells must form a tree (perfect maze)"
+    sx, sy = m["start"]; ex, ey = m["end"]; kx, ky = m["key"]
+    assert sx % 2 == 0 and sy % 2 == 0 and open_[sy, sx]
+    assert ex in (0, W - 1) and open_[ey, ex] and (ex, ey) != (sx, sy)
+    assert open_[ky, kx] and (kx, ky) not in ((sx, sy), (ex, ey))
+    p1 = m["path1"]; assert abs(p1[0] - sx) + abs(p1[1] - sy) == 1 and open_[p1[1], p1[0]]
+
+
+@pytest.mark.parametrize("cfg", [dict(side=(13, 13), rand_start=True, difficulty=1), dict(side=(12, 13), rand_start=True, difficulty=1),
+                                 dict(side=(25, 25), rand_start=True, difficulty=3), dict(side=(4, 9), rand_start=False, difficulty=2),
+                                 dict(side=(27, 27), rand_start=True, difficulty=1)])
+def test_generator_matches_oracle_philox(cfg):
+    from marl_maze_b200 import MazeEngine
+    n = 300
+    smax = cfg["side"][1] * 2 - 1
+    eng = MazeEngine(4, smax=smax, max_timestep=100, pool_size=n)
+    seed, id_base = 0x1234_5678_9ABC_DEF0, 77
+    eng.generate(seed, side_range=cfg["side"], rand_start=cfg["rand_start"], difficulty=cfg["difficulty"], id_base=id_base)
+    o = OracleMaze(max_timestep=10, difficulty=cfg["difficulty"], rand_start=cfg["rand_start"], rand_sizes=True, rand_range=cfg["side"], default_size=(4, 4))
+    for p in list(range(0, 40)) + [n - 1]:
+        g = eng.pool_maze(p)
+        o.seed_philox(seed, id_base + p); o.build(); m = o.maze()
+        assert (g["width"], g["height"]) == (m["width"], m["height"])
+        assert np.array_equal(g["layout"], m["layout"]), f"maze {p} layout"
+        assert g["start"] == m["start"] and g["end"] == m["end"] and g["key"] == m["key"], (p, g["start"], m["start"], g["end"], m["end"], g["key"], m["key"])
+        assert g["path1"] == m["path1"] and g["shortest_path_len"] == m["shortest_path_len"]
+        # dir-to-exit field: following it from every cell of the oracle's path walks that path
+        path = m["path"]
+        for (x, y), (nx, ny) in zip(path[:-1], path[1:]):
+            k = int(g["d2e"][y, x]); assert (x + (k == 1) - (k == 3), y + (k == 2) - (k == 0)) == (nx, ny)
+        _check_tree_properties(g)
+
+
+def test_generated_pool_steps_bit_exact_vs_oracle():
+    """End to end without any injected data: K1 fills the pool, K2 steps it; the oracle generates the same mazes itself."""
+    import torch
+    from marl_maze_b200 import MazeEngine
+    from oracle import OracleBatch
+    E, S, max_t = 512, 25, 150
+    eng = MazeEngine(E, smax=S, max_timestep=max_t, pool_size=2 * E)
+    eng.generate(99, side_range=(12, 13), difficulty=2, id_base=5)
+    ob = OracleBatch(E, 2 * E, max_timestep=max_t, threads=8)
+    o = OracleMaze(max_timestep=10, difficulty=2, rand_start=True, rand_sizes=True, rand_range=(12, 13), default_size=(4, 4))
+    for p in range(2 * E):
+        o.seed_philox(99, 5 + p); o.build(); ob.set_pool_maze(p, o.maze())
+    oo, om = ob.reset_all(); go, gm = eng.reset()
+    assert np.array_equal(go.cpu().numpy().view(np.uint32), oo.view(np.uint32)) and np.array_equal(gm.cpu().numpy(), om)
+    rng = (np.arange(E, dtype=np.uint64) + 3) * np.uint64(0x9E3779B97F4A7C15)
+    for t in range(320):
+        act = ob.guided_actions(rng, p_follow=0.8, p_mark=0.3)
+        go, gm, gr, gd = eng.step(torch.from_numpy(act).to(eng.device))
+        oo, om, orr, od = ob.step(act)
+        assert np.array_equal(go.cpu().numpy().view(np.uint32), oo.view(np.uint32)), t
+        assert np.array_equal(gm.cpu().numpy(), om) and np.array_equal(gr.cpu().numpy(), orr) and np.array_equal(gd.cpu().numpy(), od), t
+    assert np.array_equal(eng.agents(), ob.agents())
