@@ -35,7 +35,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("MARL_MAZE_LIB", _build.LIB)  # override: A/B-testing kernel variants
     if not os.path.exists(path):
         # sources present (a checkout): build in-tree; otherwise fail loudly -- there is no other code path
         try:

@@ -38,12 +38,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in srcs + hdrs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """extra_flags/out: build a kernel variant (e.g. -DMM_K2_MINBLOCKS=6) beside the default library for A/B runs."""
+    LIB = out or globals()["LIB"]
+    if not force and not extra_flags and not needs_build():
         return LIB
     srcs, _ = sources()
     tmp = LIB + f".tmp{os.getpid()}"
-    cmd = [_nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+    cmd = [_nvcc()] + FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
