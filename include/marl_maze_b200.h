@@ -87,12 +87,14 @@ int mm_load_layouts(const mm_state *st, int first, int n, const uint8_t *layouts
  * K1 -- batched maze generator.  Replaces Maze.build_maze/get_neighbors/set_start/set_end/set_key/
  * get_shortest_path (maze.py:170-273): randomized DFS carve with the corridor-length bias, exit on the left or
  * right edge (best of `difficulty` candidates), key by rejection sampling off the start->exit path.
- * Random stream: Philox4x32-10 keyed by (seed, maze id = id_base + index) -- see DESIGN.md for the draw mapping.
+ * Random stream: Philox4x32-10 keyed by (seed, maze id) -- see DESIGN.md for the draw mapping.  maze id of entry i (0-based in
+ * this call) = id_base + i when id_mod == 0, else id_base + (i % id_mod) * id_mul + i / id_mod (pool slot e + k*E -> global
+ * env slot * episodes + k, which keeps ids independent of how envs are sharded over GPUs).
  * side_lo..side_hi: the maze side is (randint(side_lo, side_hi))*2-1 like rand_range (maze.py:172); side_lo >= 4 (7x7), the
  * smallest size on which the reference's rejection loops for exit and key are guaranteed to terminate.
  */
 int mm_generate(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
-                uint64_t seed, uint32_t id_base, void *scratch, void *stream);
+                uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, void *stream);
 
 /*
  * Maze.reset() (maze.py:55-72) + Agent.reset() (maze_agent.py:59-79) for every env with reset_mask[e] != 0
@@ -131,6 +133,28 @@ int mm_unpack_pool(const mm_state *st, int p, uint8_t *out_layout, uint8_t *out_
  */
 int mm_gae(const float *reward, const float *value, const uint8_t *done, const float *v_boot, float *adv, float *rtg,
            int T, int E, double gamma, double lam, void *stream);
+
+/*
+ * K4 -- actor / critic forward over the whole env batch + fused action sampling.  Replaces Actor.forward (with Projection and
+ * m_Attention, networks.py:31-41,58-65,75-82), Critic.forward (networks.py:96-102) and PPO.get_action (PPO.py:170-186).
+ *   weights: one flat fp32 buffer; block offsets (in floats) are returned by mm_policy_offsets (order: proj_w [23][20][4],
+ *            proj_b [23][20], proj_col [23], proj_dim [23], att_k [10][20], att_q [10][20], att_v [20][20], l0_w [264][460], l0_b,
+ *            l1_w [264][264], l1_b, l2_w, l2_b, head_w [6][264] (5 move rows + mark row), head_b [6], c0_w [64][130], c0_b, c1_w
+ *            [64][64], c1_b, c2_w [64], c2_b [1], total).  proj_col[i] is the first obs column projection i reads: 0 for every i
+ *            reproduces the reference's Projection.forward (networks.py:59-63); sum(FEATURE_DIMS[:i]) is the indexed variant.
+ *   obs [E][2][65] f32, masks [E][2][6] u8, scratch: mm_sizeof_policy_scratch(E) bytes.
+ *   actions_in == NULL: sample (Philox keyed by seed, counter, env_offset+env, agent) into actions_out [E][2][2] u8;
+ *   actions_in != NULL: evaluate those actions instead (actions_out unused).
+ *   logp [E] f32 = joint log-prob of both agents' actions (PPO.py:118,121); value [E] f32 (may be NULL); logits_out [E][2][6]
+ *   f32 (may be NULL; 5 move logits + mark logit, unmasked).
+ */
+int mm_policy_offsets(int32_t *out /* [24] */);
+/* critic only: value [E] = Critic(obs [E][2][65]) (networks.py:96-102); used for the bootstrap value V(s_T) */
+int mm_critic_forward(const float *weights, const float *obs, int n_envs, float *value, void *stream);
+size_t mm_sizeof_policy_scratch(int n_envs);
+int mm_policy_forward(const float *weights, const float *obs, const uint8_t *masks, int n_envs, void *scratch, const uint8_t *actions_in,
+                      uint8_t *actions_out, float *logp, float *value, float *logits_out, int env_offset, uint64_t seed, uint64_t counter,
+                      void *stream);
 
 #ifdef __cplusplus
 }

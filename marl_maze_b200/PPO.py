@@ -1,0 +1,259 @@
+"""PPO: the reference's learner surface (PPO.py:11-238) driving the batched CUDA environment.
+
+Same constructor, same methods (train, get_batch, get_action, get_log_probs, get_state_values, get_GAEs, decay_lr,
+save_parameters, load_parameters), same checkpoint format -- a reference `PPO.pth` loads and a checkpoint written
+here loads in the reference.  What changes is how a batch is produced:
+
+  reference get_batch (PPO.py:89-152)  one maze, python loop, whole episodes until > batch_size steps
+  here                                 E mazes in lock-step for a fixed horizon T (T*E > batch_size), every step is
+                                       K4 (actor/critic forward + fused sampling) then K2 (fused env step + obs, with
+                                       in-launch auto-reset), writing straight into the [T+1,E,...] rollout buffers;
+                                       advantages by K3 (reverse scan; episodes still open at T are bootstrapped)
+
+The update (PPO.py:46-85) stays PyTorch autograd over networks.Actor/Critic -- clipped surrogate on the JOINT ratio of
+both agents, MSE critic, grad-norm clip 0.5, two Adams, lr x0.997 per update -- with gradients averaged over ranks
+(NCCL) when torch.distributed is initialised, and advantage statistics taken over all ranks.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .engine import gae as _gae
+from .networks import Actor, Critic
+from .policy import PolicyRunner
+
+MODEL_PATH = "PPO.pth"
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+class PPO:
+    def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
+                 *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
+                 verbose: bool = True, micro_batch: int = 1 << 17):
+        if agent_amount != 2:
+            raise NotImplementedError("two agents (README.md:34)")
+        self.maze = None  # injected by Maze.__init__ (maze.py:40-42)
+        self.device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+        torch.manual_seed(seed)  # PPO.py:7
+        self.actor = Actor([264, 264, 264], faithful_projection=faithful_projection).to(self.device)
+        self.critic = Critic(agent_amount, hidden_sizes=[64, 64]).to(self.device)
+        self.actor_optim = torch.optim.Adam(self.actor.parameters(), lr=lr)
+        self.critic_optim = torch.optim.Adam(self.critic.parameters(), lr=lr)
+        self.epochs, self.batch_size, self.lr, self.discount_rate, self.lam = epochs, batch_size, lr, discount_rate, lam
+        self.updates_per_batch, self.mbatch_size, self.clip, self.max_grad = updates_per_batch, batch_size // 5, clip, max_grad
+        self.horizon, self.seed, self.model_path, self.verbose, self.micro_batch = horizon, seed, model_path, verbose, micro_batch
+        self._runner: Optional[PolicyRunner] = None
+        self._rollouts = 0
+        self.last_stats: dict = {}
+        d = _dist()
+        if d is not None and d.get_world_size() > 1:  # identical initial weights on every rank
+            for p in list(self.actor.parameters()) + list(self.critic.parameters()):
+                d.broadcast(p.data, 0)
+        self.load_parameters()
+
+    # ------------------------------------------------------------------ rollout
+    def _policy(self) -> PolicyRunner:
+        E = self.maze.num_envs
+        if self._runner is None or self._runner.E != E:
+            self._runner = PolicyRunner(self.actor, self.critic, E, self.device, env_offset=self.maze.env_offset, seed=self.seed)
+        return self._runner
+
+    def get_batch(self):
+        """Fixed-horizon vectorised rollout.  Returns the reference's tuple (PPO.py:151-152) flattened t-major:
+        b_obs [N,2,65], b_actions [N,2,2] f32, b_log_probs [N], b_shortest_paths, episode_lens, b_masks [N,2,6] bool, b_advs [N], b_vals [N]."""
+        maze = self.maze
+        E = maze.num_envs
+        T = self.horizon or (self.batch_size // E + 1)  # total_timesteps > batch_size (PPO.py:140)
+        need = max(4, math.ceil(T / 24))                # pool mazes per env so that an env never meets a maze twice in one rollout
+        if maze.engine is not None and maze.pool_episodes < need:
+            maze.engine = None
+        maze.pool_episodes = max(maze.pool_episodes, need)
+        eng = maze._ensure_engine()
+        if self._rollouts > 0 or maze._resets_since_fill > 0:
+            maze.refill_pool()  # the reference builds a new maze for every episode (maze.py:57)
+        dev = self.device
+        obs = torch.empty(T + 1, E, 2, 65, dtype=torch.float32, device=dev)
+        masks = torch.empty(T + 1, E, 2, 6, dtype=torch.uint8, device=dev)
+        actions = torch.empty(T, E, 2, 2, dtype=torch.uint8, device=dev)
+        logp = torch.empty(T, E, dtype=torch.float32, device=dev)
+        values = torch.empty(T + 1, E, dtype=torch.float32, device=dev)
+        reward = torch.empty(T, E, dtype=torch.float32, device=dev)
+        done = torch.empty(T, E, dtype=torch.uint8, device=dev)
+        pol = self._policy()
+        pol.refresh()
+        maze.reset(obs=obs[0], masks=masks[0])  # PPO.py:104
+        for t in range(T):                      # PPO.py:108-141, one iteration = one step of every env
+            pol.forward(obs[t], masks[t], actions_out=actions[t], logp=logp[t], value=values[t])
+            eng.step(actions[t], auto_reset=True, obs=obs[t + 1], masks=masks[t + 1], reward=reward[t], done=done[t])
+        pol.values(obs[T], values[T])  # V(s_T) bootstraps the episodes still open at the horizon
+        adv = _gae(reward, values[:T], done, values[T], self.discount_rate, self.lam)
+        self._rollouts += 1
+        maze._obs, maze._masks = obs[T], masks[T]
+
+        # episode statistics for the progress prints (PPO.py:36-43): lengths of finished episodes and their shortest paths
+        t_idx = torch.arange(1, T + 1, device=dev, dtype=torch.int32).view(T, 1).expand(T, E)
+        d = done.bool()
+        last = torch.where(d, t_idx, torch.zeros_like(t_idx))
+        prev_end = torch.cat([torch.zeros(1, E, dtype=torch.int32, device=dev), torch.cummax(last, 0).values[:-1]], 0)
+        episode_lens = (t_idx - prev_end)[d]
+        k_idx = (torch.cumsum(d.int(), 0) - 1)[d]                       # episode index within the rollout, per finished episode
+        e_idx = torch.arange(E, device=dev).view(1, E).expand(T, E)[d]
+        spl_all = (eng.pool_hdr.view(torch.int32).view(-1, 4)[:, 2] >> 16) & 0xFFFF
+        b_shortest = spl_all[(e_idx + k_idx * E) % eng.P]
+        self.last_stats = dict(env_steps=T * E, episodes=int(d.sum()), solved=int((reward == 1).sum()), keys=int((reward == 0.5).sum()),
+                               mean_reward_per_step=float(reward.mean()), horizon=T, num_envs=E)
+        N = T * E
+        return (obs[:T].reshape(N, 2, 65), actions.reshape(N, 2, 2).float(), logp.reshape(N), b_shortest.cpu().numpy(), episode_lens.cpu().numpy(),
+                masks[:T].reshape(N, 2, 6).bool(), adv.reshape(N), values[:T].reshape(N))
+
+    def get_action(self, obs, action_mask):
+        """One agent's action from ONE observation (PPO.py:170-186) -- the reference's single-env interface, kept for
+        Agent.get_action / viewers.  The batched rollout does not come through here (it uses the fused kernel)."""
+        with torch.no_grad():
+            move_logits, mark_logits = self.actor(obs)
+            mask = torch.as_tensor(action_mask, dtype=torch.bool, device=self.device).reshape(-1)
+            dist = torch.distributions.Categorical(logits=torch.where(mask[:5], move_logits, torch.tensor(-float("inf"), device=self.device)))
+            move = dist.sample()
+            p = torch.sigmoid(mark_logits) if bool(mask[5]) else torch.zeros(1, 1, device=self.device)
+            mark = torch.bernoulli(p)
+            p = p if mark == 1 else 1 - p
+            log_prob = dist.log_prob(move) + torch.log(p)
+        return [int(move.item()), float(mark.item())], log_prob
+
+    # ------------------------------------------------------------------ update-side helpers (autograd)
+    def get_log_probs(self, i, batch_obs, batch_actions, batch_masks):
+        """Log-prob of agent i's recorded actions under the current actor (PPO.py:154-168)."""
+        moves, marks = batch_actions[:, i, 0], batch_actions[:, i, 1]
+        move_logits, mark_logits = self.actor(batch_obs[:, i, :])
+        move_logits = move_logits.masked_fill(~batch_masks[:, i, 0:5], float("-inf"))
+        lp_move = torch.distributions.Categorical(logits=move_logits).log_prob(moves)
+        p = torch.sigmoid(mark_logits.reshape(-1).masked_fill(~batch_masks[:, i, 5], float("-inf")))
+        p = torch.where(marks.bool(), p, 1 - p)
+        return lp_move + torch.log(p)
+
+    def get_state_values(self, batch_obs):
+        return self.critic(batch_obs).squeeze(-1)
+
+    def get_GAEs(self, ep_rew, ep_values, ep_dones):
+        """One complete episode (PPO.py:193-203) through the reverse-scan kernel."""
+        L = len(ep_rew)
+        r = torch.as_tensor(np.asarray(ep_rew, np.float32), device=self.device).view(L, 1).contiguous()
+        v = torch.as_tensor(np.asarray([float(x) for x in ep_values], np.float32), device=self.device).view(L, 1).contiguous()
+        d = torch.as_tensor(np.asarray(ep_dones, np.uint8), device=self.device).view(L, 1).contiguous()
+        return _gae(r, v, d, None, self.discount_rate, self.lam).view(L).cpu().numpy().astype(np.float64)
+
+    def decay_lr(self):  # PPO.py:216-220
+        for opt in (self.actor_optim, self.critic_optim):
+            for g in opt.param_groups:
+                g["lr"] *= 0.997
+
+    # ------------------------------------------------------------------ training
+    def _allreduce_grads(self, module):
+        d = _dist()
+        if d is None or d.get_world_size() == 1:
+            return
+        grads = [p.grad for p in module.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])  # one bucket: 1.06 MB actor / 50 KB critic, latency-bound on NVSwitch
+        d.all_reduce(flat)
+        flat /= d.get_world_size()
+        o = 0
+        for g in grads:
+            g.copy_(flat[o:o + g.numel()].view_as(g)); o += g.numel()
+
+    def _normalise(self, adv):
+        """(adv - mean) / (unbiased std + 1e-10), PPO.py:47, statistics over every rank's samples."""
+        d = _dist()
+        if d is None or d.get_world_size() == 1:
+            return (adv - adv.mean()) / (adv.std() + 1e-10)
+        s = torch.stack([torch.tensor(float(adv.numel()), device=adv.device, dtype=torch.float64), adv.double().sum(), (adv.double() ** 2).sum()])
+        d.all_reduce(s)
+        n, mean = s[0], s[1] / s[0]
+        std = torch.sqrt(torch.clamp(s[2] - n * mean * mean, min=0) / (n - 1))
+        return ((adv - mean.float()) / (std.float() + 1e-10))
+
+    def update(self, batch):
+        """The 5 x 5 minibatch schedule of PPO.train (PPO.py:46-85) on one rollout."""
+        b_obs, b_actions, b_log_probs, _, _, b_masks, b_advs, b_vals = batch
+        N = b_obs.shape[0]
+        b_rtgs = b_advs + b_vals.detach()
+        b_advs = self._normalise(b_advs)
+        g = torch.Generator(device=self.device); g.manual_seed(self.seed + 7919 * self._rollouts)
+        index_list = torch.randperm(N, device=self.device, generator=g)
+        used = min(self.batch_size, N)
+        mb = max(1, self.mbatch_size if self.batch_size <= N else N // 5)
+        stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0)
+        for _ in range(self.updates_per_batch):
+            self.decay_lr()
+            for start in range(0, used, mb):
+                idx = index_list[start:start + mb]
+                n = idx.numel()
+                self.actor_optim.zero_grad(set_to_none=True)
+                a_loss = 0.0
+                for s0 in range(0, n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
+                    j = idx[s0:s0 + self.micro_batch]
+                    m_obs, m_act, m_masks = b_obs[j], b_actions[j], b_masks[j]
+                    cur = self.get_log_probs(0, m_obs, m_act, m_masks) + self.get_log_probs(1, m_obs, m_act, m_masks)
+                    ratio = torch.exp(cur - b_log_probs[j])
+                    adv = b_advs[j]
+                    loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
+                    loss.backward()
+                    a_loss += float(loss.detach())
+                self._allreduce_grads(self.actor)
+                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
+                self.actor_optim.step()
+                self.critic_optim.zero_grad(set_to_none=True)
+                c_loss = 0.0
+                for s0 in range(0, n, self.micro_batch):
+                    j = idx[s0:s0 + self.micro_batch]
+                    loss = ((self.get_state_values(b_obs[j]) - b_rtgs[j]) ** 2).sum() / n
+                    loss.backward()
+                    c_loss += float(loss.detach())
+                self._allreduce_grads(self.critic)
+                torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad)
+                self.critic_optim.step()
+                stats["actor_loss"] += a_loss; stats["critic_loss"] += c_loss; stats["steps"] += 1
+        return stats
+
+    def train(self):
+        d = _dist()
+        rank0 = d is None or d.get_rank() == 0
+        for epoch in range(self.epochs):
+            batch = self.get_batch()
+            episode_lens, b_shortest = batch[4], batch[3]
+            if self.verbose and rank0:
+                print(f"-------------------- Epoch #{epoch} --------------------")
+                print(f"Mazes solved in current epoch: {self.last_stats['solved']} of {len(episode_lens)} finished episodes "
+                      f"({self.last_stats['env_steps']} env-steps on {self.last_stats['num_envs']} mazes)")
+                if len(episode_lens):
+                    print(f"Average Exit Time: {np.mean(episode_lens):.1f}  Best: {np.min(episode_lens)}  Worst: {np.max(episode_lens)}")
+                    print(f"Average Length of Shortest Path: {np.mean(b_shortest):.1f}")
+                print("--------------------------------------------------", flush=True)
+            self.last_update = self.update(batch)
+            if rank0:
+                self.save_parameters()
+
+    # ------------------------------------------------------------------ checkpoint I/O (PPO.py:222-238, same format)
+    def save_parameters(self):
+        if not self.model_path:
+            return
+        torch.save({"actor": self.actor.state_dict(), "critic": self.critic.state_dict(),
+                    "actor_optim": self.actor_optim.state_dict(), "critic_optim": self.critic_optim.state_dict()}, self.model_path)
+
+    def load_parameters(self):
+        if self.model_path and os.path.exists(self.model_path):
+            sd = torch.load(self.model_path, map_location=self.device)
+            self.actor.load_state_dict(sd["actor"]); self.critic.load_state_dict(sd["critic"])
+            self.actor_optim.load_state_dict(sd["actor_optim"]); self.critic_optim.load_state_dict(sd["critic_optim"])
+            if self.verbose:
+                print("successfuly loaded existing parameters")
+            return True
+        return False

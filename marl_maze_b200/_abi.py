@@ -12,6 +12,7 @@ EXPORTS = [
     "mm_sizeof_env_episode", "mm_sizeof_agent_a", "mm_sizeof_agent_b", "mm_sizeof_finalize_scratch", "mm_sizeof_generate_scratch",
     "mm_init_state", "mm_load_layouts", "mm_generate", "mm_reset", "mm_step_obs",
     "mm_unpack_agents", "mm_unpack_envs", "mm_unpack_layout", "mm_unpack_pool", "mm_gae",
+    "mm_policy_offsets", "mm_sizeof_policy_scratch", "mm_policy_forward", "mm_critic_forward",
 ]
 
 
@@ -56,7 +57,7 @@ def lib():
         "mm_sizeof_finalize_scratch": (sz, [i32, i32]), "mm_sizeof_generate_scratch": (sz, [i32, i32]),
         "mm_init_state": (i32, [st, vp]),
         "mm_load_layouts": (i32, [st, i32, i32, vp, vp, vp, vp]),
-        "mm_generate": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, vp, vp]),
+        "mm_generate": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, i32, i32, vp, vp]),
         "mm_reset": (i32, [st, vp, vp, vp, vp]),
         "mm_step_obs": (i32, [st, vp, vp, vp, vp, vp, i32, u64, vp, vp]),
         "mm_unpack_agents": (i32, [st, vp, vp]),
@@ -64,6 +65,10 @@ def lib():
         "mm_unpack_layout": (i32, [st, i32, vp, vp]),
         "mm_unpack_pool": (i32, [st, i32, vp, vp, vp, vp]),
         "mm_gae": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp]),
+        "mm_policy_offsets": (i32, [C.POINTER(C.c_int32)]),
+        "mm_sizeof_policy_scratch": (sz, [i32]),
+        "mm_critic_forward": (i32, [vp, vp, i32, vp, vp]),
+        "mm_policy_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, u64, u64, vp]),
     }
     for name in EXPORTS:
         if not hasattr(L, name):

@@ -7,7 +7,11 @@ namespace mm {
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream);
 cudaError_t launch_gae(const float*, const float*, const uint8_t*, const float*, float*, float*, int, int, double, double, cudaStream_t);
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
-                            uint64_t seed, uint32_t id_base, void* scratch, cudaStream_t stream);
+                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, cudaStream_t stream);
+cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
+                          cudaStream_t);
+int policy_offsets_host(int32_t* out);
+cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream);
 __global__ void k_load_layouts(ulonglong2*, ulonglong2*, uint4*, int, int, int, int, const uint8_t*, const int32_t*, uint16_t*);
 __global__ void k_init_state(uint4*, uint32_t*, uint4*, uint32_t*, int);
 __global__ void k_unpack_agents(const uint4*, const uint32_t*, const uint4*, const ulonglong2*, int, int, int32_t*);
@@ -79,12 +83,12 @@ int mm_load_layouts(const mm_state* st, int first, int n, const uint8_t* layouts
 }
 
 int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
-                void* scratch, void* stream) {
+                int id_mod, int id_mul, void* scratch, void* stream) {
     if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 4 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
-        (n && !scratch))
+        id_mod < 0 || (n && !scratch))
         return MM_ERR_BAD_ARG;
     if (n == 0) return MM_OK;
-    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, scratch, (cudaStream_t)stream));
+    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, (cudaStream_t)stream));
 }
 
 int mm_reset(const mm_state* st, const uint8_t* reset_mask, float* obs, uint8_t* masks, void* stream) {
@@ -136,6 +140,19 @@ int mm_gae(const float* reward, const float* value, const uint8_t* done, const f
            double lam, void* stream) {
     if (!reward || !value || !done || !adv || T < 0 || E < 0) return MM_ERR_BAD_ARG;
     return cuda_status(launch_gae(reward, value, done, v_boot, adv, rtg, T, E, gamma, lam, (cudaStream_t)stream));
+}
+
+int mm_policy_offsets(int32_t* out) { return out ? policy_offsets_host(out) : MM_ERR_BAD_ARG; }
+int mm_critic_forward(const float* weights, const float* obs, int n_envs, float* value, void* stream) {
+    if (!weights || !obs || !value || n_envs <= 0) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_critic(weights, obs, n_envs, value, (cudaStream_t)stream));
+}
+size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (460 + 264 + 264) * sizeof(float); }
+int mm_policy_forward(const float* weights, const float* obs, const uint8_t* masks, int n_envs, void* scratch, const uint8_t* actions_in,
+                      uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter, void* stream) {
+    if (!weights || !obs || !masks || n_envs <= 0 || !scratch || !logp || (!actions_in && !actions_out)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_policy(weights, obs, masks, n_envs, (float*)scratch, actions_in, actions_out, logp, value, logits_out, env_offset, seed,
+                                     counter, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -31,12 +31,14 @@ struct PhiloxStream {
 };
 
 __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglong2* pool_d2e, uint4* pool_hdr, int first, int n, int rows, int smax,
-                                                int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base, uint16_t* scratch) {
+                                                int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base, int id_mod, int id_mul,
+                                                uint16_t* scratch) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int p = first + i;
     uint16_t* q = scratch + (size_t)i * smax * smax;  // DFS stack, then BFS queue
-    PhiloxStream rng; rng.seed(seed, id_base + (uint32_t)i);
+    const uint32_t maze_id = id_mod ? id_base + (uint32_t)(i % id_mod) * (uint32_t)id_mul + (uint32_t)(i / id_mod) : id_base + (uint32_t)i;
+    PhiloxStream rng; rng.seed(seed, maze_id);
 
     unsigned long long open_rows[kMaxSide], seen[kMaxSide], dlo[kMaxSide], dhi[kMaxSide];
     for (int y = 0; y < smax; y++) { open_rows[y] = 0; seen[y] = 0; dlo[y] = 0; dhi[y] = 0; }
@@ -165,13 +167,13 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
     for (int y = 0; y < smax; y++) dd[y] = make_ulonglong2(dlo[y], dhi[y]);
     pool_hdr[p] = make_uint4((uint32_t)W | ((uint32_t)Hh << 8) | ((uint32_t)sx << 16) | ((uint32_t)sy << 24),
                              (uint32_t)p1x | ((uint32_t)p1y << 8) | ((uint32_t)ex << 16) | ((uint32_t)ey << 24),
-                             (uint32_t)kx | ((uint32_t)ky << 8) | ((uint32_t)spl << 16), id_base + (uint32_t)i);
+                             (uint32_t)kx | ((uint32_t)ky << 8) | ((uint32_t)spl << 16), maze_id);
 }
 
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed,
-                            uint32_t id_base, void* scratch, cudaStream_t stream) {
+                            uint32_t id_base, int id_mod, int id_mul, void* scratch, cudaStream_t stream) {
     k_generate<<<(n + 63) / 64, 64, 0, stream>>>((ulonglong2*)st->pool_grid, (ulonglong2*)st->pool_d2e, (uint4*)st->pool_hdr, first, n,
-                                                 st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, (uint16_t*)scratch);
+                                                 st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, (uint16_t*)scratch);
     return cudaGetLastError();
 }
 

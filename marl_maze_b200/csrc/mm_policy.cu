@@ -1,0 +1,264 @@
+// mm_policy.cu -- K4: actor / critic forward over the whole environment batch with action sampling fused behind it.
+//
+// Replaces Actor.forward (+Projection, m_Attention), Critic.forward (networks.py:31-41,58-65,75-82,96-102) and
+// PPO.get_action (PPO.py:170-186) for the rollout.  fp32 throughout (parity bar: 1e-5 relative on logits, values and
+// log-probs, which single-pass bf16/tf32 tensor-core math cannot meet; the error-compensated tcgen05 path is
+// DESIGN.md section 9 "next").  Stages, all on the caller's stream:
+//   k_tokens   : obs [R,65] -> projection (23 tokens x 20) -> self-attention + residual -> x0 [R,460]
+//   k_linear   : Y = relu(X W^T + b), smem-tiled SGEMM (460->264, 264->264, 264->264)
+//   k_heads    : 5 move logits + 1 mark logit, mask, Categorical / Bernoulli sample (Philox) or evaluate given actions,
+//                joint log-prob per env (sum over the two agents, PPO.py:118,121)
+//   k_critic   : centralised critic [E,130] -> 64 -> 64 -> 1
+// Weights arrive as ONE flat fp32 buffer laid out by mm_policy_offsets() (host packs it from the state_dict).
+#include "mm_env.cuh"
+
+namespace mm {
+
+constexpr int kTok = 23, kEmb = 20, kKQ = 10, kX0 = kTok * kEmb;  // 460
+constexpr int kHid = 264, kCH = 64;
+
+// flat weight buffer layout (floats)
+struct PolicyOffsets {
+    int proj_w, proj_b, proj_col, proj_dim;  // [23][20][4], [23][20], [23] (as float), [23] (as float)
+    int att_k, att_q, att_v;                 // [10][20], [10][20], [20][20]
+    int l0_w, l0_b, l1_w, l1_b, l2_w, l2_b;  // [264][460],[264] ; [264][264],[264] x2
+    int head_w, head_b;                      // [6][264] (5 move rows then the mark row), [6]
+    int c0_w, c0_b, c1_w, c1_b, c2_w, c2_b;  // critic [64][130],[64],[64][64],[64],[1][64],[1]
+    int total;
+};
+__host__ __device__ inline PolicyOffsets policy_offsets() {
+    PolicyOffsets o; int p = 0;
+    auto take = [&](int n) { int r = p; p += (n + 3) & ~3; return r; };  // keep every block 16-byte aligned
+    o.proj_w = take(kTok * kEmb * 4); o.proj_b = take(kTok * kEmb); o.proj_col = take(kTok); o.proj_dim = take(kTok);
+    o.att_k = take(kKQ * kEmb); o.att_q = take(kKQ * kEmb); o.att_v = take(kEmb * kEmb);
+    o.l0_w = take(kHid * kX0); o.l0_b = take(kHid); o.l1_w = take(kHid * kHid); o.l1_b = take(kHid); o.l2_w = take(kHid * kHid); o.l2_b = take(kHid);
+    o.head_w = take(6 * kHid); o.head_b = take(6);
+    o.c0_w = take(kCH * 130); o.c0_b = take(kCH); o.c1_w = take(kCH * kCH); o.c1_b = take(kCH); o.c2_w = take(kCH); o.c2_b = take(1);
+    o.total = p;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------ tokens + attention
+// One warp per row.  Everything for a row lives in that warp's shared-memory slice.
+constexpr int kTokWarps = 4;
+__global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int R) {
+    const PolicyOffsets o = policy_offsets();
+    __shared__ float s_tok[kTokWarps][kTok][kEmb + 1], s_k[kTokWarps][kTok][kKQ + 1], s_q[kTokWarps][kTok][kKQ + 1], s_v[kTokWarps][kTok][kEmb + 1];
+    __shared__ float s_p[kTokWarps][kTok][kTok + 1], s_obs[kTokWarps][68];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kTokWarps + w;
+    if (row >= R) return;
+    for (int i = lane; i < kObs; i += 32) s_obs[w][i] = obs[(size_t)row * kObs + i];
+    __syncwarp();
+    for (int i = lane; i < kX0; i += 32) {  // projection: token t, dim d
+        const int t = i / kEmb, d = i - t * kEmb;
+        const int c0 = (int)wts[o.proj_col + t], nd = (int)wts[o.proj_dim + t];
+        float acc = wts[o.proj_b + i];
+        const float* pw = wts + o.proj_w + i * 4;
+        for (int c = 0; c < nd; c++) acc = fmaf(s_obs[w][c0 + c], pw[c], acc);
+        s_tok[w][t][d] = acc;
+    }
+    __syncwarp();
+    for (int i = lane; i < kTok * (2 * kKQ + kEmb); i += 32) {  // K, Q (10 each) and V (20) per token
+        const int t = i / (2 * kKQ + kEmb), j = i - t * (2 * kKQ + kEmb);
+        const float* wr = j < kKQ ? wts + o.att_k + j * kEmb : (j < 2 * kKQ ? wts + o.att_q + (j - kKQ) * kEmb : wts + o.att_v + (j - 2 * kKQ) * kEmb);
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < kEmb; d++) acc = fmaf(s_tok[w][t][d], wr[d], acc);
+        if (j < kKQ) s_k[w][t][j] = acc; else if (j < 2 * kKQ) s_q[w][t][j - kKQ] = acc; else s_v[w][t][j - 2 * kKQ] = acc;
+    }
+    __syncwarp();
+    const float scale = 0.31622776601683794f;  // 1/sqrt(10)
+    for (int i = lane; i < kTok * kTok; i += 32) {
+        const int a = i / kTok, b = i - a * kTok;
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < kKQ; d++) acc = fmaf(s_q[w][a][d], s_k[w][b][d], acc);
+        s_p[w][a][b] = acc * scale;
+    }
+    __syncwarp();
+    if (lane < kTok) {  // softmax over each row of scores
+        float m = -INFINITY;
+        for (int b = 0; b < kTok; b++) m = fmaxf(m, s_p[w][lane][b]);
+        float s = 0.f;
+        for (int b = 0; b < kTok; b++) { const float e = expf(s_p[w][lane][b] - m); s_p[w][lane][b] = e; s += e; }
+        const float inv = 1.f / s;
+        for (int b = 0; b < kTok; b++) s_p[w][lane][b] *= inv;
+    }
+    __syncwarp();
+    for (int i = lane; i < kX0; i += 32) {
+        const int t = i / kEmb, d = i - t * kEmb;
+        float acc = 0.f;
+        for (int b = 0; b < kTok; b++) acc = fmaf(s_p[w][t][b], s_v[w][b][d], acc);
+        x0[(size_t)row * kX0 + i] = s_tok[w][t][d] + acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Y = relu(X W^T + b)
+// 128x64 output tile per block, 256 threads, 8x4 outputs per thread, K in slabs of 16 through shared memory.
+constexpr int BM = 128, BN = 64, BK = 16;
+__global__ void __launch_bounds__(256) k_linear_relu(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                                                     float* __restrict__ Y, int M, int N, int K) {
+    __shared__ float As[BK][BM + 4], Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int tm = (tid >> 4) * 8, tn = (tid & 15) * 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int i = tid; i < BM * BK; i += 256) {  // X tile: consecutive threads walk k (contiguous in memory)
+            const int r = i / BK, c = i - r * BK;
+            const int gm = m0 + r, gk = k0 + c;
+            As[c][r] = (gm < M && gk < K) ? X[(size_t)gm * K + gk] : 0.f;
+        }
+        for (int i = tid; i < BN * BK; i += 256) {
+            const int r = i / BK, c = i - r * BK;
+            const int gn = n0 + r, gk = k0 + c;
+            Bs[c][r] = (gn < N && gk < K) ? W[(size_t)gn * K + gk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            float a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = As[k][tm + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[k][tn + j];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int gm = m0 + tm + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gn = n0 + tn + j;
+            if (gn < N) Y[(size_t)gm * N + gn] = fmaxf(acc[i][j] + bias[gn], 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ heads + sampling
+// One warp per ENV (both agents), lanes split the 264-long dot products; lane 0 finishes the distribution math.
+__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ h, const float* __restrict__ wts, const uint8_t* __restrict__ masks,
+                                               const uint8_t* __restrict__ actions_in, uint8_t* __restrict__ actions_out, float* __restrict__ logp,
+                                               float* __restrict__ logits_out, int E, int env_offset, uint64_t seed, uint64_t counter) {
+    const PolicyOffsets o = policy_offsets();
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= E) return;
+    float lp_env = 0.f;
+    for (int a = 0; a < 2; a++) {
+        const float* hr = h + ((size_t)w * 2 + a) * kHid;
+        float l[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            float acc = 0.f;
+            for (int k = lane; k < kHid; k += 32) acc = fmaf(hr[k], wts[o.head_w + j * kHid + k], acc);
+#pragma unroll
+            for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
+            l[j] = acc + wts[o.head_b + j];
+        }
+        if (lane == 0) {
+            const uint8_t* mk = masks + ((size_t)w * 2 + a) * 6;
+            if (logits_out) for (int j = 0; j < 6; j++) logits_out[((size_t)w * 2 + a) * 6 + j] = l[j];
+            // masked Categorical over the 5 moves (PPO.py:174-176)
+            float m = -INFINITY;
+            for (int j = 0; j < 5; j++) if (mk[j]) m = fmaxf(m, l[j]);
+            float p[5], s = 0.f;
+            for (int j = 0; j < 5; j++) { p[j] = mk[j] ? expf(l[j] - m) : 0.f; s += p[j]; }
+            const float p_mark = mk[5] ? 1.f / (1.f + expf(-l[5])) : 0.f;  // PPO.py:179
+            int move, mark;
+            if (actions_in) { move = actions_in[((size_t)w * 2 + a) * 2]; mark = actions_in[((size_t)w * 2 + a) * 2 + 1]; }
+            else {
+                uint32_t r[4];
+                philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)(env_offset + w) * 2u + (uint32_t)a, 0x504f4c49u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * s;  // inverse CDF over the unnormalised masses
+                float c = 0.f; move = -1; int last = 4;
+                for (int j = 0; j < 5; j++) if (mk[j]) { last = j; c += p[j]; if (move < 0 && u < c) move = j; }
+                if (move < 0) move = last;
+                mark = ((float)(r[1] >> 8) * (1.0f / 16777216.0f) < p_mark) ? 1 : 0;  // torch.bernoulli(p)
+                actions_out[((size_t)w * 2 + a) * 2] = (uint8_t)move; actions_out[((size_t)w * 2 + a) * 2 + 1] = (uint8_t)mark;
+            }
+            const float lp_move = (move < 5 && mk[move]) ? (l[move] - m) - logf(s) : -INFINITY;  // Categorical.log_prob
+            lp_env += lp_move + logf(mark ? p_mark : 1.f - p_mark);                                // PPO.py:181-184
+        }
+    }
+    if (lane == 0) logp[w] = lp_env;
+}
+
+// ------------------------------------------------------------------------------------------------ critic
+// One warp per env: 130 -> 64 -> 64 -> 1, hidden vectors in registers (2 per lane).
+__global__ void __launch_bounds__(128) k_critic(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ value, int E) {
+    const PolicyOffsets o = policy_offsets();
+    __shared__ float s_in[4][132], s_h[4][kCH];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + wl;
+    if (w >= E) return;
+    for (int i = lane; i < 130; i += 32) s_in[wl][i] = obs[(size_t)w * 130 + i];
+    __syncwarp();
+    float h0[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int j = lane + 32 * q;
+        float acc = wts[o.c0_b + j];
+        const float* wr = wts + o.c0_w + j * 130;
+        for (int k = 0; k < 130; k++) acc = fmaf(s_in[wl][k], wr[k], acc);
+        h0[q] = fmaxf(acc, 0.f);
+    }
+    s_h[wl][lane] = h0[0]; s_h[wl][lane + 32] = h0[1];
+    __syncwarp();
+    float part = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int j = lane + 32 * q;
+        float acc = wts[o.c1_b + j];
+        const float* wr = wts + o.c1_w + j * kCH;
+#pragma unroll 8
+        for (int k = 0; k < kCH; k++) acc = fmaf(s_h[wl][k], wr[k], acc);
+        part = fmaf(fmaxf(acc, 0.f), wts[o.c2_w + j], part);
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) part += __shfl_xor_sync(kFull, part, s);
+    if (lane == 0) value[w] = part + wts[o.c2_b];
+}
+
+cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream) {
+    k_critic<<<(E + 3) / 4, 128, 0, stream>>>(obs, wts, value, E);
+    return cudaGetLastError();
+}
+
+int policy_offsets_host(int32_t* out) {
+    const PolicyOffsets o = policy_offsets();
+    const int v[24] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
+                       o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, 0, 0};
+    for (int i = 0; i < 24; i++) out[i] = v[i];
+    return 0;
+}
+
+cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
+                          uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter,
+                          cudaStream_t stream) {
+    const PolicyOffsets o = policy_offsets();
+    const int R = 2 * E;
+    float* x0 = scratch;                      // [R,460]
+    float* h1 = scratch + (size_t)R * kX0;    // [R,264]
+    float* h2 = h1 + (size_t)R * kHid;        // [R,264]
+    k_tokens<<<(R + kTokWarps - 1) / kTokWarps, kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
+    dim3 grid((R + BM - 1) / BM, (kHid + BN - 1) / BN);
+    k_linear_relu<<<grid, 256, 0, stream>>>(x0, wts + o.l0_w, wts + o.l0_b, h1, R, kHid, kX0);
+    k_linear_relu<<<grid, 256, 0, stream>>>(h1, wts + o.l1_w, wts + o.l1_b, h2, R, kHid, kHid);
+    k_linear_relu<<<grid, 256, 0, stream>>>(h2, wts + o.l2_w, wts + o.l2_b, h1, R, kHid, kHid);
+    k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h1, wts, masks, actions_in, actions_out, logp, logits_out, E, env_offset, seed, counter);
+    if (value) k_critic<<<(E + 3) / 4, 128, 0, stream>>>(obs, wts, value, E);
+    return cudaGetLastError();
+}
+
+}  // namespace mm

@@ -18,6 +18,9 @@
 namespace mm {
 
 constexpr int kThreads = 128;
+#ifndef MM_K2_MINBLOCKS
+#define MM_K2_MINBLOCKS 4
+#endif
 
 // One axis ray seen from the agent.  cw: bit j-1 = wall (or out of bounds) at distance j, j = 1..5.
 // latopen: bit j-1 = a cell left or right of the ray cell at distance j is open, j = 1..4.
@@ -50,7 +53,7 @@ __device__ __forceinline__ uint32_t rot4r(uint32_t m, int f) { return ((m | (m <
 __device__ __forceinline__ float fdiv(int a, int b) { return __fdiv_rn((float)a, (float)b); }
 
 template <bool kResetOnly>
-__global__ void __launch_bounds__(kThreads) k_step_obs(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const StepParams p) {
     extern __shared__ __align__(16) float s_obs[];  // [kThreads][65]
     const int tid = threadIdx.x, lane = tid & 31;
     const long long g = (long long)blockIdx.x * kThreads + tid;  // global agent index
@@ -412,6 +415,8 @@ cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t s
     const int blocks = (int)((agents + kThreads - 1) / kThreads);
     const size_t smem = (size_t)kThreads * kObs * sizeof(float);
     if (blocks == 0) return cudaSuccess;
+    // NOTE (measured, profiles/r01_notes.md): forcing the maximum shared-memory carveout halves throughput -- the L1 capacity left
+    // over is what buffers in-flight window loads -- so the driver's default carveout is kept.
     if (reset_only) k_step_obs<true><<<blocks, kThreads, smem, stream>>>(p);
     else k_step_obs<false><<<blocks, kThreads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -107,12 +107,12 @@ class MazeEngine:
             torch.cuda.current_stream(self.device).synchronize()  # d_lay / d_hdr die here
 
     def generate(self, seed: int, side_range=(13, 13), rand_start: bool = True, difficulty: int = 1, first: int = 0,
-                 count: Optional[int] = None, id_base: int = 0):
+                 count: Optional[int] = None, id_base: int = 0, id_mod: int = 0, id_mul: int = 0):
         """K1: fill pool entries [first, first+count) with freshly generated mazes (maze.py:170-273)."""
         n = self.P - first if count is None else count
         scratch = self._get_scratch(self.lib.mm_sizeof_generate_scratch(n, self.smax))
         _abi.check(self.lib.mm_generate(C.byref(self.st), first, n, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
-                                        C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), _ptr(scratch), self._stream()), "mm_generate")
+                                        C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(scratch), self._stream()), "mm_generate")
         self.launches += 1
 
     # ------------------------------------------------------------------ env API

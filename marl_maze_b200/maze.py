@@ -1,0 +1,161 @@
+"""Maze: the reference's environment surface (maze.py:21-163) over the batched CUDA engine.
+
+    brain = PPO(agent_amount=2, ...); agents = (Agent('RED', brain, None, None, 2), Agent('BLUE', brain, None, None, 3))
+    maze = Maze(agents=agents, max_timestep=1200, rand_sizes=True, rand_range=[12, 13], rand_start=True)   # main.py:17-20
+    obs, masks = maze.reset(); obs, masks, reward, done = maze.step([[move, mark], [move, mark]])
+
+With num_envs == 1 the calls take and return python lists exactly like the reference (done is reported, the caller
+resets).  With num_envs > 1 they take/return device tensors ([E,2,2] u8 actions -> obs [E,2,65] f32, masks [E,2,6] u8,
+reward [E] f32, done [E] u8) and finished environments restart inside the same kernel launch (auto_reset).
+Generation (Maze.build_maze, maze.py:170-273) runs on the GPU (K1) into a maze pool; `seed` replaces Python's global
+Mersenne Twister.  The pygame viewer (maze.py:276-522) is out of scope; `render_ascii()` is provided for debugging.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .engine import MazeEngine
+
+DELTAS = [(0, -1), (1, 0), (0, 1), (-1, 0)]  # N, E, S, W
+
+
+class Maze:
+    def __init__(self, agents, max_timestep=3500, difficulty=1, rand_start=False, rand_sizes=False, rand_range=[6, 12], default_size=[8, 8],
+                 num_envs: int = 1, device="cuda", seed: int = 0, pool_episodes: Optional[int] = None, env_offset: int = 0):
+        if len(agents) != 2:
+            raise NotImplementedError("the reference (and the step kernel's lane pairing) is a two-agent game (README.md:34)")
+        if sorted(a.tag for a in agents) != [2, 3] or agents[0].tag != 2:
+            raise ValueError("agents must be tagged (2, 3) in that order (main.py:18-19)")
+        if not rand_sizes and default_size[0] != default_size[1]:
+            raise NotImplementedError("the batched generator builds square mazes; use rand_sizes or a square default_size")
+        self.agents = agents
+        self.max_timestep, self.difficulty, self.rand_start, self.rand_sizes = max_timestep, difficulty, rand_start, rand_sizes
+        self.rand_range, self.default_size = list(rand_range), list(default_size)
+        self.num_envs, self.device, self.seed, self.env_offset = int(num_envs), torch.device(device), int(seed), int(env_offset)
+        self.side_range = (rand_range[0], rand_range[1]) if rand_sizes else (default_size[0], default_size[0])
+        self.pool_episodes = pool_episodes or (64 if self.num_envs == 1 else 4)
+        for i, agent in enumerate(self.agents):  # maze.py:40-42
+            agent.maze = self
+            agent.brain.maze = self
+            agent._index = i
+        self.engine: Optional[MazeEngine] = None
+        self._generation = 0
+        self._resets_since_fill = 0
+        self._obs = self._masks = None
+        self.exit_found = False
+
+    # ------------------------------------------------------------------ engine / pool
+    def _ensure_engine(self):
+        if self.engine is None:
+            smax = self.side_range[1] * 2 - 1
+            self.engine = MazeEngine(self.num_envs, smax=smax, max_timestep=self.max_timestep, pool_size=self.num_envs * self.pool_episodes,
+                                     device=self.device, env_offset=self.env_offset)
+            self.refill_pool()
+        return self.engine
+
+    def refill_pool(self):
+        """Generate a fresh pool (K1).  Only between episodes of ALL envs: a live episode reads its maze's exit field from the pool."""
+        eng = self.engine
+        total = eng.P
+        # maze ids are global and never reused: (generation, global env slot) -> results do not depend on how envs are sharded
+        id_base = (self._generation * (1 << 26) + self.env_offset * self.pool_episodes) & 0xFFFFFFFF
+        eng.generate(self.seed, side_range=self.side_range, rand_start=self.rand_start, difficulty=self.difficulty, id_base=id_base,
+                     id_mod=self.num_envs, id_mul=self.pool_episodes)
+        eng.env_episode.zero_()
+        self._generation += 1
+        self._resets_since_fill = 0
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self, mask: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None):
+        eng = self._ensure_engine()
+        if mask is None:
+            self._resets_since_fill += 1
+            if self._resets_since_fill > self.pool_episodes:
+                self.refill_pool(); self._resets_since_fill = 1
+        self._obs, self._masks = eng.reset(mask, obs=obs, masks=masks)
+        self.exit_found = False
+        return self._emit(self._obs, self._masks)
+
+    def step(self, action, auto_reset: Optional[bool] = None, **out):
+        eng = self._ensure_engine()
+        if self.num_envs == 1 and not torch.is_tensor(action):
+            a = torch.tensor([[int(action[0][0]), int(action[0][1])], [int(action[1][0]), int(action[1][1])]], dtype=torch.uint8).view(1, 2, 2)
+            action = a.to(self.device)
+        auto = (self.num_envs > 1) if auto_reset is None else auto_reset
+        self._obs, self._masks, r, d = eng.step(action, auto_reset=auto, **out)
+        if self.num_envs == 1:
+            o, m = self._emit(self._obs, self._masks)
+            return o, m, float(r.item()), bool(d.item())
+        return self._obs, self._masks, r, d
+
+    def _emit(self, obs, masks):
+        if self.num_envs == 1:
+            return obs[0].tolist(), [[bool(v) for v in row] for row in masks[0].tolist()]
+        return obs, masks
+
+    def is_valid_cell(self, x, y):
+        return 0 <= x < self.width and 0 <= y < self.height
+
+    # ------------------------------------------------------------------ views used by Agent and by callers of the reference attrs
+    def _agent_state(self, agent):
+        return self.engine.agents()[agent.env, agent._index]
+
+    def _last_obs_of(self, agent):
+        o, m = self._obs[agent.env, agent._index], self._masks[agent.env, agent._index]
+        return o.tolist(), [bool(v) for v in m.tolist()]
+
+    def _env_row(self, e=0):
+        return self.engine.envs()[e]
+
+    def _pool(self, e=0):
+        return self.engine.pool_maze(int(self._env_row(e)[3]))
+
+    current_t = property(lambda s: int(s._env_row()[0]))
+    width = property(lambda s: int(s._env_row()[4]) if s.engine is not None else s.side_range[1] * 2 - 1)
+    height = property(lambda s: int(s._env_row()[5]) if s.engine is not None else s.side_range[1] * 2 - 1)
+    start = property(lambda s: s._pool()["start"])
+    end = property(lambda s: s._pool()["end"])
+    shortest_path_len = property(lambda s: s._pool()["shortest_path_len"])
+
+    @property
+    def key(self):  # tuple, or 0 once picked up (maze.py:158)
+        r = self._env_row()
+        return 0 if r[1] < 0 else (int(r[1]), int(r[2]))
+
+    @property
+    def layout(self):
+        return self.engine.layout(0)[:self.height, :self.width].tolist()
+
+    @property
+    def shortest_path(self):
+        """start -> exit path, recovered by following the dir-to-exit field (get_shortest_path, maze.py:261-273)."""
+        m = self._pool()
+        (x, y), path = m["start"], [m["start"]]
+        while (x, y) != m["end"] and len(path) < 4096:
+            dx, dy = DELTAS[int(m["d2e"][y][x])]
+            x, y = x + dx, y + dy
+            path.append((x, y))
+        return path
+
+    @property
+    def agent_positions(self):
+        pos = {}
+        for a in self.agents:
+            pos.setdefault((a.x, a.y), []).append(a)
+        return pos
+
+    def render_ascii(self, e: int = 0) -> str:
+        eng = self.engine
+        row = eng.envs()[e]; W, H = int(row[4]), int(row[5])
+        lay = eng.layout(e)[:H, :W]
+        m = eng.pool_maze(int(row[3])); ag = eng.agents()[e]
+        ch = {0: " ", 1: "#", 2: "r", 3: "b"}
+        g = [[ch[int(v)] for v in r] for r in lay]
+        g[m["end"][1]][m["end"][0]] = "E"
+        if row[1] >= 0:
+            g[int(row[2])][int(row[1])] = "K"
+        for i, c in enumerate("RB"):
+            g[int(ag[i][1])][int(ag[i][0])] = c
+        return "\n".join("".join(r) for r in g)

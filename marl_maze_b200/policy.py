@@ -1,0 +1,97 @@
+"""PolicyRunner: batched actor/critic forward with fused action sampling (K4) for the rollout.
+
+Packs the reference-shaped state_dicts (networks.Actor / networks.Critic) into the flat fp32 buffer the kernels read and
+launches mm_policy_forward.  Used by PPO.get_action / PPO.get_batch; autograd never sees this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+from .networks import FEATURE_DIMS, EMBEDDING_DIM
+
+_NAMES = ["proj_w", "proj_b", "proj_col", "proj_dim", "att_k", "att_q", "att_v", "l0_w", "l0_b", "l1_w", "l1_b", "l2_w", "l2_b",
+          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total"]
+
+
+def offsets() -> dict:
+    out = (C.c_int32 * 24)()
+    _abi.check(_abi.lib().mm_policy_offsets(out), "mm_policy_offsets")
+    return {n: int(out[i]) for i, n in enumerate(_NAMES)}
+
+
+def pack_weights(actor, critic, device=None) -> torch.Tensor:
+    """Flatten actor+critic parameters into the layout of mm_policy_offsets (include/marl_maze_b200.h)."""
+    if tuple(l.out_features for l in actor.layers) != (264, 264, 264) or actor.layers[0].in_features != 460:
+        raise ValueError("the fused policy kernel is built for the reference architecture Actor([264,264,264])")
+    if tuple(l.out_features for l in critic.layers) != (64, 64, 1) or critic.layers[0].in_features != 130:
+        raise ValueError("the fused policy kernel is built for the reference architecture Critic(2, [64,64])")
+    o = offsets()
+    dev = device or actor.move_head.weight.device
+    buf = torch.zeros(o["total"], dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        pw = torch.zeros(len(FEATURE_DIMS), EMBEDDING_DIM, 4, device=dev)
+        col = torch.zeros(len(FEATURE_DIMS), device=dev); dim = torch.zeros(len(FEATURE_DIMS), device=dev)
+        c = 0
+        for i, (lin, d) in enumerate(zip(actor.projection.layers, FEATURE_DIMS)):
+            pw[i, :, :d] = lin.weight
+            col[i] = 0 if actor.projection.faithful else c
+            dim[i] = d
+            c += d
+
+        def put(name, t):
+            t = t.detach().to(dev, torch.float32).reshape(-1)
+            buf[o[name]:o[name] + t.numel()] = t
+        put("proj_w", pw); put("proj_b", torch.cat([l.bias for l in actor.projection.layers])); put("proj_col", col); put("proj_dim", dim)
+        put("att_k", actor.attention.keys.weight); put("att_q", actor.attention.querys.weight); put("att_v", actor.attention.values.weight)
+        for i in range(3):
+            put(f"l{i}_w", actor.layers[i].weight); put(f"l{i}_b", actor.layers[i].bias)
+        put("head_w", torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)); put("head_b", torch.cat([actor.move_head.bias, actor.mark_head.bias]))
+        for i in range(3):
+            put(f"c{i}_w", critic.layers[i].weight); put(f"c{i}_b", critic.layers[i].bias)
+    return buf
+
+
+class PolicyRunner:
+    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0):
+        self.lib = _abi.lib()
+        self.E, self.device, self.env_offset, self.seed = int(num_envs), torch.device(device), int(env_offset), int(seed) & (2**64 - 1)
+        self.actor, self.critic = actor, critic
+        self.weights = pack_weights(actor, critic, self.device)
+        self.scratch = torch.empty(int(self.lib.mm_sizeof_policy_scratch(self.E)), dtype=torch.uint8, device=self.device)
+        self.counter = 0
+        self.launches = 0
+
+    def refresh(self):
+        """Re-pack after an optimiser step."""
+        self.weights = pack_weights(self.actor, self.critic, self.device)
+
+    def values(self, obs: torch.Tensor, value: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Critic only (bootstrap value of the state after the last rollout step)."""
+        E = obs.shape[0]
+        value = torch.empty(E, dtype=torch.float32, device=self.device) if value is None else value
+        _abi.check(self.lib.mm_critic_forward(C.c_void_p(self.weights.data_ptr()), C.c_void_p(obs.data_ptr()), E, C.c_void_p(value.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_critic_forward")
+        self.launches += 1
+        return value
+
+    def forward(self, obs: torch.Tensor, masks: torch.Tensor, actions_in: Optional[torch.Tensor] = None, actions_out: Optional[torch.Tensor] = None,
+                logp: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None, want_value: bool = True):
+        """Sample (actions_in None) or evaluate actions for all envs.  Returns (actions [E,2,2] u8, joint logp [E], value [E] | None)."""
+        E = obs.shape[0]
+        assert E <= self.E and obs.is_contiguous() and masks.is_contiguous() and obs.dtype == torch.float32 and masks.dtype == torch.uint8
+        if actions_in is None and actions_out is None:
+            actions_out = torch.empty(E, 2, 2, dtype=torch.uint8, device=self.device)
+        logp = torch.empty(E, dtype=torch.float32, device=self.device) if logp is None else logp
+        if want_value and value is None:
+            value = torch.empty(E, dtype=torch.float32, device=self.device)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        self.counter += 1
+        _abi.check(self.lib.mm_policy_forward(p(self.weights), p(obs), p(masks), E, p(self.scratch), p(actions_in), p(actions_out), p(logp),
+                                              p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(self.counter),
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
+        self.launches += 6 if want_value else 5
+        return (actions_in if actions_in is not None else actions_out), logp, (value if want_value else None)

@@ -1,0 +1,89 @@
+"""K4 (fused actor/critic forward + sampling) against the numpy oracle restatement of networks.py / PPO.get_action and the
+recorded reference outputs.  Tolerance: 1e-5 relative (+2e-6 absolute) on logits, values and log-probs -- fp32 with re-associated sums."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import GOLDEN
+from oracle import ppo_oracle as po
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-5, atol=2e-6)
+
+
+def _nets(seed, faithful=True):
+    from marl_maze_b200.networks import Actor, Critic
+    asd, csd = po.seeded_state_dicts(seed)
+    actor = Actor([264, 264, 264], faithful_projection=faithful).cuda(); critic = Critic(2, hidden_sizes=[64, 64]).cuda()
+    actor.load_state_dict({k: torch.from_numpy(v) for k, v in asd.items()}); critic.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+    return actor, critic, asd, csd
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_policy_kernel_vs_reference_golden(seed):
+    from marl_maze_b200.policy import PolicyRunner
+    Z = np.load(os.path.join(GOLDEN, "ppo_kats.npz"))
+    obs, masks, acts = Z["net/obs"], Z["net/masks"], Z["net/actions"]
+    actor, critic, _, _ = _nets(seed)
+    E = obs.shape[0]
+    run = PolicyRunner(actor, critic, E, "cuda")
+    logits = torch.zeros(E, 2, 6, device="cuda")
+    _, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), actions_in=torch.from_numpy(acts).cuda(), logits=logits)
+    lg = logits.cpu().numpy()
+    assert np.allclose(lg[:, :, :5].reshape(-1, 5), Z[f"net/{seed}/move_logits"], **TOL)
+    assert np.allclose(lg[:, :, 5].reshape(-1, 1), Z[f"net/{seed}/mark_logits"], **TOL)
+    assert np.allclose(val.cpu().numpy(), Z[f"net/{seed}/values"].reshape(-1), **TOL)
+    want = Z[f"net/{seed}/log_probs"].sum(1)  # joint log-prob, PPO.py:118,121
+    fin = np.isfinite(want)
+    got = logp.cpu().numpy()
+    assert np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], want[fin], **TOL)
+
+
+@pytest.mark.parametrize("faithful", [True, False])
+def test_policy_kernel_vs_oracle_random_obs_and_sampling(faithful):
+    from marl_maze_b200.policy import PolicyRunner
+    actor, critic, asd, csd = _nets(5, faithful)
+    rng = np.random.default_rng(3)
+    E = 3000
+    obs = rng.random((E, 2, 65)).astype(np.float32)
+    masks = (rng.random((E, 2, 6)) < 0.6).astype(np.uint8); masks[:, :, 0] |= (masks[:, :, :5].sum(-1) == 0).astype(np.uint8)
+    run = PolicyRunner(actor, critic, E, "cuda", seed=9)
+    logits = torch.zeros(E, 2, 6, device="cuda")
+    act, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), logits=logits)
+    act = act.cpu().numpy()
+    mv, mk = po.actor_forward(asd, obs.reshape(-1, 65), faithful=faithful)
+    assert np.allclose(logits.cpu().numpy()[:, :, :5].reshape(-1, 5), mv, **TOL) and np.allclose(logits.cpu().numpy()[:, :, 5].reshape(-1, 1), mk, **TOL)
+    assert np.allclose(val.cpu().numpy(), po.critic_forward(csd, obs).reshape(-1), **TOL)
+    # sampled actions are mask-legal and their log-prob is the oracle's
+    assert np.take_along_axis(masks[:, :, :5], act[:, :, :1].astype(np.int64), 2).all() and (act[:, :, 1] <= masks[:, :, 5]).all()
+    lp = sum(po.action_log_prob(mv.reshape(E, 2, 5)[:, i], mk.reshape(E, 2)[:, i], masks[:, i], act[:, i, 0], act[:, i, 1]) for i in range(2))
+    assert np.allclose(logp.cpu().numpy(), lp, **TOL)
+    # a second call draws different actions (counter advances); evaluating recorded actions reproduces the log-prob
+    act2, _, _ = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda())
+    assert (act2.cpu().numpy() != act).any()
+    _, lp_eval, _ = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), actions_in=torch.from_numpy(act).cuda())
+    assert torch.equal(lp_eval, logp)
+
+
+def test_sampling_distribution_chi_square():
+    """Fused sampler follows the masked softmax / Bernoulli(sigmoid) distribution (chi-square, fixed seed)."""
+    from marl_maze_b200.policy import PolicyRunner
+    actor, critic, asd, _ = _nets(21)
+    E = 1 << 17
+    obs = np.zeros((E, 2, 65), np.float32); obs[:, :, 1] = 1.0   # every row identical: facing east
+    masks = np.tile(np.array([1, 1, 0, 1, 0, 1], np.uint8), (E, 2, 1))
+    run = PolicyRunner(actor, critic, E, "cuda", seed=1)
+    act, _, _ = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda())
+    act = act.cpu().numpy().reshape(-1, 2)
+    mv, mk = po.actor_forward(asd, obs[:1, 0])
+    l = np.where(masks[0, 0, :5] == 1, mv[0].astype(np.float64), -np.inf); p = np.exp(l - l.max()); p /= p.sum()
+    n = len(act)
+    cnt = np.bincount(act[:, 0], minlength=5)
+    assert cnt[2] == 0 and cnt[4] == 0
+    chi = sum((cnt[j] - n * p[j]) ** 2 / (n * p[j]) for j in (0, 1, 3))
+    assert chi < 20.0, (chi, cnt, p)          # 2 dof; p(chi2 > 20) ~ 5e-5
+    pm = 1 / (1 + np.exp(-float(mk[0, 0])))
+    z = (act[:, 1].mean() - pm) / np.sqrt(pm * (1 - pm) / n)
+    assert abs(z) < 4.5, (z, pm)

@@ -1,0 +1,100 @@
+"""The reference's class surface end to end on the GPU: Maze / Agent / PPO wiring of main.py, list semantics at one env,
+batched rollout + GAE + update, checkpoint round trip."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(num_envs, tmp_path, batch_size=600, **kw):
+    from marl_maze_b200.PPO import PPO
+    from marl_maze_b200.maze import Maze
+    from marl_maze_b200.maze_agent import Agent
+    brain = PPO(agent_amount=2, batch_size=batch_size, lr=0.00014, epochs=1, verbose=False, model_path=str(tmp_path / "PPO.pth"), **kw)
+    agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
+    maze = Maze(agents=agents, max_timestep=120, rand_sizes=True, rand_range=[12, 13], rand_start=True, difficulty=1, default_size=[4, 4],
+                num_envs=num_envs, seed=5)  # main.py:17-20
+    return brain, agents, maze
+
+
+def test_single_env_list_semantics_match_oracle(tmp_path):
+    """E=1: reset()/step() take and return python lists like the reference; values equal the oracle's on the same maze."""
+    from oracle import OracleMaze
+    brain, agents, maze = _make(1, tmp_path)
+    assert brain.maze is maze and agents[0].maze is maze
+    obs, masks = maze.reset()
+    assert isinstance(obs, list) and len(obs) == 2 and len(obs[0]) == 65 and isinstance(masks[0][0], bool)
+    o = OracleMaze(max_timestep=120)
+    m = maze.engine.pool_maze(int(maze.engine.envs()[0, 3]))
+    oo, om = o.reset_injected(m)
+    assert np.array_equal(np.asarray(obs, np.float32), oo) and np.array_equal(np.asarray(masks, np.uint8), om)
+    assert (agents[0].x, agents[0].y) == m["path0"] and (agents[1].x, agents[1].y) == m["path1"] and agents[0].direction == 2
+    assert maze.shortest_path[0] == m["start"] and maze.shortest_path[-1] == m["end"] and len(maze.shortest_path) == maze.shortest_path_len
+    rng = np.random.default_rng(0)
+    for t in range(150):
+        act = [[int(rng.choice([k for k in range(5) if masks[i][k]])), int(rng.integers(0, 2)) if masks[i][5] else 0] for i in range(2)]
+        obs, masks, r, d = maze.step(act)
+        oo, om, orr, od = o.step(np.asarray(act).reshape(4))
+        assert np.array_equal(np.asarray(obs, np.float32), oo) and np.array_equal(np.asarray(masks, np.uint8), om) and r == orr and d == od
+        assert maze.current_t == t % 120 + 1
+        if d:
+            obs, masks = maze.reset()
+            oo, om = o.reset_injected(maze.engine.pool_maze(int(maze.engine.envs()[0, 3])))
+            assert np.array_equal(np.asarray(obs, np.float32), oo)
+    a, p = agents[0].get_action(obs[0], masks[0])
+    assert masks[0][a[0]] and 0 < p <= 1
+    assert "R" in maze.render_ascii() and "E" in maze.render_ascii()
+
+
+def test_batched_rollout_gae_and_update(tmp_path):
+    from oracle import ppo_oracle as po
+    brain, agents, maze = _make(256, tmp_path, batch_size=256 * 40 - 1, horizon=40)
+    b_obs, b_act, b_logp, b_sp, ep_lens, b_masks, b_advs, b_vals = brain.get_batch()
+    N = 256 * 40
+    assert b_obs.shape == (N, 2, 65) and b_act.shape == (N, 2, 2) and b_logp.shape == (N,) and b_masks.dtype == torch.bool and b_advs.shape == (N,)
+    # recorded actions are legal under the recorded masks, and the recorded joint log-prob is what the autograd path computes
+    legal = torch.gather(b_masks[:, :, :5], 2, b_act[:, :, :1].long())
+    assert legal.all() and (b_act[:, :, 1] <= b_masks[:, :, 5].float()).all()
+    with torch.no_grad():
+        lp = brain.get_log_probs(0, b_obs, b_act, b_masks) + brain.get_log_probs(1, b_obs, b_act, b_masks)
+        v = brain.get_state_values(b_obs)
+    assert torch.allclose(lp, b_logp, rtol=1e-5, atol=2e-6) and torch.allclose(v, b_vals, rtol=1e-5, atol=2e-6)
+    assert len(ep_lens) == len(b_sp) == brain.last_stats["episodes"]
+    before = [p.detach().clone() for p in brain.actor.parameters()]
+    stats = brain.update((b_obs, b_act, b_logp, b_sp, ep_lens, b_masks, b_advs, b_vals))
+    assert stats["steps"] == 25 and np.isfinite(stats["actor_loss"]) and np.isfinite(stats["critic_loss"])
+    assert any((a != b).any() for a, b in zip(before, brain.actor.parameters()))
+    assert abs(brain.actor_optim.param_groups[0]["lr"] - 0.00014 * 0.997 ** 5) < 1e-12
+
+
+def test_train_epoch_and_checkpoint_round_trip(tmp_path):
+    brain, agents, maze = _make(64, tmp_path, batch_size=64 * 30 - 1, horizon=30)
+    brain.epochs = 2
+    brain.train()
+    path = tmp_path / "PPO.pth"
+    assert path.exists()
+    sd = torch.load(path, map_location="cpu")
+    assert set(sd) == {"actor", "critic", "actor_optim", "critic_optim"} and "projection.layers.22.weight" in sd["actor"] and "layers.2.bias" in sd["critic"]
+    brain2, _, _ = _make(64, tmp_path, batch_size=64 * 30 - 1, horizon=30)  # loads the file in __init__ (PPO.py:31)
+    for a, b in zip(brain.actor.parameters(), brain2.actor.parameters()):
+        assert torch.equal(a, b)
+    assert brain2.actor_optim.param_groups[0]["lr"] == brain.actor_optim.param_groups[0]["lr"]
+
+
+def test_reference_checkpoint_drives_the_kernel_policy(tmp_path):
+    """Config 1 flavour: the shipped PPO.pth (when present) through the fused policy kernel on one maze."""
+    src = "/root/reference/PPO.pth"
+    if not os.path.exists(src):
+        pytest.skip("reference checkpoint not on this box")
+    import shutil
+    shutil.copy(src, tmp_path / "PPO.pth")
+    brain, agents, maze = _make(1, tmp_path)
+    obs, masks = maze.reset()
+    for _ in range(50):
+        acts = [agents[i].get_action(obs[i], masks[i])[0] for i in range(2)]
+        obs, masks, r, d = maze.step(acts)
+        if d:
+            obs, masks = maze.reset()

@@ -1,0 +1,82 @@
+"""oracle/ppo_oracle.py (numpy restatement of PPO.get_GAEs, Actor/Critic forward, action log-probs) and the product's
+torch networks against known answers recorded from the reference's own PPO.py / networks.py (tests/golden/ppo_kats.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import GOLDEN
+from oracle import ppo_oracle as po
+
+Z = np.load(os.path.join(GOLDEN, "ppo_kats.npz"))
+
+
+def test_gae_oracle_bit_exact_vs_reference():
+    for k in range(int(Z["gae/n"])):
+        rew, val, adv = Z[f"gae/{k}/rew"], Z[f"gae/{k}/val"], Z[f"gae/{k}/adv"]
+        dones = [False] * (len(rew) - 1) + [True]
+        got = po.get_gaes(rew, val, dones)
+        assert np.array_equal(got.view(np.uint32), adv.view(np.uint32)), (k, np.abs(got - adv).max())
+
+
+def test_gae_kat4():
+    got = po.get_gaes([0, .5, 0, 1], np.full(4, 0.1, np.float32), [False, False, False, True])
+    assert np.array_equal(got, Z["gae/kat4"])
+    assert np.allclose(got, [1.12857449, 1.20103621, 0.74644995, 0.89999998], rtol=0, atol=1e-7)  # SURVEY 8c KAT(4)
+
+
+def test_gae_fixed_horizon_equals_per_episode():
+    rng = np.random.default_rng(0)
+    T, E = 64, 9
+    rew = rng.choice([0.0, 0.5, 1.0], size=(T, E)).astype(np.float32); val = rng.standard_normal((T, E)).astype(np.float32)
+    done = (rng.random((T, E)) < 0.08); done[-1, ::2] = True
+    vb = rng.standard_normal(E).astype(np.float32)
+    adv = po.gae_fixed_horizon(rew, val, done, vb)
+    e = 0
+    cuts = [-1] + [t for t in range(T) if done[t, e]]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        assert np.array_equal(adv[a + 1:b + 1, e], po.get_gaes(rew[a + 1:b + 1, e], val[a + 1:b + 1, e], done[a + 1:b + 1, e]))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_network_oracle_and_torch_modules_vs_reference(seed):
+    """tolerance: 1e-5 relative (north_star) on logits / values / log-probs; reductions are re-associated, nothing else differs."""
+    from marl_maze_b200.networks import Actor, Critic
+    asd, csd = po.seeded_state_dicts(seed)
+    obs, masks, acts = Z["net/obs"], Z["net/masks"], Z["net/actions"]
+    mv_ref, mk_ref, v_ref, lp_ref = (Z[f"net/{seed}/{k}"] for k in ("move_logits", "mark_logits", "values", "log_probs"))
+    mv, mk = po.actor_forward(asd, obs.reshape(-1, 65)); v = po.critic_forward(csd, obs)
+    tol = dict(rtol=1e-5, atol=2e-6)
+    assert np.allclose(mv, mv_ref, **tol) and np.allclose(mk, mk_ref, **tol) and np.allclose(v, v_ref, **tol)
+    lp = np.stack([po.action_log_prob(mv.reshape(-1, 2, 5)[:, i], mk.reshape(-1, 2)[:, i], masks[:, i], acts[:, i, 0], acts[:, i, 1]) for i in range(2)], 1)
+    fin = np.isfinite(lp_ref)
+    assert np.array_equal(np.isfinite(lp), fin) and np.allclose(lp[fin], lp_ref[fin], rtol=1e-5, atol=2e-6)
+    actor = Actor([264, 264, 264]); critic = Critic(2, hidden_sizes=[64, 64])
+    actor.load_state_dict({k: torch.from_numpy(x) for k, x in asd.items()}); critic.load_state_dict({k: torch.from_numpy(x) for k, x in csd.items()})
+    with torch.no_grad():
+        tmv, tmk = actor(torch.from_numpy(obs.reshape(-1, 65))); tv = critic(torch.from_numpy(obs))
+    assert np.allclose(tmv.numpy(), mv_ref, **tol) and np.allclose(tmk.numpy(), mk_ref, **tol) and np.allclose(tv.numpy(), v_ref, **tol)
+    # the faithful actor is a function of obs[:, 0:4] only (Projection never advances its index, networks.py:59-63)
+    obs2 = obs.reshape(-1, 65).copy(); obs2[:, 4:] = 0.123
+    with torch.no_grad():
+        assert torch.allclose(actor(torch.from_numpy(obs2))[0], tmv, atol=1e-6)
+    indexed = Actor([264, 264, 264], faithful_projection=False); indexed.load_state_dict(actor.state_dict())
+    with torch.no_grad():
+        assert not torch.allclose(indexed(torch.from_numpy(obs2))[0], indexed(torch.from_numpy(obs.reshape(-1, 65)))[0], atol=1e-4)
+
+
+def test_reference_checkpoint_loads_and_matches_kat5():
+    """SURVEY 8c KAT(5): PPO.pth actor on the 4 facing one-hots.  Only where the reference checkout is mounted."""
+    path = "/root/reference/PPO.pth"
+    if not os.path.exists(path):
+        pytest.skip("reference checkpoint not present on this box")
+    from marl_maze_b200.networks import Actor, Critic
+    sd = torch.load(path, map_location="cpu")
+    actor = Actor([264, 264, 264]); critic = Critic(2, hidden_sizes=[64, 64])
+    actor.load_state_dict(sd["actor"]); critic.load_state_dict(sd["critic"])
+    x = torch.zeros(4, 65); x[torch.arange(4), torch.arange(4)] = 1
+    with torch.no_grad():
+        mv, mk = actor(x)
+    assert np.allclose(mv[0].numpy(), [5.7483, -0.3037, -7.4898, 10.1972, -9.9180], atol=2e-4)
+    assert np.allclose(torch.sigmoid(mk).reshape(-1).numpy(), [.5609, .5664, .5459, .5300], atol=2e-4)

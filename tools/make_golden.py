@@ -142,5 +142,65 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--ppo" not in sys.argv:
     main()
+
+
+def make_ppo_kats():
+    """GAE and network known answers from the reference's own PPO.py / networks.py (torch CPU)."""
+    import contextlib, io, random
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import ppo_oracle as po
+    rh.load_reference()
+    sys.path.insert(0, rh.REFERENCE_DIR)
+    cwd = os.getcwd(); os.chdir("/tmp")  # PPO.__init__ would load ./PPO.pth (PPO.py:229-238): stay away from it
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import PPO as ref_ppo, networks as ref_net
+    finally:
+        os.chdir(cwd); sys.path.remove(rh.REFERENCE_DIR)
+    out = {}
+
+    class Dummy:
+        discount_rate = 0.99; lam = 0.95
+    rng = np.random.default_rng(42)
+    lens = [1, 2, 3, 4, 7, 33, 200, 1200]
+    for k, L in enumerate(lens):
+        rew = [0.0] * L
+        for _ in range(min(2, L)):
+            rew[int(rng.integers(0, L))] = 0.5
+        rew[-1] = 1 if (k % 2 == 0 and L > 1) else 0.0  # maze.py:118 sets the int 1; an all-int list (1-step success) is unreachable
+        vals = rng.standard_normal(L).astype(np.float32)
+        dones = [False] * (L - 1) + [True]
+        with contextlib.redirect_stdout(io.StringIO()):
+            adv = ref_ppo.PPO.get_GAEs(Dummy(), list(rew), [torch.tensor([[v]], dtype=torch.float32) for v in vals], dones)
+        out[f"gae/{k}/rew"] = np.asarray(rew, np.float32); out[f"gae/{k}/val"] = vals; out[f"gae/{k}/adv"] = np.asarray(adv, np.float32)
+    out["gae/n"] = np.int32(len(lens))
+    # SURVEY 8c KAT(4)
+    adv = ref_ppo.PPO.get_GAEs(Dummy(), [0, .5, 0, 1], [torch.tensor([[0.1]])] * 4, [False, False, False, True])
+    out["gae/kat4"] = np.asarray(adv, np.float32)
+
+    # networks: seeded weights with the reference's names/shapes, real observations from a recorded trace
+    z = np.load(os.path.join(OUT, "env_traces.npz"))
+    obs = z["guided_a/step_obs"][:192]            # [192,2,65]
+    masks = z["guided_a/step_masks"][:192].astype(bool)
+    acts = z["guided_a/actions"][1:193]           # the actions taken FROM those observations
+    for seed in (11, 12):
+        asd, csd = po.seeded_state_dicts(seed)
+        actor = ref_net.Actor([264, 264, 264]); critic = ref_net.Critic(2, hidden_sizes=[64, 64])
+        actor.load_state_dict({k: torch.from_numpy(v) for k, v in asd.items()}); critic.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+        with torch.no_grad():
+            mv, mk = actor(torch.from_numpy(obs.reshape(-1, 65)))
+            val = critic(torch.from_numpy(obs))
+            holder = Dummy(); holder.actor = actor
+            lps = [ref_ppo.PPO.get_log_probs(holder, i, torch.from_numpy(obs), torch.from_numpy(acts.astype(np.float32)), torch.from_numpy(masks)).numpy() for i in range(2)]
+        out[f"net/{seed}/move_logits"] = mv.numpy(); out[f"net/{seed}/mark_logits"] = mk.numpy(); out[f"net/{seed}/values"] = val.numpy()
+        out[f"net/{seed}/log_probs"] = np.stack(lps, 1)
+    out["net/obs"] = obs; out["net/masks"] = masks.astype(np.uint8); out["net/actions"] = acts
+    np.savez_compressed(os.path.join(OUT, "ppo_kats.npz"), **out)
+    print("ppo_kats.npz", os.path.getsize(os.path.join(OUT, "ppo_kats.npz")))
+
+
+if __name__ == "__main__" and "--ppo" in sys.argv:
+    make_ppo_kats()
