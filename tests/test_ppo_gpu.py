@@ -51,7 +51,7 @@ def test_single_env_list_semantics_match_oracle(tmp_path):
 
 def test_batched_rollout_gae_and_update(tmp_path):
     from oracle import ppo_oracle as po
-    brain, agents, maze = _make(256, tmp_path, batch_size=256 * 40 - 1, horizon=40)
+    brain, agents, maze = _make(256, tmp_path, batch_size=10000, horizon=40)
     b_obs, b_act, b_logp, b_sp, ep_lens, b_masks, b_advs, b_vals = brain.get_batch()
     N = 256 * 40
     assert b_obs.shape == (N, 2, 65) and b_act.shape == (N, 2, 2) and b_logp.shape == (N,) and b_masks.dtype == torch.bool and b_advs.shape == (N,)
