@@ -125,6 +125,10 @@ int mm_unpack_layout(const mm_state *st, int env, uint8_t *out, void *stream);
 /* byte layout + dir-to-exit of pool maze p: out_layout [smax][smax] u8, out_d2e [smax][smax] u8, out_hdr [11] i32 */
 int mm_unpack_pool(const mm_state *st, int p, uint8_t *out_layout, uint8_t *out_d2e, int32_t *out_hdr, void *stream);
 
+/* Self-test: counts (into *mismatches, a zeroed device u64) the pairs a in [-amax, amax], b in [1, bmax] for which K2's
+ * reciprocal-based integer division differs from IEEE div.rn -- must be 0 (the ratio features of the observation rely on it). */
+int mm_selftest_div(int amax, int bmax, uint64_t *mismatches, void *stream);
+
 /*
  * K3 -- GAE reverse scan.  Replaces PPO.get_GAEs (PPO.py:193-203) over fixed-horizon [T][E] buffers with
  * episode boundaries marked by done[t][e]; v_boot[e] = V(s_T) bootstraps episodes still open at t = T-1

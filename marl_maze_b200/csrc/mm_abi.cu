@@ -11,6 +11,7 @@ cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, i
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
                           cudaStream_t);
 int policy_offsets_host(int32_t* out);
+cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatches, cudaStream_t stream);
 cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream);
 __global__ void k_load_layouts(ulonglong2*, ulonglong2*, uint4*, int, int, int, int, const uint8_t*, const int32_t*, uint16_t*);
 __global__ void k_init_state(uint4*, uint32_t*, uint4*, uint32_t*, int);
@@ -39,6 +40,7 @@ static StepParams make_params(const mm_state* st) {
     p.env_grid = (ulonglong2*)st->env_grid; p.env_hdr = (uint4*)st->env_hdr; p.env_episode = (uint32_t*)st->env_episode;
     p.agent_a = (uint4*)st->agent_a; p.agent_b = (uint32_t*)st->agent_b;
     p.E = st->n_envs; p.P = st->n_pool; p.rows = st->smax + 2 * MM_PAD; p.smax = st->smax; p.max_t = st->max_timestep; p.env_offset = st->env_offset;
+    p.inv_max_t = 1.0f / (float)st->max_timestep;
     return p;
 }
 
@@ -142,6 +144,10 @@ int mm_gae(const float* reward, const float* value, const uint8_t* done, const f
     return cuda_status(launch_gae(reward, value, done, v_boot, adv, rtg, T, E, gamma, lam, (cudaStream_t)stream));
 }
 
+int mm_selftest_div(int amax, int bmax, uint64_t* mismatches, void* stream) {
+    if (amax < 0 || bmax < 1 || !mismatches) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_selftest_div(amax, bmax, (unsigned long long*)mismatches, (cudaStream_t)stream));
+}
 int mm_policy_offsets(int32_t* out) { return out ? policy_offsets_host(out) : MM_ERR_BAD_ARG; }
 int mm_critic_forward(const float* weights, const float* obs, int n_envs, float* value, void* stream) {
     if (!weights || !obs || !value || n_envs <= 0) return MM_ERR_BAD_ARG;

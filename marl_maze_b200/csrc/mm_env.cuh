@@ -38,6 +38,7 @@ struct StepParams {
     uint8_t* done;                         // [E]
     int E, P, rows, smax, max_t, auto_reset, env_offset;
     int obs_vec4;                          // obs pointer is 16-byte aligned: whole-warp float4 copy-out allowed
+    float inv_max_t;                       // correctly rounded 1/max_t (host: 1.0f / (float)max_t)
     uint64_t action_seed;
 };
 

@@ -17,7 +17,10 @@
 
 namespace mm {
 
-constexpr int kThreads = 128;
+#ifndef MM_K2_THREADS
+#define MM_K2_THREADS 128
+#endif
+constexpr int kThreads = MM_K2_THREADS;
 #ifndef MM_K2_MINBLOCKS
 #define MM_K2_MINBLOCKS 4
 #endif
@@ -50,7 +53,16 @@ __device__ __forceinline__ void locate(int dx, int dy, int& dir, int& j) {
 
 __device__ __forceinline__ uint32_t rev5(uint32_t v) { return __brev(v & 0x1fu) >> 27; }
 __device__ __forceinline__ uint32_t rot4r(uint32_t m, int f) { return ((m | (m << 4)) >> f) & 0xfu; }  // abs-direction bits -> relative
-__device__ __forceinline__ float fdiv(int a, int b) { return __fdiv_rn((float)a, (float)b); }
+// a / b for small integers (|a|, b <= 4096, b >= 1), correctly rounded like IEEE div.rn -- which is what makes the 7 ratio
+// features bit-identical to the reference's float64-divide-then-cast.  div.rn itself takes a ~100-instruction
+// slow path whenever the numerator is 0 (most of the time here); this is the Markstein sequence (correctly rounded
+// reciprocal, one FMA residual, one FMA correction), checked exhaustively against div.rn by mm_selftest_div.
+__device__ __forceinline__ float idiv_rcp(float fa, float fb, float rcp) {
+    const float q = __fmul_rn(fa, rcp);
+    const float e = __fmaf_rn(-q, fb, fa);
+    return __fmaf_rn(e, rcp, q);
+}
+__device__ __forceinline__ float fdiv(int a, int b) { const float fb = (float)b; return idiv_rcp((float)a, fb, __frcp_rn(fb)); }
 
 template <bool kResetOnly>
 __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const StepParams p) {
@@ -172,16 +184,42 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
 
         // ------------------------------------------------------------ window: rows y-5..y+5 of both bit planes
         const int x = me.x, y = me.y, f = me.dir;
-        ulonglong2 w[11];
+        uint32_t l[11], h[11];  // the window shifted so that column x-5 is bit 0 (the agent's column is bit 5); lo / hi planes
         ulonglong2 dd = make_ulonglong2(0, 0);
-        if (act) {
+        ulonglong2 wrow = make_ulonglong2(0, 0);  // full-width row holding this agent's pre-move cell (marks are written back through it)
+        // Step pass: the 12 in-flight 16-byte rows per lane go global -> shared with cp.async.cg (LDGSTS.BYPASS): they never
+        // occupy L1, whose capacity otherwise caps the number of outstanding window loads per SM (profiles/r01_notes.md).
+        // Slot = the warp's own observation staging area: [lane][11 rows] then [lane] field row, consumed into registers
+        // before any lane writes observation floats there (the __syncwarp below).  The (rare) reset pass must not touch
+        // that area -- it already holds the step-pass observations of the lanes that are not resetting -- and loads directly.
+        if (pass == 0 && !kResetOnly) {
+            char* wbase_s = reinterpret_cast<char*>(s_obs + (tid & ~31) * kObs);
+            ulonglong2* slot = reinterpret_cast<ulonglong2*>(wbase_s + lane * 176);
+            ulonglong2* dslot = reinterpret_cast<ulonglong2*>(wbase_s + 32 * 176 + lane * 16);
+            if (act) {
+                const ulonglong2* grid = (const ulonglong2*)(p.env_grid + (size_t)e * p.rows);
+                const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(slot), s1 = (uint32_t)__cvta_generic_to_shared(dslot);
+#pragma unroll
+                for (int r = 0; r < 11; r++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16 * r), "l"(grid + y + r) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + y) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 11; r++) {
+                const ulonglong2 v = act ? slot[r] : make_ulonglong2(~0ull, 0ull);
+                l[r] = (uint32_t)(v.x >> x); h[r] = (uint32_t)(v.y >> x);
+            }
+            if (act) { dd = *dslot; if (mk) wrow = slot[py - y + kPad]; }
+            __syncwarp();  // every lane has its window in registers; the area may now receive observation floats
+        } else {
             const ulonglong2* grid = pass == 0 ? (const ulonglong2*)(p.env_grid + (size_t)e * p.rows) : (p.pool_grid + (size_t)pidx * p.rows);
 #pragma unroll
-            for (int r = 0; r < 11; r++) w[r] = __ldcg(&grid[y + r]);
-            dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < 11; r++) w[r] = make_ulonglong2(~0ull, 0ull);
+            for (int r = 0; r < 11; r++) {
+                const ulonglong2 v = act ? __ldcg(&grid[y + r]) : make_ulonglong2(~0ull, 0ull);
+                l[r] = (uint32_t)(v.x >> x); h[r] = (uint32_t)(v.y >> x);
+            }
+            if (act) dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
         }
         const int d2e_here = (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
 
@@ -191,20 +229,19 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
             const int opx = __shfl_xor_sync(kFull, px, 1), opy = __shfl_xor_sync(kFull, py, 1);
             const bool m0 = a ? (omk != 0) : mk, m1 = a ? mk : (omk != 0);
             const int m0x = a ? opx : px, m0y = a ? opy : py, m1x = a ? px : opx, m1y = a ? py : opy;
-            if (m0) {  // tag 2: hi=1, lo=0
-                const int rr = m0y - y + kPad; const unsigned long long bit = 1ull << (m0x + kPad);
+            {   // tag 2: hi=1, lo=0 ; then tag 3: hi=1, lo=1 -- on the shifted window (columns outside it cannot be seen)
+                const int c0 = m0x - x + kPad, r0 = m0y - y + kPad, c1 = m1x - x + kPad, r1 = m1y - y + kPad;
+                const uint32_t b0 = (m0 && c0 >= 0 && c0 <= 10) ? (1u << c0) : 0u, b1 = (m1 && c1 >= 0 && c1 <= 10) ? (1u << c1) : 0u;
 #pragma unroll
-                for (int r = 0; r < 11; r++) if (rr == r) { w[r].y |= bit; w[r].x &= ~bit; }
+                for (int r = 0; r < 11; r++) {
+                    if (r0 == r) { h[r] |= b0; l[r] &= ~b0; }
+                    if (r1 == r) { h[r] |= b1; l[r] |= b1; }
+                }
             }
-            if (m1) {  // tag 3: hi=1, lo=1
-                const int rr = m1y - y + kPad; const unsigned long long bit = 1ull << (m1x + kPad);
-#pragma unroll
-                for (int r = 0; r < 11; r++) if (rr == r) { w[r].y |= bit; w[r].x |= bit; }
-            }
-            if (mk && act) {  // the marked row (pre-move cell: window row 4, 5 or 6) goes back to HBM with both marks applied
-                const int rr = py - y + kPad;
-                const ulonglong2 row = rr == 4 ? w[4] : (rr == 6 ? w[6] : w[5]);
-                p.env_grid[(size_t)e * p.rows + py + kPad] = row;
+            if (mk && act) {  // the marked row (pre-move cell) goes back to HBM with both marks applied, in order
+                if (m0 && m0y == py) { const unsigned long long bit = 1ull << (m0x + kPad); wrow.y |= bit; wrow.x &= ~bit; }
+                if (m1 && m1y == py) { const unsigned long long bit = 1ull << (m1x + kPad); wrow.y |= bit; wrow.x |= bit; }
+                p.env_grid[(size_t)e * p.rows + py + kPad] = wrow;
             }
         }
 
@@ -213,9 +250,6 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
         uint32_t cw[4] = {0, 0, 0, 0}, lat[4] = {0, 0, 0, 0}, ownm[4] = {0, 0, 0, 0}, othm[4] = {0, 0, 0, 0};
         const uint32_t ua = (uint32_t)a;
         {
-            uint32_t l[11], h[11];
-#pragma unroll
-            for (int r = 0; r < 11; r++) { l[r] = (uint32_t)(w[r].x >> x); h[r] = (uint32_t)(w[r].y >> x); }
             l5 = l[5]; h5 = h[5]; wl4 = l[4] & ~h[4]; wl5 = l5 & ~h5; wl6 = l[6] & ~h[6];
 #pragma unroll
             for (int j = 1; j <= 5; j++) {
@@ -328,7 +362,11 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
         if (act) {
             me.last_mask = mask6;
             // -------------------------------------------------------- observation vector (maze_agent.py:92-130)
+#ifdef MM_K2_DIRECT_STORE
+            float* so = p.obs + g * kObs;  // experiment: no shared-memory staging (uncoalesced 4-byte stores)
+#else
             float* so = s_obs + tid * kObs;
+#endif
             const uint32_t OWNr = __funnelshift_r(OWN32, OWN32, 8 * f), OTHr = __funnelshift_r(OTH32, OTH32, 8 * f);
             const uint32_t keyr = visK ? (1u << rK) : 0u;
 #pragma unroll
@@ -358,17 +396,18 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
             const int we = (me.maxx - me.minx) ? (me.maxx - me.minx) : 1, he = (me.maxy - me.miny) ? (me.maxy - me.miny) : 1;
 #pragma unroll
             for (int i = 0; i < 4; i++) { so[44 + i] = (float)((lmr >> i) & 1u); so[53 + i] = (float)((nm >> i) & 1u); }
-            so[48] = fdiv(x - me.minx, we);
-            so[49] = fdiv(me.maxy - y, he);
-            so[50] = fdiv(me.olsx - me.minx, we);
-            so[51] = fdiv(me.maxy - me.olsy, he);
+            const float fwe = (float)we, fhe = (float)he, rwe = __frcp_rn(fwe), rhe = __frcp_rn(fhe);
+            so[48] = idiv_rcp((float)(x - me.minx), fwe, rwe);
+            so[49] = idiv_rcp((float)(me.maxy - y), fhe, rhe);
+            so[50] = idiv_rcp((float)(me.olsx - me.minx), fwe, rwe);
+            so[51] = idiv_rcp((float)(me.maxy - me.olsy), fhe, rhe);
             so[52] = (float)s_se;
-            so[57] = me.exit_len < 40 ? fdiv(me.exit_len, 40) : 1.f;
+            so[57] = me.exit_len < 40 ? idiv_rcp((float)me.exit_len, 40.f, 0.025f) : 1.f;
             so[58] = (float)s_oke;
             so[59] = (float)me.has;
             so[60] = (float)s_team;
-            so[61] = me.time < 40u ? fdiv((int)me.time, 40) : 1.f;
-            so[62] = fdiv((int)t, p.max_t);
+            so[61] = me.time < 40u ? idiv_rcp((float)me.time, 40.f, 0.025f) : 1.f;
+            so[62] = idiv_rcp((float)t, (float)p.max_t, p.inv_max_t);
             so[63] = a ? 0.f : 1.f;
             so[64] = a ? 1.f : 0.f;
             uint16_t* mo = reinterpret_cast<uint16_t*>(p.masks) + g * 3;
@@ -391,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
     }
 
     // ---------------------------------------------------------------- observations: shared memory -> HBM, coalesced per warp
+#ifndef MM_K2_DIRECT_STORE
     __syncwarp();
     const uint32_t wmask = __ballot_sync(kFull, wrote);
     const int wbase = tid & ~31;
@@ -408,12 +448,30 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
             for (int i = lane; i < kObs; i += 32) o[i] = s[i];
         }
     }
+#endif
+}
+
+__global__ void k_selftest_div(int amax, int bmax, unsigned long long* mismatches) {
+    const long long n = (2ll * amax + 1) * bmax;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i / bmax) - amax, b = (int)(i % bmax) + 1;
+        const float want = __fdiv_rn((float)a, (float)b), got = fdiv(a, b);
+        if (__float_as_uint(want) != __float_as_uint(got)) atomicAdd(mismatches, 1ull);
+    }
+}
+cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatches, cudaStream_t stream) {
+    k_selftest_div<<<148 * 8, 256, 0, stream>>>(amax, bmax, mismatches);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream) {
     const long long agents = 2ll * p.E;
     const int blocks = (int)((agents + kThreads - 1) / kThreads);
+#ifdef MM_K2_DIRECT_STORE
+    const size_t smem = 0;
+#else
     const size_t smem = (size_t)kThreads * kObs * sizeof(float);
+#endif
     if (blocks == 0) return cudaSuccess;
     // NOTE (measured, profiles/r01_notes.md): forcing the maximum shared-memory carveout halves throughput -- the L1 capacity left
     // over is what buffers in-flight window loads -- so the driver's default carveout is kept.

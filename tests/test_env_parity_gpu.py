@@ -198,3 +198,13 @@ def test_world_size_independence():
         ob_, mb, rb, db = big.step(None, action_seed=3, actions_out=ao_b)
         os_, ms, rs, ds = small.step(None, action_seed=3, actions_out=ao_s)
         assert torch.equal(ao_b[lo:hi], ao_s) and torch.equal(ob_[lo:hi], os_) and torch.equal(mb[lo:hi], ms) and torch.equal(db[lo:hi], ds)
+
+
+def test_reciprocal_division_is_ieee_exact_exhaustively():
+    """K2's ratio features use rcp + 2 FMA instead of div.rn; every quotient a/b the observation can form must match div.rn."""
+    import ctypes as C
+    from marl_maze_b200 import _abi
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _abi.check(_abi.lib().mm_selftest_div(4096, 4096, C.c_void_p(cnt.data_ptr()), None), "mm_selftest_div")
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 0
