@@ -144,7 +144,8 @@ int mm_gae(const float *reward, const float *value, const uint8_t *done, const f
  *   weights: one flat fp32 buffer; block offsets (in floats) are returned by mm_policy_offsets (order: proj_w [23][20][4],
  *            proj_b [23][20], proj_col [23], proj_dim [23], att_k [10][20], att_q [10][20], att_v [20][20], l0_w [264][460], l0_b,
  *            l1_w [264][264], l1_b, l2_w, l2_b, head_w [6][264] (5 move rows + mark row), head_b [6], c0_w [64][130], c0_b, c1_w
- *            [64][64], c1_b, c2_w [64], c2_b [1], total).  proj_col[i] is the first obs column projection i reads: 0 for every i
+ *            [64][64], c1_b, c2_w [64], c2_b [1], total, then l{0,1,2}_w{hi,lo}: the trunk weights split as w = hi + lo with hi = w
+ *            truncated to TF32 -- only read by the tensor-core path).  proj_col[i] is the first obs column projection i reads: 0 for every i
  *            reproduces the reference's Projection.forward (networks.py:59-63); sum(FEATURE_DIMS[:i]) is the indexed variant.
  *   obs [E][2][65] f32, masks [E][2][6] u8, scratch: mm_sizeof_policy_scratch(E) bytes.
  *   actions_in == NULL: sample (Philox keyed by seed, counter, env_offset+env, agent) into actions_out [E][2][2] u8;
@@ -152,13 +153,14 @@ int mm_gae(const float *reward, const float *value, const uint8_t *done, const f
  *   logp [E] f32 = joint log-prob of both agents' actions (PPO.py:118,121); value [E] f32 (may be NULL); logits_out [E][2][6]
  *   f32 (may be NULL; 5 move logits + mark logit, unmasked).
  */
-int mm_policy_offsets(int32_t *out /* [24] */);
+int mm_policy_offsets(int32_t *out /* [32] */);
 /* critic only: value [E] = Critic(obs [E][2][65]) (networks.py:96-102); used for the bootstrap value V(s_T) */
 int mm_critic_forward(const float *weights, const float *obs, int n_envs, float *value, void *stream);
 size_t mm_sizeof_policy_scratch(int n_envs);
 int mm_policy_forward(const float *weights, const float *obs, const uint8_t *masks, int n_envs, void *scratch, const uint8_t *actions_in,
                       uint8_t *actions_out, float *logp, float *value, float *logits_out, int env_offset, uint64_t seed, uint64_t counter,
-                      void *stream);
+                      int flags, void *stream);
+#define MM_POLICY_TCGEN05 1 /* flags: trunk GEMMs as error-compensated 3xTF32 tcgen05.mma (TMA + TMEM); 0 = fp32 SIMT tiles */
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,7 @@ def lib():
         "mm_sizeof_policy_scratch": (sz, [i32]),
         "mm_critic_forward": (i32, [vp, vp, i32, vp, vp]),
         "mm_selftest_div": (i32, [i32, i32, vp, vp]),
-        "mm_policy_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, u64, u64, vp]),
+        "mm_policy_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, u64, u64, i32, vp]),
     }
     for name in EXPORTS:
         if not hasattr(L, name):

@@ -88,4 +88,13 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// x -> nearest TF32 value (10 explicit mantissa bits), returned as fp32.  The 3xTF32 trunk carries every operand as
+// hi = tf32(x), lo = tf32(x - hi): both terms are exact TF32 numbers, so the tensor core's own operand truncation is a no-op and
+// the representation error |x - hi - lo| <= 2^-22 |x| is zero-mean (plain truncation would bias every post-ReLU activation down).
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 }  // namespace mm

@@ -24,6 +24,7 @@ struct PolicyOffsets {
     int l0_w, l0_b, l1_w, l1_b, l2_w, l2_b;  // [264][460],[264] ; [264][264],[264] x2
     int head_w, head_b;                      // [6][264] (5 move rows then the mark row), [6]
     int c0_w, c0_b, c1_w, c1_b, c2_w, c2_b;  // critic [64][130],[64],[64][64],[64],[1][64],[1]
+    int l0_whi, l0_wlo, l1_whi, l1_wlo, l2_whi, l2_wlo;  // TF32 hi/lo splits of the three trunk weights (tensor-core path)
     int total;
 };
 __host__ __device__ inline PolicyOffsets policy_offsets() {
@@ -34,6 +35,8 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
     o.l0_w = take(kHid * kX0); o.l0_b = take(kHid); o.l1_w = take(kHid * kHid); o.l1_b = take(kHid); o.l2_w = take(kHid * kHid); o.l2_b = take(kHid);
     o.head_w = take(6 * kHid); o.head_b = take(6);
     o.c0_w = take(kCH * 130); o.c0_b = take(kCH); o.c1_w = take(kCH * kCH); o.c1_b = take(kCH); o.c2_w = take(kCH); o.c2_b = take(1);
+    o.l0_whi = take(kHid * kX0); o.l0_wlo = take(kHid * kX0); o.l1_whi = take(kHid * kHid); o.l1_wlo = take(kHid * kHid);
+    o.l2_whi = take(kHid * kHid); o.l2_wlo = take(kHid * kHid);
     o.total = p;
     return o;
 }
@@ -41,7 +44,9 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
 // ------------------------------------------------------------------------------------------------ tokens + attention
 // One warp per row.  Everything for a row lives in that warp's shared-memory slice.
 constexpr int kTokWarps = 4;
-__global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int R) {
+template <bool kSplit>  // kSplit: write x0 as the exact TF32 pair (hi, lo) for the tensor-core trunk
+__global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0,
+                                                         float* __restrict__ x0_lo, int R) {
     const PolicyOffsets o = policy_offsets();
     __shared__ float s_tok[kTokWarps][kTok][kEmb + 1], s_k[kTokWarps][kTok][kKQ + 1], s_q[kTokWarps][kTok][kKQ + 1], s_v[kTokWarps][kTok][kEmb + 1];
     __shared__ float s_p[kTokWarps][kTok][kTok + 1], s_obs[kTokWarps][68];
@@ -90,7 +95,13 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restri
         const int t = i / kEmb, d = i - t * kEmb;
         float acc = 0.f;
         for (int b = 0; b < kTok; b++) acc = fmaf(s_p[w][t][b], s_v[w][b][d], acc);
-        x0[(size_t)row * kX0 + i] = s_tok[w][t][d] + acc;
+        const float v = s_tok[w][t][d] + acc;
+        if (kSplit) {
+            const float hi = tf32_rn(v);
+            x0[(size_t)row * kX0 + i] = hi; x0_lo[(size_t)row * kX0 + i] = tf32_rn(v - hi);
+        } else {
+            x0[(size_t)row * kX0 + i] = v;
+        }
     }
 }
 
@@ -237,26 +248,46 @@ cudaError_t launch_critic(const float* wts, const float* obs, int E, float* valu
 
 int policy_offsets_host(int32_t* out) {
     const PolicyOffsets o = policy_offsets();
-    const int v[24] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
-                       o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, 0, 0};
-    for (int i = 0; i < 24; i++) out[i] = v[i];
+    const int v[32] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
+                       o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, o.l0_whi, o.l0_wlo, o.l1_whi, o.l1_wlo, o.l2_whi, o.l2_wlo,
+                       0, 0, 0, 0};
+    for (int i = 0; i < 32; i++) out[i] = v[i];
     return 0;
 }
 
+cudaError_t launch_linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias, float* y_hi, float* y_lo, int M, int K,
+                             int split_out, cudaStream_t stream);
+
+// flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
                           uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter,
-                          cudaStream_t stream) {
+                          int flags, cudaStream_t stream) {
     const PolicyOffsets o = policy_offsets();
     const int R = 2 * E;
-    float* x0 = scratch;                      // [R,460]
-    float* h1 = scratch + (size_t)R * kX0;    // [R,264]
-    float* h2 = h1 + (size_t)R * kHid;        // [R,264]
-    k_tokens<<<(R + kTokWarps - 1) / kTokWarps, kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
-    dim3 grid((R + BM - 1) / BM, (kHid + BN - 1) / BN);
-    k_linear_relu<<<grid, 256, 0, stream>>>(x0, wts + o.l0_w, wts + o.l0_b, h1, R, kHid, kX0);
-    k_linear_relu<<<grid, 256, 0, stream>>>(h1, wts + o.l1_w, wts + o.l1_b, h2, R, kHid, kHid);
-    k_linear_relu<<<grid, 256, 0, stream>>>(h2, wts + o.l2_w, wts + o.l2_b, h1, R, kHid, kHid);
-    k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h1, wts, masks, actions_in, actions_out, logp, logits_out, E, env_offset, seed, counter);
+    const float* h_final;
+    if (flags & 1) {
+        float* x0h = scratch; float* x0l = x0h + (size_t)R * kX0;
+        float* h1h = x0l + (size_t)R * kX0; float* h1l = h1h + (size_t)R * kHid;
+        float* h2h = h1l + (size_t)R * kHid; float* h2l = h2h + (size_t)R * kHid;
+        float* h3 = h2l + (size_t)R * kHid;
+        k_tokens<true><<<(R + kTokWarps - 1) / kTokWarps, kTokWarps * 32, 0, stream>>>(obs, wts, x0h, x0l, R);
+        cudaError_t e;
+        if ((e = launch_linear_tc(x0h, x0l, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1h, h1l, R, kX0, 1, stream)) != cudaSuccess) return e;
+        if ((e = launch_linear_tc(h1h, h1l, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2h, h2l, R, kHid, 1, stream)) != cudaSuccess) return e;
+        if ((e = launch_linear_tc(h2h, h2l, wts + o.l2_whi, wts + o.l2_wlo, wts + o.l2_b, h3, h3, R, kHid, 0, stream)) != cudaSuccess) return e;
+        h_final = h3;
+    } else {
+        float* x0 = scratch;                      // [R,460]
+        float* h1 = scratch + (size_t)R * kX0;    // [R,264]
+        float* h2 = h1 + (size_t)R * kHid;        // [R,264]
+        k_tokens<false><<<(R + kTokWarps - 1) / kTokWarps, kTokWarps * 32, 0, stream>>>(obs, wts, x0, nullptr, R);
+        dim3 grid((R + BM - 1) / BM, (kHid + BN - 1) / BN);
+        k_linear_relu<<<grid, 256, 0, stream>>>(x0, wts + o.l0_w, wts + o.l0_b, h1, R, kHid, kX0);
+        k_linear_relu<<<grid, 256, 0, stream>>>(h1, wts + o.l1_w, wts + o.l1_b, h2, R, kHid, kHid);
+        k_linear_relu<<<grid, 256, 0, stream>>>(h2, wts + o.l2_w, wts + o.l2_b, h1, R, kHid, kHid);
+        h_final = h1;
+    }
+    k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h_final, wts, masks, actions_in, actions_out, logp, logits_out, E, env_offset, seed, counter);
     if (value) k_critic<<<(E + 3) / 4, 128, 0, stream>>>(obs, wts, value, E);
     return cudaGetLastError();
 }

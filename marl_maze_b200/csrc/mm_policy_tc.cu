@@ -1,0 +1,225 @@
+// mm_policy_tc.cu -- K4 tensor-core path: Y = relu(X W^T + b) on tcgen05 with error-compensated TF32 (3xTF32), sm_100a.
+//
+// The parity bar of the policy path is 1e-5 relative on logits / values / log-probs (BASELINE north_star), which single-pass
+// TF32/BF16 tensor-core math cannot meet.  Every operand is therefore carried as a two-term split x ~ x_hi + x_lo with
+// x_hi = tf32(x) and x_lo = tf32(x - x_hi), both rounded to nearest (|x - x_hi - x_lo| <= 2^-22 |x|, zero-mean), and each
+// k-step issues three MMAs into the same fp32 TMEM accumulator:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is ~2^-22).
+//
+// One CTA = one 128-row tile of X through one layer (N = 264 outputs, padded to 272 = 144 + 128 so that each half is a legal
+// UMMA N for M = 128).  Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2-5 = epilogue (TMEM -> registers -> bias + ReLU -> hi/lo split -> global).  Operands are staged by TMA
+// (cp.async.bulk.tensor, SWIZZLE_128B, K-major 128-byte rows = 32 fp32) through a 2-stage mbarrier ring; out-of-bounds rows /
+// columns (M tail, K = 460 -> 480, N = 264 -> 272) are zero-filled by TMA, so nothing is physically padded in HBM.
+#include <cuda.h>
+#include <stdio.h>
+#include "mm_env.cuh"
+
+namespace mm {
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_N1 = 144, TC_N2 = 128, TC_N = 264, TC_STAGES = 2;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
+constexpr uint32_t TC_B1_BYTES = TC_N1 * TC_BK * 4;   // 18432
+constexpr uint32_t TC_B2_BYTES = TC_N2 * TC_BK * 4;   // 16384
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * (TC_B1_BYTES + TC_B2_BYTES);  // 102400
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(map),
+                 "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 1024 bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc),
+                 "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TcMaps {
+    CUtensorMap a_hi, a_lo, w1_hi, w2_hi, w1_lo, w2_lo;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y_hi, float* __restrict__ y_lo, int M, int K, int split_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tmem_full = empty + TC_STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM;
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % TC_STAGES;
+                mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * TC_STAGE_BYTES;
+                mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+                const int k0 = kb * TC_BK;
+                tma_load_2d(st, &maps.a_hi, k0, m0, &full[s]);
+                tma_load_2d(st + TC_A_BYTES, &maps.a_lo, k0, m0, &full[s]);
+                tma_load_2d(st + 2 * TC_A_BYTES, &maps.w1_hi, k0, 0, &full[s]);
+                tma_load_2d(st + 2 * TC_A_BYTES + TC_B1_BYTES, &maps.w2_hi, k0, TC_N1, &full[s]);
+                tma_load_2d(st + 2 * TC_A_BYTES + TC_B1_BYTES + TC_B2_BYTES, &maps.w1_lo, k0, 0, &full[s]);
+                tma_load_2d(st + 2 * TC_A_BYTES + 2 * TC_B1_BYTES + TC_B2_BYTES, &maps.w2_lo, k0, TC_N1, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer: D[128 x 272] (two N chunks) += A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T
+            constexpr uint32_t id1 = umma_idesc_tf32(TC_BM, TC_N1), id2 = umma_idesc_tf32(TC_BM, TC_N2);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % TC_STAGES;
+                mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
+                const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TC_A_BYTES);
+                const uint64_t b1_hi = umma_desc(st + 2 * TC_A_BYTES), b2_hi = umma_desc(st + 2 * TC_A_BYTES + TC_B1_BYTES);
+                const uint64_t b1_lo = umma_desc(st + 2 * TC_A_BYTES + TC_B1_BYTES + TC_B2_BYTES), b2_lo = umma_desc(st + 2 * TC_A_BYTES + 2 * TC_B1_BYTES + TC_B2_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the 128-byte swizzle row
+                    const uint64_t o = (uint64_t)(k * 2);
+                    const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, a_hi + o, b1_hi + o, id1, first);
+                    umma_tf32(tmem_base, a_lo + o, b1_hi + o, id1, 1u);
+                    umma_tf32(tmem_base, a_hi + o, b1_lo + o, id1, 1u);
+                    umma_tf32(tmem_base + TC_N1, a_hi + o, b2_hi + o, id2, first);
+                    umma_tf32(tmem_base + TC_N1, a_lo + o, b2_hi + o, id2, 1u);
+                    umma_tf32(tmem_base + TC_N1, a_hi + o, b2_lo + o, id2, 1u);
+                }
+                umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+            }
+            umma_commit(tmem_full);      // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31; one thread = one output row
+        const int quarter = warp & 3;
+        const int row = m0 + quarter * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < 17; c++) {
+            uint32_t v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr + (uint32_t)(c * 16)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                const int ncol = (c == 16) ? 8 : 16;  // 264 = 16*16 + 8
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int col = c * 16 + j;
+                    float yv = __uint_as_float(v[j]) + (col < TC_N ? bias[col] : 0.f);
+                    yv = fmaxf(yv, 0.f);
+                    if (split_out) { hi[j] = tf32_rn(yv); lo[j] = tf32_rn(yv - hi[j]); }
+                    else { hi[j] = yv; lo[j] = 0.f; }
+                }
+                float4* ph = reinterpret_cast<float4*>(y_hi + (size_t)row * TC_N + c * 16);
+                float4* pl = reinterpret_cast<float4*>(y_lo + (size_t)row * TC_N + c * 16);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (q * 4 < ncol) {
+                        ph[q] = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                        if (split_out) pl[q] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+// fp32 row-major [rows][cols] with a {32 cols x box_rows} box, 128-byte swizzle, zero fill out of bounds
+static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Y = relu(X W^T + b) with X given as (x_hi, x_lo) [M][K], W as (w_hi, w_lo) [264][K]; writes (y_hi, y_lo) or plain y into y_hi.
+cudaError_t launch_linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias, float* y_hi, float* y_lo, int M, int K,
+                             int split_out, cudaStream_t stream) {
+    TcMaps maps;
+    if (!make_map(&maps.a_hi, x_hi, M, K, TC_BM) || !make_map(&maps.a_lo, x_lo, M, K, TC_BM) || !make_map(&maps.w1_hi, w_hi, TC_N, K, TC_N1) ||
+        !make_map(&maps.w2_hi, w_hi, TC_N, K, TC_N2) || !make_map(&maps.w1_lo, w_lo, TC_N, K, TC_N1) || !make_map(&maps.w2_lo, w_lo, TC_N, K, TC_N2))
+        return cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_linear_tf32x3<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y_hi, y_lo, M, K, split_out);
+    return cudaGetLastError();
+}
+
+}  // namespace mm

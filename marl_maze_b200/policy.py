@@ -14,13 +14,18 @@ from . import _abi
 from .networks import FEATURE_DIMS, EMBEDDING_DIM
 
 _NAMES = ["proj_w", "proj_b", "proj_col", "proj_dim", "att_k", "att_q", "att_v", "l0_w", "l0_b", "l1_w", "l1_b", "l2_w", "l2_b",
-          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total"]
+          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo"]
 
 
 def offsets() -> dict:
-    out = (C.c_int32 * 24)()
+    out = (C.c_int32 * 32)()
     _abi.check(_abi.lib().mm_policy_offsets(out), "mm_policy_offsets")
     return {n: int(out[i]) for i, n in enumerate(_NAMES)}
+
+
+def _tf32_rn(x: torch.Tensor) -> torch.Tensor:
+    """Nearest TF32 value (10 explicit mantissa bits, ties away from zero) -- same rounding as cvt.rna.tf32.f32 on the device."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
 
 
 def pack_weights(actor, critic, device=None) -> torch.Tensor:
@@ -48,7 +53,10 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
         put("proj_w", pw); put("proj_b", torch.cat([l.bias for l in actor.projection.layers])); put("proj_col", col); put("proj_dim", dim)
         put("att_k", actor.attention.keys.weight); put("att_q", actor.attention.querys.weight); put("att_v", actor.attention.values.weight)
         for i in range(3):
-            put(f"l{i}_w", actor.layers[i].weight); put(f"l{i}_b", actor.layers[i].bias)
+            w = actor.layers[i].weight.detach().to(dev, torch.float32).contiguous()
+            put(f"l{i}_w", w); put(f"l{i}_b", actor.layers[i].bias)
+            hi = _tf32_rn(w)
+            put(f"l{i}_whi", hi); put(f"l{i}_wlo", _tf32_rn(w - hi))
         put("head_w", torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)); put("head_b", torch.cat([actor.move_head.bias, actor.mark_head.bias]))
         for i in range(3):
             put(f"c{i}_w", critic.layers[i].weight); put(f"c{i}_b", critic.layers[i].bias)
@@ -56,7 +64,7 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
 
 
 class PolicyRunner:
-    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0):
+    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0, tensor_cores: bool = True):
         self.lib = _abi.lib()
         self.E, self.device, self.env_offset, self.seed = int(num_envs), torch.device(device), int(env_offset), int(seed) & (2**64 - 1)
         self.actor, self.critic = actor, critic
@@ -64,6 +72,7 @@ class PolicyRunner:
         self.scratch = torch.empty(int(self.lib.mm_sizeof_policy_scratch(self.E)), dtype=torch.uint8, device=self.device)
         self.counter = 0
         self.launches = 0
+        self.flags = 1 if tensor_cores else 0  # MM_POLICY_TCGEN05
 
     def refresh(self):
         """Re-pack after an optimiser step."""
@@ -92,6 +101,6 @@ class PolicyRunner:
         self.counter += 1
         _abi.check(self.lib.mm_policy_forward(p(self.weights), p(obs), p(masks), E, p(self.scratch), p(actions_in), p(actions_out), p(logp),
                                               p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(self.counter),
-                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
+                                              self.flags, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
         self.launches += 6 if want_value else 5
         return (actions_in if actions_in is not None else actions_out), logp, (value if want_value else None)

@@ -21,14 +21,15 @@ def _nets(seed, faithful=True):
     return actor, critic, asd, csd
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["simt_fp32", "tcgen05_3xtf32"])
 @pytest.mark.parametrize("seed", [11, 12])
-def test_policy_kernel_vs_reference_golden(seed):
+def test_policy_kernel_vs_reference_golden(seed, tc):
     from marl_maze_b200.policy import PolicyRunner
     Z = np.load(os.path.join(GOLDEN, "ppo_kats.npz"))
     obs, masks, acts = Z["net/obs"], Z["net/masks"], Z["net/actions"]
     actor, critic, _, _ = _nets(seed)
     E = obs.shape[0]
-    run = PolicyRunner(actor, critic, E, "cuda")
+    run = PolicyRunner(actor, critic, E, "cuda", tensor_cores=tc)
     logits = torch.zeros(E, 2, 6, device="cuda")
     _, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), actions_in=torch.from_numpy(acts).cuda(), logits=logits)
     lg = logits.cpu().numpy()
@@ -41,15 +42,16 @@ def test_policy_kernel_vs_reference_golden(seed):
     assert np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], want[fin], **TOL)
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["simt_fp32", "tcgen05_3xtf32"])
 @pytest.mark.parametrize("faithful", [True, False])
-def test_policy_kernel_vs_oracle_random_obs_and_sampling(faithful):
+def test_policy_kernel_vs_oracle_random_obs_and_sampling(faithful, tc):
     from marl_maze_b200.policy import PolicyRunner
     actor, critic, asd, csd = _nets(5, faithful)
     rng = np.random.default_rng(3)
     E = 3000
     obs = rng.random((E, 2, 65)).astype(np.float32)
     masks = (rng.random((E, 2, 6)) < 0.6).astype(np.uint8); masks[:, :, 0] |= (masks[:, :, :5].sum(-1) == 0).astype(np.uint8)
-    run = PolicyRunner(actor, critic, E, "cuda", seed=9)
+    run = PolicyRunner(actor, critic, E, "cuda", seed=9, tensor_cores=tc)
     logits = torch.zeros(E, 2, 6, device="cuda")
     act, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), logits=logits)
     act = act.cpu().numpy()
