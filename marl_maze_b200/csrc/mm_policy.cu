@@ -25,6 +25,7 @@ struct PolicyOffsets {
     int head_w, head_b;                      // [6][264] (5 move rows then the mark row), [6]
     int c0_w, c0_b, c1_w, c1_b, c2_w, c2_b;  // critic [64][130],[64],[64][64],[64],[1][64],[1]
     int l0_whi, l0_wlo, l1_whi, l1_wlo, l2_whi, l2_wlo;  // TF32 hi/lo splits of the three trunk weights (tensor-core path)
+    int c0_wt, c1_wt;                                    // critic weights transposed: [130][64], [64][64] (coalesced lane = neuron reads)
     int total;
 };
 __host__ __device__ inline PolicyOffsets policy_offsets() {
@@ -37,70 +38,100 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
     o.c0_w = take(kCH * 130); o.c0_b = take(kCH); o.c1_w = take(kCH * kCH); o.c1_b = take(kCH); o.c2_w = take(kCH); o.c2_b = take(1);
     o.l0_whi = take(kHid * kX0); o.l0_wlo = take(kHid * kX0); o.l1_whi = take(kHid * kHid); o.l1_wlo = take(kHid * kHid);
     o.l2_whi = take(kHid * kHid); o.l2_wlo = take(kHid * kHid);
+    o.c0_wt = take(130 * kCH); o.c1_wt = take(kCH * kCH);
     o.total = p;
     return o;
 }
 
 // ------------------------------------------------------------------------------------------------ tokens + attention
-// One warp per row.  Everything for a row lives in that warp's shared-memory slice.
-constexpr int kTokWarps = 4;
-template <bool kSplit>  // kSplit: write x0 as the exact TF32 pair (hi, lo) for the tensor-core trunk
+// One warp per row, one LANE per feature token (23 of 32 lanes active): the lane keeps its token, query and context in
+// registers; keys / values of the row's 23 tokens are exchanged through a small per-warp shared-memory tile (broadcast reads);
+// the tiny weights (K, Q, V, projections) are staged once per block in shared memory and read as broadcast float4.
+constexpr int kTokWarps = 8;
+template <bool kSplit>  // kSplit: write x0 as the TF32 pair (hi, lo) for the tensor-core trunk
 __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0,
                                                          float* __restrict__ x0_lo, int R) {
     const PolicyOffsets o = policy_offsets();
-    __shared__ float s_tok[kTokWarps][kTok][kEmb + 1], s_k[kTokWarps][kTok][kKQ + 1], s_q[kTokWarps][kTok][kKQ + 1], s_v[kTokWarps][kTok][kEmb + 1];
-    __shared__ float s_p[kTokWarps][kTok][kTok + 1], s_obs[kTokWarps][68];
+    __shared__ __align__(16) float s_wkqv[40][kEmb];           // rows 0-9 keys, 10-19 querys, 20-39 values
+    __shared__ __align__(16) float s_pw[kTok][kEmb][4];
+    __shared__ float s_pb[kTok][kEmb];
+    __shared__ __align__(16) float s_k[kTokWarps][kTok][12], s_v[kTokWarps][kTok][kEmb];
+    for (int i = threadIdx.x; i < 10 * kEmb; i += blockDim.x) { (&s_wkqv[0][0])[i] = wts[o.att_k + i]; (&s_wkqv[10][0])[i] = wts[o.att_q + i]; }
+    for (int i = threadIdx.x; i < kEmb * kEmb; i += blockDim.x) (&s_wkqv[20][0])[i] = wts[o.att_v + i];
+    for (int i = threadIdx.x; i < kTok * kEmb * 4; i += blockDim.x) (&s_pw[0][0][0])[i] = wts[o.proj_w + i];
+    for (int i = threadIdx.x; i < kTok * kEmb; i += blockDim.x) (&s_pb[0][0])[i] = wts[o.proj_b + i];
+    __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kTokWarps + w;
     if (row >= R) return;
-    for (int i = lane; i < kObs; i += 32) s_obs[w][i] = obs[(size_t)row * kObs + i];
-    __syncwarp();
-    for (int i = lane; i < kX0; i += 32) {  // projection: token t, dim d
-        const int t = i / kEmb, d = i - t * kEmb;
-        const int c0 = (int)wts[o.proj_col + t], nd = (int)wts[o.proj_dim + t];
-        float acc = wts[o.proj_b + i];
-        const float* pw = wts + o.proj_w + i * 4;
-        for (int c = 0; c < nd; c++) acc = fmaf(s_obs[w][c0 + c], pw[c], acc);
-        s_tok[w][t][d] = acc;
+    const bool on = lane < kTok;
+    const int a = on ? lane : 0;
+    float tok[kEmb], q[kKQ];
+    {   // projection of this token: <= 4 observation columns (networks.py:58-65)
+        const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
+        float x[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) x[c] = (c < nd) ? obs[(size_t)row * kObs + c0 + c] : 0.f;
+#pragma unroll
+        for (int d = 0; d < kEmb; d++) {
+            const float4 pw = *reinterpret_cast<const float4*>(&s_pw[a][d][0]);
+            tok[d] = fmaf(x[3], pw.w, fmaf(x[2], pw.z, fmaf(x[1], pw.y, fmaf(x[0], pw.x, s_pb[a][d]))));
+        }
     }
-    __syncwarp();
-    for (int i = lane; i < kTok * (2 * kKQ + kEmb); i += 32) {  // K, Q (10 each) and V (20) per token
-        const int t = i / (2 * kKQ + kEmb), j = i - t * (2 * kKQ + kEmb);
-        const float* wr = j < kKQ ? wts + o.att_k + j * kEmb : (j < 2 * kKQ ? wts + o.att_q + (j - kKQ) * kEmb : wts + o.att_v + (j - 2 * kKQ) * kEmb);
+#pragma unroll
+    for (int j = 0; j < 40; j++) {  // keys, querys, values of this token
         float acc = 0.f;
 #pragma unroll
-        for (int d = 0; d < kEmb; d++) acc = fmaf(s_tok[w][t][d], wr[d], acc);
-        if (j < kKQ) s_k[w][t][j] = acc; else if (j < 2 * kKQ) s_q[w][t][j - kKQ] = acc; else s_v[w][t][j - 2 * kKQ] = acc;
+        for (int d4 = 0; d4 < kEmb / 4; d4++) {
+            const float4 wv = *reinterpret_cast<const float4*>(&s_wkqv[j][4 * d4]);
+            acc = fmaf(tok[4 * d4 + 3], wv.w, fmaf(tok[4 * d4 + 2], wv.z, fmaf(tok[4 * d4 + 1], wv.y, fmaf(tok[4 * d4], wv.x, acc))));
+        }
+        if (j < kKQ) { if (on) s_k[w][a][j] = acc; }
+        else if (j < 2 * kKQ) q[j - kKQ] = acc;
+        else if (on) s_v[w][a][j - 2 * kKQ] = acc;
     }
     __syncwarp();
-    const float scale = 0.31622776601683794f;  // 1/sqrt(10)
-    for (int i = lane; i < kTok * kTok; i += 32) {
-        const int a = i / kTok, b = i - a * kTok;
+    float p[kTok];
+    float m = -INFINITY;
+#pragma unroll
+    for (int b = 0; b < kTok; b++) {  // scores against every key of the row (networks.py:79)
         float acc = 0.f;
 #pragma unroll
-        for (int d = 0; d < kKQ; d++) acc = fmaf(s_q[w][a][d], s_k[w][b][d], acc);
-        s_p[w][a][b] = acc * scale;
+        for (int d = 0; d < kKQ; d++) acc = fmaf(q[d], s_k[w][b][d], acc);
+        p[b] = acc * 0.31622776601683794f;  // 1/sqrt(10)
+        m = fmaxf(m, p[b]);
     }
-    __syncwarp();
-    if (lane < kTok) {  // softmax over each row of scores
-        float m = -INFINITY;
-        for (int b = 0; b < kTok; b++) m = fmaxf(m, s_p[w][lane][b]);
-        float s = 0.f;
-        for (int b = 0; b < kTok; b++) { const float e = expf(s_p[w][lane][b] - m); s_p[w][lane][b] = e; s += e; }
-        const float inv = 1.f / s;
-        for (int b = 0; b < kTok; b++) s_p[w][lane][b] *= inv;
+    float sum = 0.f;
+#pragma unroll
+    for (int b = 0; b < kTok; b++) { p[b] = expf(p[b] - m); sum += p[b]; }
+    const float inv = 1.f / sum;
+    float ctx[kEmb];
+#pragma unroll
+    for (int d = 0; d < kEmb; d++) ctx[d] = 0.f;
+#pragma unroll
+    for (int b = 0; b < kTok; b++) {
+        const float pb = p[b] * inv;
+#pragma unroll
+        for (int d4 = 0; d4 < kEmb / 4; d4++) {
+            const float4 vv = *reinterpret_cast<const float4*>(&s_v[w][b][4 * d4]);
+            ctx[4 * d4] = fmaf(pb, vv.x, ctx[4 * d4]); ctx[4 * d4 + 1] = fmaf(pb, vv.y, ctx[4 * d4 + 1]);
+            ctx[4 * d4 + 2] = fmaf(pb, vv.z, ctx[4 * d4 + 2]); ctx[4 * d4 + 3] = fmaf(pb, vv.w, ctx[4 * d4 + 3]);
+        }
     }
-    __syncwarp();
-    for (int i = lane; i < kX0; i += 32) {
-        const int t = i / kEmb, d = i - t * kEmb;
-        float acc = 0.f;
-        for (int b = 0; b < kTok; b++) acc = fmaf(s_p[w][t][b], s_v[w][b][d], acc);
-        const float v = s_tok[w][t][d] + acc;
-        if (kSplit) {
-            const float hi = tf32_rn(v);
-            x0[(size_t)row * kX0 + i] = hi; x0_lo[(size_t)row * kX0 + i] = tf32_rn(v - hi);
-        } else {
-            x0[(size_t)row * kX0 + i] = v;
+    if (on) {  // residual (networks.py:82); lane a owns columns 20a .. 20a+19 of the row
+        float4* oh = reinterpret_cast<float4*>(x0 + (size_t)row * kX0 + a * kEmb);
+        float4* ol = kSplit ? reinterpret_cast<float4*>(x0_lo + (size_t)row * kX0 + a * kEmb) : nullptr;
+#pragma unroll
+        for (int d4 = 0; d4 < kEmb / 4; d4++) {
+            float v[4], hi[4], lo[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                v[c] = tok[4 * d4 + c] + ctx[4 * d4 + c];
+                hi[c] = kSplit ? tf32_rn(v[c]) : v[c];
+                lo[c] = kSplit ? tf32_rn(v[c] - hi[c]) : 0.f;
+            }
+            oh[d4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            if (kSplit) ol[d4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 }
@@ -206,43 +237,52 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ h, cons
 }
 
 // ------------------------------------------------------------------------------------------------ critic
-// One warp per env: 130 -> 64 -> 64 -> 1, hidden vectors in registers (2 per lane).
+// 130 -> 64 -> 64 -> 1.  One warp handles 4 envs at a time; lane j owns hidden neurons j and j+32, weights are read from the
+// TRANSPOSED copies ([k][neuron]: a warp reads 2 x 128 contiguous bytes per k, L1-resident), inputs are broadcast from shared.
+constexpr int kCrEnvs = 4;
 __global__ void __launch_bounds__(128) k_critic(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ value, int E) {
     const PolicyOffsets o = policy_offsets();
-    __shared__ float s_in[4][132], s_h[4][kCH];
+    __shared__ float s_in[4][kCrEnvs][132], s_h[4][kCrEnvs][kCH];
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * 4 + wl;
-    if (w >= E) return;
-    for (int i = lane; i < 130; i += 32) s_in[wl][i] = obs[(size_t)w * 130 + i];
+    const int e0 = (blockIdx.x * 4 + wl) * kCrEnvs;
+    if (e0 >= E) return;
+    const int ne = min(kCrEnvs, E - e0);
+    for (int i = lane; i < kCrEnvs * 130; i += 32) { const int e = i / 130, k = i - e * 130; s_in[wl][e][k] = e < ne ? obs[(size_t)(e0 + e) * 130 + k] : 0.f; }
     __syncwarp();
-    float h0[2];
+    float a0[kCrEnvs], a1[kCrEnvs];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int j = lane + 32 * q;
-        float acc = wts[o.c0_b + j];
-        const float* wr = wts + o.c0_w + j * 130;
-        for (int k = 0; k < 130; k++) acc = fmaf(s_in[wl][k], wr[k], acc);
-        h0[q] = fmaxf(acc, 0.f);
-    }
-    s_h[wl][lane] = h0[0]; s_h[wl][lane + 32] = h0[1];
-    __syncwarp();
-    float part = 0.f;
+    for (int e = 0; e < kCrEnvs; e++) { a0[e] = wts[o.c0_b + lane]; a1[e] = wts[o.c0_b + lane + 32]; }
+    const float* w0 = wts + o.c0_wt;
+#pragma unroll 2
+    for (int k = 0; k < 130; k++) {
+        const float wa = w0[k * kCH + lane], wb = w0[k * kCH + lane + 32];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int j = lane + 32 * q;
-        float acc = wts[o.c1_b + j];
-        const float* wr = wts + o.c1_w + j * kCH;
-#pragma unroll 8
-        for (int k = 0; k < kCH; k++) acc = fmaf(s_h[wl][k], wr[k], acc);
-        part = fmaf(fmaxf(acc, 0.f), wts[o.c2_w + j], part);
+        for (int e = 0; e < kCrEnvs; e++) { const float x = s_in[wl][e][k]; a0[e] = fmaf(x, wa, a0[e]); a1[e] = fmaf(x, wb, a1[e]); }
     }
 #pragma unroll
-    for (int s = 16; s; s >>= 1) part += __shfl_xor_sync(kFull, part, s);
-    if (lane == 0) value[w] = part + wts[o.c2_b];
+    for (int e = 0; e < kCrEnvs; e++) { s_h[wl][e][lane] = fmaxf(a0[e], 0.f); s_h[wl][e][lane + 32] = fmaxf(a1[e], 0.f); }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < kCrEnvs; e++) { a0[e] = wts[o.c1_b + lane]; a1[e] = wts[o.c1_b + lane + 32]; }
+    const float* w1 = wts + o.c1_wt;
+#pragma unroll 4
+    for (int k = 0; k < kCH; k++) {
+        const float wa = w1[k * kCH + lane], wb = w1[k * kCH + lane + 32];
+#pragma unroll
+        for (int e = 0; e < kCrEnvs; e++) { const float x = s_h[wl][e][k]; a0[e] = fmaf(x, wa, a0[e]); a1[e] = fmaf(x, wb, a1[e]); }
+    }
+    const float v0 = wts[o.c2_w + lane], v1 = wts[o.c2_w + lane + 32], vb = wts[o.c2_b];
+#pragma unroll
+    for (int e = 0; e < kCrEnvs; e++) {
+        float part = fmaf(fmaxf(a0[e], 0.f), v0, fmaxf(a1[e], 0.f) * v1);
+#pragma unroll
+        for (int sft = 16; sft; sft >>= 1) part += __shfl_xor_sync(kFull, part, sft);
+        if (lane == 0 && e < ne) value[e0 + e] = part + vb;
+    }
 }
 
 cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream) {
-    k_critic<<<(E + 3) / 4, 128, 0, stream>>>(obs, wts, value, E);
+    k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
     return cudaGetLastError();
 }
 
@@ -250,7 +290,7 @@ int policy_offsets_host(int32_t* out) {
     const PolicyOffsets o = policy_offsets();
     const int v[32] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
                        o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, o.l0_whi, o.l0_wlo, o.l1_whi, o.l1_wlo, o.l2_whi, o.l2_wlo,
-                       0, 0, 0, 0};
+                       o.c0_wt, o.c1_wt, 0, 0};
     for (int i = 0; i < 32; i++) out[i] = v[i];
     return 0;
 }
@@ -288,7 +328,7 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         h_final = h1;
     }
     k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h_final, wts, masks, actions_in, actions_out, logp, logits_out, E, env_offset, seed, counter);
-    if (value) k_critic<<<(E + 3) / 4, 128, 0, stream>>>(obs, wts, value, E);
+    if (value) k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ from . import _abi
 from .networks import FEATURE_DIMS, EMBEDDING_DIM
 
 _NAMES = ["proj_w", "proj_b", "proj_col", "proj_dim", "att_k", "att_q", "att_v", "l0_w", "l0_b", "l1_w", "l1_b", "l2_w", "l2_b",
-          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo"]
+          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo", "c0_wt", "c1_wt"]
 
 
 def offsets() -> dict:
@@ -60,6 +60,7 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
         put("head_w", torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)); put("head_b", torch.cat([actor.move_head.bias, actor.mark_head.bias]))
         for i in range(3):
             put(f"c{i}_w", critic.layers[i].weight); put(f"c{i}_b", critic.layers[i].bias)
+        put("c0_wt", critic.layers[0].weight.t().contiguous()); put("c1_wt", critic.layers[1].weight.t().contiguous())
     return buf
 
 
