@@ -47,7 +47,7 @@ def _peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index: int, period=0.02):
+    def __init__(self, index: int, period=0.004):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
