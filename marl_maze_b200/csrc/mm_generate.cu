@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
             if (nx >= 0 && nx < W && ny >= 0 && ny < Hh && !is_open(nx, ny)) nb[nn++] = ny * 64 + nx;
         }
         bool go = false;
-        if (nn) go = __fmul_rn((float)(rng.next() >> 8), 1.0f / 16777216.0f) > cc;
+        // (0,1]: with a 24-bit draw an exact 0 would (once in 2^24) lose against corridor_const == 0 and stop the carve at a
+        // single cell; Python's 53-bit random() never does in practice
+        if (nn) go = __fmul_rn((float)((rng.next() >> 8) + 1u), 1.0f / 16777216.0f) > cc;
         if (go) {
             const uint32_t pick = rng.below((uint32_t)nn);
             const int nc = pick == 0 ? nb[0] : pick == 1 ? nb[1] : pick == 2 ? nb[2] : nb[3];
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
         while ((x != ex || y != ey) && spl < 4096) {
             const int k = (int)(((dhi[y] >> (x + kPad)) & 1ull) << 1 | ((dlo[y] >> (x + kPad)) & 1ull));
             x += (k == 1) - (k == 3); y += (k == 2) - (k == 0);
+            if (x < 0 || x >= W || y < 0 || y >= Hh) { x = sx; y = sy; break; }  // unreachable on a connected maze; never walk out of the arrays
             seen[y] |= 1ull << (x + kPad);
             if (spl == 1) { p1x = x; p1y = y; }
             spl++;

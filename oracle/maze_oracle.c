@@ -91,7 +91,7 @@ static uint32_t mt_randbelow(PyMT *r, uint32_t n) { /* Random._randbelow_with_ge
  * carving algorithm (maze.py:170-273) under either stream: MT pins the algorithm against the reference,
  * Philox pins K1 bit-exactly against the oracle.   Draw mapping for the Philox stream (shared with
  * csrc/mm_generate.cuh): word i of the stream = lane (i&3) of Philox(counter=(i>>2,0,0,0), key=(seed_lo ^ id, seed_hi + C)).
- *   random()      -> (float)(w >> 8) * 2^-24  compared in fp32 against an fp32 corridor accumulator
+ *   random()      -> (float)((w >> 8) + 1) * 2^-24 in (0,1], compared in fp32 against an fp32 corridor accumulator
  *   randbelow(n)  -> (uint64)w * n >> 32
  * ------------------------------------------------------------------------------------------------ */
 typedef struct { uint32_t key0, key1; uint32_t ctr; uint32_t buf[4]; int have; } Philox;
@@ -277,7 +277,8 @@ void omaze_build(OMaze *m) { /* maze.py:170-218 */
         int go = 0;
         if (nn) { /* `neighbors and random.random() > corridor_const` short-circuits, maze.py:188 */
             if (m->rng.kind == 0) go = mt_random(&m->rng.mt) > cc;
-            else go = ((float)(philox_u32(&m->rng.px) >> 8) * (1.0f / 16777216.0f)) > ccf;
+            else go = ((float)((philox_u32(&m->rng.px) >> 8) + 1u) * (1.0f / 16777216.0f)) > ccf; /* (0,1]: like random() it never
+                                                                                                   loses against corridor_const == 0 */
         }
         if (go) {
             int nc = nb[rng_below(&m->rng, (uint32_t)nn)]; /* random.choice */

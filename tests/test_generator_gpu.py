@@ -67,3 +67,19 @@ def test_generated_pool_steps_bit_exact_vs_oracle():
         assert np.array_equal(go.cpu().numpy().view(np.uint32), oo.view(np.uint32)), t
         assert np.array_equal(gm.cpu().numpy(), om) and np.array_equal(gr.cpu().numpy(), orr) and np.array_equal(gd.cpu().numpy(), od), t
     assert np.array_equal(eng.agents(), ob.agents())
+
+
+def test_generator_regression_zero_draw_maze():
+    """Maze id whose first carve draw is 0 in 24 bits: a [0,1) mapping stopped the carve at one cell (found at 8 x 1 Mi mazes)."""
+    from marl_maze_b200 import MazeEngine
+    bad = 4 * (1 << 20) + 9 * 65536 + 25010
+    eng = MazeEngine(4, smax=49, max_timestep=100, pool_size=64)
+    eng.generate(2026, side_range=(25, 25), id_base=bad - 10)
+    o = OracleMaze(max_timestep=10, difficulty=1, rand_start=True, rand_sizes=True, rand_range=(25, 25), default_size=(4, 4))
+    for p in range(64):
+        g = eng.pool_maze(p)
+        o.seed_philox(2026, bad - 10 + p); o.build(); m = o.maze()
+        assert np.array_equal(g["layout"], m["layout"]) and g["end"] == m["end"] and g["key"] == m["key"]
+        _check_tree_properties(g)
+        assert int((g["layout"] == 0).sum()) == 1249  # every room carved
+    assert o.error() == 0
