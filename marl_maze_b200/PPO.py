@@ -38,7 +38,7 @@ def _dist():
 class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
-                 verbose: bool = True, micro_batch: int = 1 << 17):
+                 verbose: bool = True, micro_batch: int = 1 << 17, update_tf32: bool = False):
         if agent_amount != 2:
             raise NotImplementedError("two agents (README.md:34)")
         self.maze = None  # injected by Maze.__init__ (maze.py:40-42)
@@ -51,6 +51,7 @@ class PPO:
         self.epochs, self.batch_size, self.lr, self.discount_rate, self.lam = epochs, batch_size, lr, discount_rate, lam
         self.updates_per_batch, self.mbatch_size, self.clip, self.max_grad = updates_per_batch, batch_size // 5, clip, max_grad
         self.horizon, self.seed, self.model_path, self.verbose, self.micro_batch = horizon, seed, model_path, verbose, micro_batch
+        self.update_tf32 = update_tf32  # let cuBLAS use TF32 tensor cores in the autograd update (the reference is fp32; off by default)
         self._runner: Optional[PolicyRunner] = None
         self._rollouts = 0
         self.last_stats: dict = {}
@@ -182,6 +183,14 @@ class PPO:
 
     def update(self, batch):
         """The 5 x 5 minibatch schedule of PPO.train (PPO.py:46-85) on one rollout."""
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.update_tf32)
+        try:
+            return self._update(batch)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _update(self, batch):
         b_obs, b_actions, b_log_probs, _, _, b_masks, b_advs, b_vals = batch
         N = b_obs.shape[0]
         b_rtgs = b_advs + b_vals.detach()

@@ -208,10 +208,25 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
 // Y = relu(X W^T + b) with X given as (x_hi, x_lo) [M][K], W as (w_hi, w_lo) [264][K]; writes (y_hi, y_lo) or plain y into y_hi.
 cudaError_t launch_linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias, float* y_hi, float* y_lo, int M, int K,
                              int split_out, cudaStream_t stream) {
-    TcMaps maps;
-    if (!make_map(&maps.a_hi, x_hi, M, K, TC_BM) || !make_map(&maps.a_lo, x_lo, M, K, TC_BM) || !make_map(&maps.w1_hi, w_hi, TC_N, K, TC_N1) ||
-        !make_map(&maps.w2_hi, w_hi, TC_N, K, TC_N2) || !make_map(&maps.w1_lo, w_lo, TC_N, K, TC_N1) || !make_map(&maps.w2_lo, w_lo, TC_N, K, TC_N2))
-        return cudaErrorInvalidValue;
+    // The rollout calls this with the same scratch / weight pointers every step: keep the encoded maps (a tensor map depends only on
+    // base pointer, extents and box) in a small per-thread cache instead of re-encoding 18 of them per policy step.
+    struct Entry { const float *xh, *xl, *wh, *wl; int M, K; TcMaps maps; };
+    static thread_local Entry cache[8];
+    static thread_local int next_slot = 0;
+    const TcMaps* found = nullptr;
+    for (int i = 0; i < 8; i++)
+        if (cache[i].xh == x_hi && cache[i].xl == x_lo && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].M == M && cache[i].K == K) { found = &cache[i].maps; break; }
+    if (!found) {
+        Entry& e = cache[next_slot];
+        next_slot = (next_slot + 1) % 8;
+        e.xh = nullptr;
+        if (!make_map(&e.maps.a_hi, x_hi, M, K, TC_BM) || !make_map(&e.maps.a_lo, x_lo, M, K, TC_BM) || !make_map(&e.maps.w1_hi, w_hi, TC_N, K, TC_N1) ||
+            !make_map(&e.maps.w2_hi, w_hi, TC_N, K, TC_N2) || !make_map(&e.maps.w1_lo, w_lo, TC_N, K, TC_N1) || !make_map(&e.maps.w2_lo, w_lo, TC_N, K, TC_N2))
+            return cudaErrorInvalidValue;
+        e.xh = x_hi; e.xl = x_lo; e.wh = w_hi; e.wl = w_lo; e.M = M; e.K = K;
+        found = &e.maps;
+    }
+    const TcMaps& maps = *found;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);

@@ -80,3 +80,20 @@ def test_reference_checkpoint_loads_and_matches_kat5():
         mv, mk = actor(x)
     assert np.allclose(mv[0].numpy(), [5.7483, -0.3037, -7.4898, 10.1972, -9.9180], atol=2e-4)
     assert np.allclose(torch.sigmoid(mk).reshape(-1).numpy(), [.5609, .5664, .5459, .5300], atol=2e-4)
+
+
+def test_actor_embedding_dedup_matches_per_row_evaluation():
+    """Large faithful batches evaluate projection+attention once per distinct obs[:, 0:4] prefix; values and gradients must equal
+    the plain per-row evaluation."""
+    from marl_maze_b200.networks import Actor
+    torch.manual_seed(0)
+    actor = Actor([264, 264, 264])
+    obs = torch.rand(6000, 65); obs[:, :4] = torch.eye(4)[torch.randint(0, 4, (6000,))]
+    out = actor(obs)[0].sum() + actor(obs)[1].sum()
+    g1 = torch.autograd.grad(out, list(actor.parameters()), allow_unused=True)
+    small = [actor(obs[i:i + 1000]) for i in range(0, 6000, 1000)]  # below the dedup threshold: per-row path
+    mv = torch.cat([s[0] for s in small]); mk = torch.cat([s[1] for s in small])
+    assert torch.allclose(actor(obs)[0], mv, atol=1e-6) and torch.allclose(actor(obs)[1], mk, atol=1e-6)
+    g2 = torch.autograd.grad(mv.sum() + mk.sum(), list(actor.parameters()), allow_unused=True)
+    for a, b in zip(g1, g2):
+        assert (a is None and b is None) or torch.allclose(a, b, rtol=1e-4, atol=1e-4)
