@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
         const int x = me.x, y = me.y, f = me.dir;
         uint32_t l[11], h[11];  // the window shifted so that column x-5 is bit 0 (the agent's column is bit 5); lo / hi planes
         ulonglong2 dd = make_ulonglong2(0, 0);
-        ulonglong2 wrow = make_ulonglong2(0, 0);  // full-width row holding this agent's pre-move cell (marks are written back through it)
         // Step pass: the 12 in-flight 16-byte rows per lane go global -> shared with cp.async.cg (LDGSTS.BYPASS): they never
         // occupy L1, whose capacity otherwise caps the number of outstanding window loads per SM (profiles/r01_notes.md).
         // Slot = the warp's own observation staging area: [lane][11 rows] then [lane] field row, consumed into registers
@@ -204,13 +203,24 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + y) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
+            // marks of this step (agent 0's first, then agent 1's: maze.py:80-90,132-133), exchanged while the rows are in flight
+            const uint32_t omk = __shfl_xor_sync(kFull, (uint32_t)mk, 1);
+            const int opx = __shfl_xor_sync(kFull, px, 1), opy = __shfl_xor_sync(kFull, py, 1);
+            const bool m0 = a ? (omk != 0) : mk, m1 = a ? mk : (omk != 0);
+            const int m0x = a ? opx : px, m0y = a ? opy : py, m1x = a ? px : opx, m1y = a ? py : opy;
             asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (act) {  // apply both marks to this lane's private copy of its window rows (dynamic row index = plain smem addressing)
+                const int r0 = m0y - y + kPad, r1 = m1y - y + kPad;
+                if (m0 && r0 >= 0 && r0 <= 10) { ulonglong2 v = slot[r0]; const unsigned long long bit = 1ull << (m0x + kPad); v.y |= bit; v.x &= ~bit; slot[r0] = v; }  // tag 2
+                if (m1 && r1 >= 0 && r1 <= 10) { ulonglong2 v = slot[r1]; const unsigned long long bit = 1ull << (m1x + kPad); v.y |= bit; v.x |= bit; slot[r1] = v; }   // tag 3
+                if (mk) p.env_grid[(size_t)e * p.rows + py + kPad] = slot[py - y + kPad];  // the marked row goes back to HBM with both marks applied
+                dd = *dslot;
+            }
 #pragma unroll
             for (int r = 0; r < 11; r++) {
                 const ulonglong2 v = act ? slot[r] : make_ulonglong2(~0ull, 0ull);
                 l[r] = (uint32_t)(v.x >> x); h[r] = (uint32_t)(v.y >> x);
             }
-            if (act) { dd = *dslot; if (mk) wrow = slot[py - y + kPad]; }
             __syncwarp();  // every lane has its window in registers; the area may now receive observation floats
         } else {
             const ulonglong2* grid = pass == 0 ? (const ulonglong2*)(p.env_grid + (size_t)e * p.rows) : (p.pool_grid + (size_t)pidx * p.rows);
@@ -222,28 +232,6 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
             if (act) dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
         }
         const int d2e_here = (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
-
-        // ------------------------------------------------------------ marks of this step (agent 0's first, maze.py:80-90,132-133)
-        if (pass == 0) {
-            const uint32_t omk = __shfl_xor_sync(kFull, (uint32_t)mk, 1);
-            const int opx = __shfl_xor_sync(kFull, px, 1), opy = __shfl_xor_sync(kFull, py, 1);
-            const bool m0 = a ? (omk != 0) : mk, m1 = a ? mk : (omk != 0);
-            const int m0x = a ? opx : px, m0y = a ? opy : py, m1x = a ? px : opx, m1y = a ? py : opy;
-            {   // tag 2: hi=1, lo=0 ; then tag 3: hi=1, lo=1 -- on the shifted window (columns outside it cannot be seen)
-                const int c0 = m0x - x + kPad, r0 = m0y - y + kPad, c1 = m1x - x + kPad, r1 = m1y - y + kPad;
-                const uint32_t b0 = (m0 && c0 >= 0 && c0 <= 10) ? (1u << c0) : 0u, b1 = (m1 && c1 >= 0 && c1 <= 10) ? (1u << c1) : 0u;
-#pragma unroll
-                for (int r = 0; r < 11; r++) {
-                    if (r0 == r) { h[r] |= b0; l[r] &= ~b0; }
-                    if (r1 == r) { h[r] |= b1; l[r] |= b1; }
-                }
-            }
-            if (mk && act) {  // the marked row (pre-move cell) goes back to HBM with both marks applied, in order
-                if (m0 && m0y == py) { const unsigned long long bit = 1ull << (m0x + kPad); wrow.y |= bit; wrow.x &= ~bit; }
-                if (m1 && m1y == py) { const unsigned long long bit = 1ull << (m1x + kPad); wrow.y |= bit; wrow.x |= bit; }
-                p.env_grid[(size_t)e * p.rows + py + kPad] = wrow;
-            }
-        }
 
         // ------------------------------------------------------------ per-direction bit masks (abs 0 N, 1 E, 2 S, 3 W)
         uint32_t l5, h5, wl4, wl5, wl6;
@@ -436,10 +424,24 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
     const int wbase = tid & ~31;
     const long long gbase = g - lane;
     if (wmask == kFull && p.obs_vec4) {
+#ifdef MM_K2_LSU_COPYOUT
         const float4* s4 = reinterpret_cast<const float4*>(s_obs + wbase * kObs);
         float4* o4 = reinterpret_cast<float4*>(p.obs + gbase * kObs);
 #pragma unroll 4
         for (int i = lane; i < 32 * kObs / 4; i += 32) __stcs(&o4[i], s4[i]);
+#else
+        // the warp's 32 x 65 floats are one contiguous 8320-byte run in the rollout buffer: hand it to the bulk-copy engine
+        // (cp.async.bulk shared -> global, one instruction) instead of 16 LDS.128 + STG.128 per lane
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy STS above -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.obs + gbase * kObs),
+                         "r"((uint32_t)__cvta_generic_to_shared(s_obs + wbase * kObs)), "r"(32 * kObs * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+        }
+#endif
     } else {
         for (uint32_t m = wmask; m; m &= m - 1) {
             const int L = __ffs(m) - 1;
