@@ -24,6 +24,15 @@ constexpr int kThreads = MM_K2_THREADS;
 #ifndef MM_K2_MINBLOCKS
 #define MM_K2_MINBLOCKS 4
 #endif
+#ifndef MM_K2_MINBLOCKS2
+#define MM_K2_MINBLOCKS2 3
+#endif
+// Groups of 32 agents a warp carries through the kernel.  2 = software-pipelined (both groups' loads in flight before the first
+// observation phase).  Measured on B200 (profiles/r01_notes.md): 0.246 ms vs 0.232 ms for 1 -- at 1.1 GB of mostly sector-granular
+// DRAM traffic per launch the memory system, not exposed latency, is the limiter, and the pipelined form costs a block of occupancy.
+#ifndef MM_K2_GROUPS
+#define MM_K2_GROUPS 1
+#endif
 
 // One axis ray seen from the agent.  cw: bit j-1 = wall (or out of bounds) at distance j, j = 1..5.
 // latopen: bit j-1 = a cell left or right of the ray cell at distance j is open, j = 1..4.
@@ -64,15 +73,28 @@ __device__ __forceinline__ float idiv_rcp(float fa, float fb, float rcp) {
 }
 __device__ __forceinline__ float fdiv(int a, int b) { const float fb = (float)b; return idiv_rcp((float)a, fb, __frcp_rn(fb)); }
 
-template <bool kResetOnly>
-__global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const StepParams p) {
-    extern __shared__ __align__(16) float s_obs[];  // [kThreads][65]
-    const int tid = threadIdx.x, lane = tid & 31;
-    const long long g = (long long)blockIdx.x * kThreads + tid;  // global agent index
-    const int e = (int)(g >> 1);
-    const int a = (int)(g & 1);  // 0 = tag 2 (RED), 1 = tag 3 (BLUE), main.py:18-19
-    const bool valid = e < p.E;
+// Everything one lane carries from the step phase to the observation phase.
+struct LaneCtx {
+    long long g;      // global agent index
+    int e, a;         // environment, agent (0 = tag 2 RED, 1 = tag 3 BLUE; main.py:18-19)
+    bool valid;
+    Agent me;
+    uint32_t t, keyp, err, pidx;
+    int W, Hh, ex, ey, kx, ky;
+    float reward;
+    uint32_t done;
+    bool mk;          // this agent marked its (pre-move) cell this step
+    int px, py;       // pre-move cell
+    bool want_reset;
+    float* stage;     // this warp's 32 x 65-float staging area in shared memory (doubles as the landing zone of the window rows)
+};
 
+// Phase 1: load state, S1 (Maze.step / single_agent_step), reward/done, and put the window rows of the NEW position in flight.
+template <bool kResetOnly>
+__device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const int lane) {
+    const long long g = c.g;
+    const int e = c.e, a = c.a;
+    const bool valid = c.valid;
     uint4 H = make_uint4(0, 0, 0, 0), A = make_uint4(0, 0, 0, 0);
     uint32_t B = 0;
     if (valid) { H = p.env_hdr[e]; A = p.agent_a[g]; B = p.agent_b[g]; }
@@ -146,6 +168,42 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
         want_reset = valid && done && p.auto_reset;
     }
 
+
+    if (!kResetOnly) {
+        // the 12 in-flight 16-byte rows per lane go global -> shared with cp.async.cg (LDGSTS.BYPASS): they never occupy L1, whose
+        // capacity otherwise caps the number of outstanding window loads per SM (profiles/r01_notes.md).  Landing zone = the warp's
+        // own observation staging area: [lane][11 rows] then [lane] field row.
+        char* wbase_s = reinterpret_cast<char*>(c.stage);
+        if (valid) {
+            const ulonglong2* grid = (const ulonglong2*)(p.env_grid + (size_t)e * p.rows);
+            const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(wbase_s + lane * 176), s1 = (uint32_t)__cvta_generic_to_shared(wbase_s + 32 * 176 + lane * 16);
+#pragma unroll
+            for (int r = 0; r < 11; r++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16 * r), "l"(grid + me.y + r) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + me.y) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    c.me = me; c.t = t; c.keyp = keyp; c.err = err; c.pidx = pidx; c.W = W; c.Hh = Hh; c.ex = ex; c.ey = ey; c.kx = kx; c.ky = ky;
+    c.reward = reward; c.done = done; c.mk = mk; c.px = px; c.py = py; c.want_reset = want_reset;
+}
+
+// Phase 2: S3-S5 (observations, masks, exit_ready override), optional in-launch reset, state write-back, observation copy-out.
+// kPending = number of younger cp.async groups that may still be in flight when this group's rows are needed.
+template <bool kResetOnly, int kPending>
+__device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const int lane) {
+    const long long g = c.g;
+    const int e = c.e, a = c.a;
+    const bool valid = c.valid;
+    Agent me = c.me;
+    uint32_t t = c.t, keyp = c.keyp, err = c.err, pidx = c.pidx;
+    int W = c.W, Hh = c.Hh, ex = c.ex, ey = c.ey, kx = c.kx, ky = c.ky;
+    const float reward = c.reward;
+    const uint32_t done = c.done;
+    const bool mk = c.mk;
+    const int px = c.px, py = c.py;
+    const bool want_reset = c.want_reset;
+    float* const stage = c.stage;
+
     bool wrote = false;
 #pragma unroll 1
     for (int pass = kResetOnly ? 1 : 0; pass < 2; ++pass) {
@@ -186,29 +244,19 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
         const int x = me.x, y = me.y, f = me.dir;
         uint32_t l[11], h[11];  // the window shifted so that column x-5 is bit 0 (the agent's column is bit 5); lo / hi planes
         ulonglong2 dd = make_ulonglong2(0, 0);
-        // Step pass: the 12 in-flight 16-byte rows per lane go global -> shared with cp.async.cg (LDGSTS.BYPASS): they never
-        // occupy L1, whose capacity otherwise caps the number of outstanding window loads per SM (profiles/r01_notes.md).
-        // Slot = the warp's own observation staging area: [lane][11 rows] then [lane] field row, consumed into registers
-        // before any lane writes observation floats there (the __syncwarp below).  The (rare) reset pass must not touch
-        // that area -- it already holds the step-pass observations of the lanes that are not resetting -- and loads directly.
+        // Step pass: the rows were put in flight by phase 1 into this warp's staging area; they are consumed into registers before
+        // any lane writes observation floats there (the __syncwarp below).  The (rare) reset pass must not touch that area -- it
+        // already holds the step-pass observations of the lanes that are not resetting -- and loads directly.
         if (pass == 0 && !kResetOnly) {
-            char* wbase_s = reinterpret_cast<char*>(s_obs + (tid & ~31) * kObs);
+            char* wbase_s = reinterpret_cast<char*>(stage);
             ulonglong2* slot = reinterpret_cast<ulonglong2*>(wbase_s + lane * 176);
             ulonglong2* dslot = reinterpret_cast<ulonglong2*>(wbase_s + 32 * 176 + lane * 16);
-            if (act) {
-                const ulonglong2* grid = (const ulonglong2*)(p.env_grid + (size_t)e * p.rows);
-                const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(slot), s1 = (uint32_t)__cvta_generic_to_shared(dslot);
-#pragma unroll
-                for (int r = 0; r < 11; r++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16 * r), "l"(grid + y + r) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + y) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
             // marks of this step (agent 0's first, then agent 1's: maze.py:80-90,132-133), exchanged while the rows are in flight
             const uint32_t omk = __shfl_xor_sync(kFull, (uint32_t)mk, 1);
             const int opx = __shfl_xor_sync(kFull, px, 1), opy = __shfl_xor_sync(kFull, py, 1);
             const bool m0 = a ? (omk != 0) : mk, m1 = a ? mk : (omk != 0);
             const int m0x = a ? opx : px, m0y = a ? opy : py, m1x = a ? px : opx, m1y = a ? py : opy;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
             if (act) {  // apply both marks to this lane's private copy of its window rows (dynamic row index = plain smem addressing)
                 const int r0 = m0y - y + kPad, r1 = m1y - y + kPad;
                 if (m0 && r0 >= 0 && r0 <= 10) { ulonglong2 v = slot[r0]; const unsigned long long bit = 1ull << (m0x + kPad); v.y |= bit; v.x &= ~bit; slot[r0] = v; }  // tag 2
@@ -353,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
 #ifdef MM_K2_DIRECT_STORE
             float* so = p.obs + g * kObs;  // experiment: no shared-memory staging (uncoalesced 4-byte stores)
 #else
-            float* so = s_obs + tid * kObs;
+            float* so = stage + lane * kObs;
 #endif
             const uint32_t OWNr = __funnelshift_r(OWN32, OWN32, 8 * f), OTHr = __funnelshift_r(OTH32, OTH32, 8 * f);
             const uint32_t keyr = visK ? (1u << rK) : 0u;
@@ -421,11 +469,10 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
 #ifndef MM_K2_DIRECT_STORE
     __syncwarp();
     const uint32_t wmask = __ballot_sync(kFull, wrote);
-    const int wbase = tid & ~31;
     const long long gbase = g - lane;
     if (wmask == kFull && p.obs_vec4) {
 #ifdef MM_K2_LSU_COPYOUT
-        const float4* s4 = reinterpret_cast<const float4*>(s_obs + wbase * kObs);
+        const float4* s4 = reinterpret_cast<const float4*>(stage);
         float4* o4 = reinterpret_cast<float4*>(p.obs + gbase * kObs);
 #pragma unroll 4
         for (int i = lane; i < 32 * kObs / 4; i += 32) __stcs(&o4[i], s4[i]);
@@ -436,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
         __syncwarp();
         if (lane == 0) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.obs + gbase * kObs),
-                         "r"((uint32_t)__cvta_generic_to_shared(s_obs + wbase * kObs)), "r"(32 * kObs * 4)
+                         "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(32 * kObs * 4)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
@@ -445,12 +492,31 @@ __global__ void __launch_bounds__(kThreads, MM_K2_MINBLOCKS) k_step_obs(const St
     } else {
         for (uint32_t m = wmask; m; m &= m - 1) {
             const int L = __ffs(m) - 1;
-            const float* s = s_obs + (wbase + L) * kObs;
+            const float* s = stage + L * kObs;
             float* o = p.obs + (gbase + L) * kObs;
             for (int i = lane; i < kObs; i += 32) o[i] = s[i];
         }
     }
 #endif
+}
+
+// kGroups = 2: every warp carries TWO groups of 32 agents through the kernel, software-pipelined -- both groups' state loads and
+// window rows are in flight before the first observation phase starts, so the second DRAM round trip of group A hides behind
+// the step phase of group B, and B's behind A's whole observation phase.
+template <bool kResetOnly, int kGroups>
+__global__ void __launch_bounds__(kThreads, kGroups == 2 ? MM_K2_MINBLOCKS2 : MM_K2_MINBLOCKS) k_step_obs(const StepParams p) {
+    extern __shared__ __align__(16) float s_obs[];  // [kGroups][kThreads][65]
+    const int tid = threadIdx.x, lane = tid & 31;
+    LaneCtx c[kGroups];
+#pragma unroll
+    for (int gi = 0; gi < kGroups; gi++) {
+        c[gi].g = ((long long)blockIdx.x * kGroups + gi) * kThreads + tid;
+        c[gi].e = (int)(c[gi].g >> 1); c[gi].a = (int)(c[gi].g & 1); c[gi].valid = c[gi].e < p.E;
+        c[gi].stage = s_obs + (gi * kThreads + (tid & ~31)) * kObs;
+        k2_phase1<kResetOnly>(p, c[gi], lane);
+    }
+    if (kGroups == 2) { k2_phase2<kResetOnly, 1>(p, c[0], lane); k2_phase2<kResetOnly, 0>(p, c[kGroups - 1], lane); }
+    else k2_phase2<kResetOnly, 0>(p, c[0], lane);
 }
 
 __global__ void k_selftest_div(int amax, int bmax, unsigned long long* mismatches) {
@@ -468,17 +534,23 @@ cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatch
 
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream) {
     const long long agents = 2ll * p.E;
-    const int blocks = (int)((agents + kThreads - 1) / kThreads);
-#ifdef MM_K2_DIRECT_STORE
-    const size_t smem = 0;
-#else
-    const size_t smem = (size_t)kThreads * kObs * sizeof(float);
-#endif
-    if (blocks == 0) return cudaSuccess;
-    // NOTE (measured, profiles/r01_notes.md): forcing the maximum shared-memory carveout halves throughput -- the L1 capacity left
-    // over is what buffers in-flight window loads -- so the driver's default carveout is kept.
-    if (reset_only) k_step_obs<true><<<blocks, kThreads, smem, stream>>>(p);
-    else k_step_obs<false><<<blocks, kThreads, smem, stream>>>(p);
+    if (agents == 0) return cudaSuccess;
+    // NOTE (measured, profiles/r01_notes.md): forcing the maximum shared-memory carveout halves throughput, so the driver's default is kept.
+    if (reset_only) {
+        const int blocks = (int)((agents + kThreads - 1) / kThreads);
+        k_step_obs<true, 1><<<blocks, kThreads, (size_t)kThreads * kObs * sizeof(float), stream>>>(p);
+    } else {
+        constexpr int G = MM_K2_GROUPS;
+        const size_t smem = (size_t)G * kThreads * kObs * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_step_obs<false, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        const int blocks = (int)((agents + (long long)G * kThreads - 1) / ((long long)G * kThreads));
+        k_step_obs<false, G><<<blocks, kThreads, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
