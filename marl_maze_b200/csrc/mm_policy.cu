@@ -26,6 +26,7 @@ struct PolicyOffsets {
     int c0_w, c0_b, c1_w, c1_b, c2_w, c2_b;  // critic [64][130],[64],[64][64],[64],[1][64],[1]
     int l0_whi, l0_wlo, l1_whi, l1_wlo, l2_whi, l2_wlo;  // TF32 hi/lo splits of the three trunk weights (tensor-core path)
     int c0_wt, c1_wt;                                    // critic weights transposed: [130][64], [64][64] (coalesced lane = neuron reads)
+    int tokm, tokb;                                      // per-token affine maps [60][23][4], [60][23]: rows 0-19 token, 20-29 key, 30-39 query, 40-59 value
     int total;
 };
 __host__ __device__ inline PolicyOffsets policy_offsets() {
@@ -39,65 +40,69 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
     o.l0_whi = take(kHid * kX0); o.l0_wlo = take(kHid * kX0); o.l1_whi = take(kHid * kHid); o.l1_wlo = take(kHid * kHid);
     o.l2_whi = take(kHid * kHid); o.l2_wlo = take(kHid * kHid);
     o.c0_wt = take(130 * kCH); o.c1_wt = take(kCH * kCH);
+    o.tokm = take(60 * kTok * 4); o.tokb = take(60 * kTok);
     o.total = p;
     return o;
 }
 
 // ------------------------------------------------------------------------------------------------ tokens + attention
-// One warp per row, one LANE per feature token (23 of 32 lanes active): the lane keeps its token, query and context in
-// registers; keys / values of the row's 23 tokens are exchanged through a small per-warp shared-memory tile (broadcast reads);
-// the tiny weights (K, Q, V, projections) are staged once per block in shared memory and read as broadcast float4.
-constexpr int kTokWarps = 8;
+// One warp per row, one LANE per feature token (23 of 32 lanes active).  A token is an affine map of <= 4 observation columns
+// (networks.py:58-65), so its key, query and value are too: the host folds Wk, Wq, Wv into per-token [60 x 4] maps (rows 0-19
+// token, 20-29 key, 30-39 query, 40-59 value) and the lane evaluates all 60 outputs with 240 FMAs instead of 80 + 800.  Keys and
+// values of the row's 23 tokens are exchanged through a small per-warp shared-memory tile (broadcast reads).
+constexpr int kTokWarps = 4;
 template <bool kSplit>  // kSplit: write x0 as the TF32 pair (hi, lo) for the tensor-core trunk
 __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0,
                                                          float* __restrict__ x0_lo, int R) {
     const PolicyOffsets o = policy_offsets();
-    __shared__ __align__(16) float s_wkqv[40][kEmb];           // rows 0-9 keys, 10-19 querys, 20-39 values
-    __shared__ __align__(16) float s_pw[kTok][kEmb][4];
-    __shared__ float s_pb[kTok][kEmb];
+    __shared__ __align__(16) float s_m[60][kTok][4];
+    __shared__ float s_b[60][kTok];
     __shared__ __align__(16) float s_k[kTokWarps][kTok][12], s_v[kTokWarps][kTok][kEmb];
-    for (int i = threadIdx.x; i < 10 * kEmb; i += blockDim.x) { (&s_wkqv[0][0])[i] = wts[o.att_k + i]; (&s_wkqv[10][0])[i] = wts[o.att_q + i]; }
-    for (int i = threadIdx.x; i < kEmb * kEmb; i += blockDim.x) (&s_wkqv[20][0])[i] = wts[o.att_v + i];
-    for (int i = threadIdx.x; i < kTok * kEmb * 4; i += blockDim.x) (&s_pw[0][0][0])[i] = wts[o.proj_w + i];
-    for (int i = threadIdx.x; i < kTok * kEmb; i += blockDim.x) (&s_pb[0][0])[i] = wts[o.proj_b + i];
+    for (int i = threadIdx.x; i < 60 * kTok * 4; i += blockDim.x) (&s_m[0][0][0])[i] = wts[o.tokm + i];
+    for (int i = threadIdx.x; i < 60 * kTok; i += blockDim.x) (&s_b[0][0])[i] = wts[o.tokb + i];
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kTokWarps + w;
     if (row >= R) return;
     const bool on = lane < kTok;
     const int a = on ? lane : 0;
-    float tok[kEmb], q[kKQ];
-    {   // projection of this token: <= 4 observation columns (networks.py:58-65)
+    float x[4];
+    {
         const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
-        float x[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) x[c] = (c < nd) ? obs[(size_t)row * kObs + c0 + c] : 0.f;
+    }
+    auto affine = [&](int j) {
+        const float4 m = *reinterpret_cast<const float4*>(&s_m[j][a][0]);
+        return fmaf(x[3], m.w, fmaf(x[2], m.z, fmaf(x[1], m.y, fmaf(x[0], m.x, s_b[j][a]))));
+    };
+    {   // keys and values go straight to the row's shared tile
+        float kk[kKQ], vv[kEmb];
 #pragma unroll
-        for (int d = 0; d < kEmb; d++) {
-            const float4 pw = *reinterpret_cast<const float4*>(&s_pw[a][d][0]);
-            tok[d] = fmaf(x[3], pw.w, fmaf(x[2], pw.z, fmaf(x[1], pw.y, fmaf(x[0], pw.x, s_pb[a][d]))));
+        for (int d = 0; d < kKQ; d++) kk[d] = affine(20 + d);
+#pragma unroll
+        for (int d = 0; d < kEmb; d++) vv[d] = affine(40 + d);
+        if (on) {
+#pragma unroll
+            for (int d = 0; d < kKQ; d++) s_k[w][a][d] = kk[d];
+#pragma unroll
+            for (int d4 = 0; d4 < kEmb / 4; d4++) *reinterpret_cast<float4*>(&s_v[w][a][4 * d4]) = make_float4(vv[4 * d4], vv[4 * d4 + 1], vv[4 * d4 + 2], vv[4 * d4 + 3]);
         }
     }
+    float q[kKQ];
 #pragma unroll
-    for (int j = 0; j < 40; j++) {  // keys, querys, values of this token
-        float acc = 0.f;
-#pragma unroll
-        for (int d4 = 0; d4 < kEmb / 4; d4++) {
-            const float4 wv = *reinterpret_cast<const float4*>(&s_wkqv[j][4 * d4]);
-            acc = fmaf(tok[4 * d4 + 3], wv.w, fmaf(tok[4 * d4 + 2], wv.z, fmaf(tok[4 * d4 + 1], wv.y, fmaf(tok[4 * d4], wv.x, acc))));
-        }
-        if (j < kKQ) { if (on) s_k[w][a][j] = acc; }
-        else if (j < 2 * kKQ) q[j - kKQ] = acc;
-        else if (on) s_v[w][a][j - 2 * kKQ] = acc;
-    }
+    for (int d = 0; d < kKQ; d++) q[d] = affine(30 + d);
     __syncwarp();
     float p[kTok];
     float m = -INFINITY;
 #pragma unroll
-    for (int b = 0; b < kTok; b++) {  // scores against every key of the row (networks.py:79)
-        float acc = 0.f;
-#pragma unroll
-        for (int d = 0; d < kKQ; d++) acc = fmaf(q[d], s_k[w][b][d], acc);
+    for (int b = 0; b < kTok; b++) {  // scores of this token's query against every key of the row (networks.py:79)
+        const float4 k0 = *reinterpret_cast<const float4*>(&s_k[w][b][0]), k1 = *reinterpret_cast<const float4*>(&s_k[w][b][4]);
+        const float2 k2 = *reinterpret_cast<const float2*>(&s_k[w][b][8]);
+        float acc = q[0] * k0.x;
+        acc = fmaf(q[1], k0.y, acc); acc = fmaf(q[2], k0.z, acc); acc = fmaf(q[3], k0.w, acc);
+        acc = fmaf(q[4], k1.x, acc); acc = fmaf(q[5], k1.y, acc); acc = fmaf(q[6], k1.z, acc); acc = fmaf(q[7], k1.w, acc);
+        acc = fmaf(q[8], k2.x, acc); acc = fmaf(q[9], k2.y, acc);
         p[b] = acc * 0.31622776601683794f;  // 1/sqrt(10)
         m = fmaxf(m, p[b]);
     }
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restri
             float v[4], hi[4], lo[4];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                v[c] = tok[4 * d4 + c] + ctx[4 * d4 + c];
+                v[c] = affine(4 * d4 + c) + ctx[4 * d4 + c];  // the token itself, evaluated last to keep it out of the register budget above
                 hi[c] = kSplit ? tf32_rn(v[c]) : v[c];
                 lo[c] = kSplit ? tf32_rn(v[c] - hi[c]) : 0.f;
             }
@@ -290,7 +295,7 @@ int policy_offsets_host(int32_t* out) {
     const PolicyOffsets o = policy_offsets();
     const int v[32] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
                        o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, o.l0_whi, o.l0_wlo, o.l1_whi, o.l1_wlo, o.l2_whi, o.l2_wlo,
-                       o.c0_wt, o.c1_wt, 0, 0};
+                       o.c0_wt, o.c1_wt, o.tokm, o.tokb};
     for (int i = 0; i < 32; i++) out[i] = v[i];
     return 0;
 }

@@ -16,7 +16,16 @@
 
 namespace mm {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_N1 = 144, TC_N2 = 128, TC_N = 264, TC_STAGES = 2;
+#ifndef MM_TC_BK
+#define MM_TC_BK 32
+#endif
+#ifndef MM_TC_STAGES
+#define MM_TC_STAGES 2
+#endif
+constexpr int TC_BM = 128, TC_BK = MM_TC_BK, TC_N1 = 144, TC_N2 = 128, TC_N = 264, TC_STAGES = MM_TC_STAGES;
+constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                       // one K-block row: 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
+constexpr uint32_t TC_ATOM_BYTES = 8 * TC_ROW_BYTES;               // 8-row swizzle atom = stride byte offset of the UMMA descriptor
+constexpr uint64_t TC_LAYOUT = TC_BK == 32 ? 2ull : 4ull;          // cute::UMMA::LayoutType SWIZZLE_128B / SWIZZLE_64B
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
 constexpr uint32_t TC_B1_BYTES = TC_N1 * TC_BK * 4;   // 18432
 constexpr uint32_t TC_B2_BYTES = TC_N2 * TC_BK * 4;   // 16384
@@ -49,7 +58,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 1024 bytes.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(TC_ATOM_BYTES >> 4) << 32) | ((uint64_t)1 << 46) | (TC_LAYOUT << 61);
 }
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
@@ -138,39 +147,51 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     } else {
         // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31; one thread = one output row
         const int quarter = warp & 3;
-        const int row = m0 + quarter * 32 + lane;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // The accumulator row of a lane is scattered over rows of Y (stride 1056 B): storing straight from registers costs 32
+        // half-written sectors per instruction (measured: half of the kernel's time).  Each warp therefore transposes 32x32 blocks
+        // through shared memory -- the pipeline stages are free once tmem_full has fired -- and writes whole 128-byte row segments.
+        constexpr int kTP = 36;  // padded row pitch (floats): 16-byte aligned, conflict-free for the quarter-warp float4 patterns below
+        float* t_hi = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 2 * 32 * kTP;
+        float* t_lo = t_hi + 32 * kTP;
+        const int row0 = m0 + quarter * 32;
 #pragma unroll 1
-        for (int c = 0; c < 17; c++) {
-            uint32_t v[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(taddr + (uint32_t)(c * 16)));
+        for (int c = 0; c < 9; c++) {  // 9 x 32 columns >= 264
+            uint32_t v[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                  "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                  "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr + (uint32_t)(c * 32)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                const int ncol = (c == 16) ? 8 : 16;  // 264 = 16*16 + 8
-                float hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int col = c * 16 + j;
-                    float yv = __uint_as_float(v[j]) + (col < TC_N ? bias[col] : 0.f);
+            for (int q = 0; q < 8; q++) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int col = c * 32 + 4 * q + j;
+                    float yv = __uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f);
                     yv = fmaxf(yv, 0.f);
                     if (split_out) { hi[j] = tf32_rn(yv); lo[j] = tf32_rn(yv - hi[j]); }
                     else { hi[j] = yv; lo[j] = 0.f; }
                 }
-                float4* ph = reinterpret_cast<float4*>(y_hi + (size_t)row * TC_N + c * 16);
-                float4* pl = reinterpret_cast<float4*>(y_lo + (size_t)row * TC_N + c * 16);
+                *reinterpret_cast<float4*>(&t_hi[lane * kTP + 4 * q]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (split_out) *reinterpret_cast<float4*>(&t_lo[lane * kTP + 4 * q]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (q * 4 < ncol) {
-                        ph[q] = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                        if (split_out) pl[q] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                    }
+            for (int it = 0; it < 8; it++) {  // 4 rows x 128 contiguous bytes per instruction
+                const int r = it * 4 + (lane >> 3), c4 = lane & 7;
+                const int col = c * 32 + 4 * c4;
+                if (row0 + r < M && col < TC_N) {
+                    *reinterpret_cast<float4*>(y_hi + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_hi[r * kTP + 4 * c4]);
+                    if (split_out) *reinterpret_cast<float4*>(y_lo + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_lo[r * kTP + 4 * c4]);
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -201,7 +222,8 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
     cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

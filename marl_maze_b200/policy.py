@@ -14,7 +14,7 @@ from . import _abi
 from .networks import FEATURE_DIMS, EMBEDDING_DIM
 
 _NAMES = ["proj_w", "proj_b", "proj_col", "proj_dim", "att_k", "att_q", "att_v", "l0_w", "l0_b", "l1_w", "l1_b", "l2_w", "l2_b",
-          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo", "c0_wt", "c1_wt"]
+          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo", "c0_wt", "c1_wt", "tokm", "tokb"]
 
 
 def offsets() -> dict:
@@ -61,6 +61,13 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
         for i in range(3):
             put(f"c{i}_w", critic.layers[i].weight); put(f"c{i}_b", critic.layers[i].bias)
         put("c0_wt", critic.layers[0].weight.t().contiguous()); put("c1_wt", critic.layers[1].weight.t().contiguous())
+        # per-token affine maps: [token; key; query; value] = [I; Wk; Wq; Wv] (P_a x + b_a) -> rows 0-19, 20-29, 30-39, 40-59
+        att = actor.attention
+        stack = torch.cat([torch.eye(EMBEDDING_DIM, device=dev), att.keys.weight.detach().to(dev, torch.float32),
+                           att.querys.weight.detach().to(dev, torch.float32), att.values.weight.detach().to(dev, torch.float32)], 0).double()  # [60,20]
+        tokm = torch.einsum("jd,adc->jac", stack, pw.double()).float()                       # [60,23,4]
+        tokb = (stack @ torch.stack([l.bias.detach().to(dev) for l in actor.projection.layers], 0).double().t()).float()  # [60,23]
+        put("tokm", tokm.contiguous()); put("tokb", tokb.contiguous())
     return buf
 
 

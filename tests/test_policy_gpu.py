@@ -11,6 +11,10 @@ from oracle import ppo_oracle as po
 
 pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-5, atol=2e-6)
+# Raw LOGITS of the tensor-core path: tcgen05 accumulates its K = 460/264-long sums with truncation inside the tensor core, which
+# leaves ~1e-6 relative (max 4e-6 absolute, tools/k4_accuracy.py) on the logits -- 10x the fp32 SIMT path, still far inside the
+# north-star bar on the quantities it names (log-probs and values: 1e-5 relative, asserted with TOL for BOTH paths below).
+TOL_LOGITS = {False: TOL, True: dict(rtol=1e-5, atol=8e-6)}
 
 
 def _nets(seed, faithful=True):
@@ -33,8 +37,8 @@ def test_policy_kernel_vs_reference_golden(seed, tc):
     logits = torch.zeros(E, 2, 6, device="cuda")
     _, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), actions_in=torch.from_numpy(acts).cuda(), logits=logits)
     lg = logits.cpu().numpy()
-    assert np.allclose(lg[:, :, :5].reshape(-1, 5), Z[f"net/{seed}/move_logits"], **TOL)
-    assert np.allclose(lg[:, :, 5].reshape(-1, 1), Z[f"net/{seed}/mark_logits"], **TOL)
+    assert np.allclose(lg[:, :, :5].reshape(-1, 5), Z[f"net/{seed}/move_logits"], **TOL_LOGITS[tc])
+    assert np.allclose(lg[:, :, 5].reshape(-1, 1), Z[f"net/{seed}/mark_logits"], **TOL_LOGITS[tc])
     assert np.allclose(val.cpu().numpy(), Z[f"net/{seed}/values"].reshape(-1), **TOL)
     want = Z[f"net/{seed}/log_probs"].sum(1)  # joint log-prob, PPO.py:118,121
     fin = np.isfinite(want)
@@ -56,7 +60,7 @@ def test_policy_kernel_vs_oracle_random_obs_and_sampling(faithful, tc):
     act, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), logits=logits)
     act = act.cpu().numpy()
     mv, mk = po.actor_forward(asd, obs.reshape(-1, 65), faithful=faithful)
-    assert np.allclose(logits.cpu().numpy()[:, :, :5].reshape(-1, 5), mv, **TOL) and np.allclose(logits.cpu().numpy()[:, :, 5].reshape(-1, 1), mk, **TOL)
+    assert np.allclose(logits.cpu().numpy()[:, :, :5].reshape(-1, 5), mv, **TOL_LOGITS[tc]) and np.allclose(logits.cpu().numpy()[:, :, 5].reshape(-1, 1), mk, **TOL_LOGITS[tc])
     assert np.allclose(val.cpu().numpy(), po.critic_forward(csd, obs).reshape(-1), **TOL)
     # sampled actions are mask-legal and their log-prob is the oracle's
     assert np.take_along_axis(masks[:, :, :5], act[:, :, :1].astype(np.int64), 2).all() and (act[:, :, 1] <= masks[:, :, 5]).all()
