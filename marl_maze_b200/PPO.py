@@ -141,6 +141,17 @@ class PPO:
         p = torch.where(marks.bool(), p, 1 - p)
         return lp_move + torch.log(p)
 
+    def joint_log_probs(self, batch_obs, batch_actions, batch_masks):
+        """sum_i get_log_probs(i, ...) (PPO.py:66-68) with BOTH agents pushed through the shared actor in one batch of 2B rows."""
+        B = batch_obs.shape[0]
+        move_logits, mark_logits = self.actor(batch_obs.reshape(2 * B, -1))
+        masks = batch_masks.reshape(2 * B, 6)
+        acts = batch_actions.reshape(2 * B, 2)
+        lp_move = torch.log_softmax(move_logits.masked_fill(~masks[:, 0:5], float("-inf")), dim=-1).gather(1, acts[:, 0:1].long()).squeeze(1)
+        p = torch.sigmoid(mark_logits.reshape(-1).masked_fill(~masks[:, 5], float("-inf")))
+        p = torch.where(acts[:, 1].bool(), p, 1 - p)
+        return (lp_move + torch.log(p)).view(B, 2).sum(1)
+
     def get_state_values(self, batch_obs):
         return self.critic(batch_obs).squeeze(-1)
 
@@ -210,7 +221,7 @@ class PPO:
                 for s0 in range(0, n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
                     j = idx[s0:s0 + self.micro_batch]
                     m_obs, m_act, m_masks = b_obs[j], b_actions[j], b_masks[j]
-                    cur = self.get_log_probs(0, m_obs, m_act, m_masks) + self.get_log_probs(1, m_obs, m_act, m_masks)
+                    cur = self.joint_log_probs(m_obs, m_act, m_masks)
                     ratio = torch.exp(cur - b_log_probs[j])
                     adv = b_advs[j]
                     loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n

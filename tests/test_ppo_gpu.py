@@ -60,6 +60,8 @@ def test_batched_rollout_gae_and_update(tmp_path):
     assert legal.all() and (b_act[:, :, 1] <= b_masks[:, :, 5].float()).all()
     with torch.no_grad():
         lp = brain.get_log_probs(0, b_obs, b_act, b_masks) + brain.get_log_probs(1, b_obs, b_act, b_masks)
+        lp_joint = brain.joint_log_probs(b_obs, b_act, b_masks)  # what the update evaluates: both agents in one actor pass
+        assert torch.allclose(lp_joint, lp, rtol=1e-5, atol=2e-6)
         v = brain.get_state_values(b_obs)
     assert torch.allclose(lp, b_logp, rtol=1e-5, atol=2e-6) and torch.allclose(v, b_vals, rtol=1e-5, atol=2e-6)
     assert len(ep_lens) == len(b_sp) == brain.last_stats["episodes"]
