@@ -62,16 +62,15 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restri
     for (int i = threadIdx.x; i < 60 * kTok; i += blockDim.x) (&s_b[0][0])[i] = wts[o.tokb + i];
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kTokWarps + w;
-    if (row >= R) return;
     const bool on = lane < kTok;
     const int a = on ? lane : 0;
+    const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
+    // persistent blocks: the 27 KB of per-token maps are staged once per block, then the block's warps stride over the rows
+#pragma unroll 1
+    for (int row = blockIdx.x * kTokWarps + w; row < R; row += gridDim.x * kTokWarps) {
     float x[4];
-    {
-        const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
 #pragma unroll
-        for (int c = 0; c < 4; c++) x[c] = (c < nd) ? obs[(size_t)row * kObs + c0 + c] : 0.f;
-    }
+    for (int c = 0; c < 4; c++) x[c] = (c < nd) ? obs[(size_t)row * kObs + c0 + c] : 0.f;
     auto affine = [&](int j) {
         const float4 m = *reinterpret_cast<const float4*>(&s_m[j][a][0]);
         return fmaf(x[3], m.w, fmaf(x[2], m.z, fmaf(x[1], m.y, fmaf(x[0], m.x, s_b[j][a]))));
@@ -138,6 +137,8 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restri
             oh[d4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
             if (kSplit) ol[d4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
+    }
+    __syncwarp();  // the row's key / value tile is reused by the next row of this warp
     }
 }
 
@@ -315,7 +316,7 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         float* h1h = x0l + (size_t)R * kX0; float* h1l = h1h + (size_t)R * kHid;
         float* h2h = h1l + (size_t)R * kHid; float* h2l = h2h + (size_t)R * kHid;
         float* h3 = h2l + (size_t)R * kHid;
-        k_tokens<true><<<(R + kTokWarps - 1) / kTokWarps, kTokWarps * 32, 0, stream>>>(obs, wts, x0h, x0l, R);
+        k_tokens<true><<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0h, x0l, R);
         cudaError_t e;
         if ((e = launch_linear_tc(x0h, x0l, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1h, h1l, R, kX0, 1, stream)) != cudaSuccess) return e;
         if ((e = launch_linear_tc(h1h, h1l, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2h, h2l, R, kHid, 1, stream)) != cudaSuccess) return e;
@@ -325,7 +326,7 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         float* x0 = scratch;                      // [R,460]
         float* h1 = scratch + (size_t)R * kX0;    // [R,264]
         float* h2 = h1 + (size_t)R * kHid;        // [R,264]
-        k_tokens<false><<<(R + kTokWarps - 1) / kTokWarps, kTokWarps * 32, 0, stream>>>(obs, wts, x0, nullptr, R);
+        k_tokens<false><<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, nullptr, R);
         dim3 grid((R + BM - 1) / BM, (kHid + BN - 1) / BN);
         k_linear_relu<<<grid, 256, 0, stream>>>(x0, wts + o.l0_w, wts + o.l0_b, h1, R, kHid, kX0);
         k_linear_relu<<<grid, 256, 0, stream>>>(h1, wts + o.l1_w, wts + o.l1_b, h2, R, kHid, kHid);
