@@ -84,11 +84,17 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
     for (int d = 0; d < nd; d++) {
         const int coin = rng.randint(0, 1);
         const int x = coin == 0 ? 0 : W - 1;
-        cex[d] = x; cey[d] = 0;
-        for (int tries = 0; tries < (1 << 16); tries++) {  // the reference would spin forever on an edge without an eligible cell; sides >= 7 always have one
+        bool found = false;
+        for (int tries = 0; tries < 4096 && !found; tries++) {
             const int y = rng.randint(0, Hh - 1);
             if (x == sx && y == sy) continue;
-            if (is_open(x, y)) { cex[d] = x; cey[d] = y; break; }
+            if (is_open(x, y)) { cex[d] = x; cey[d] = y; found = true; }
+        }
+        if (!found) {  // the reference spins forever here (an edge without an eligible cell: its generator CAN leave a partial maze).
+            cex[d] = sx; cey[d] = sy;  // Way out shared with the oracle: first open cell != start in row-major order.
+            for (int yy = 0; yy < Hh && !found; yy++)
+                for (int xx = 0; xx < W && !found; xx++)
+                    if (is_open(xx, yy) && !(xx == sx && yy == sy)) { cex[d] = xx; cey[d] = yy; found = true; }
         }
         clen[d] = 0;
     }
@@ -152,12 +158,16 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
     }
     // ---- key (set_key, maze.py:252-259)
     int kx = sx, ky = sy;
-    for (int tries = 0; tries < (1 << 20); tries++) {  // bounded for the same reason
+    bool kfound = false;
+    for (int tries = 0; tries < 65536 && !kfound; tries++) {
         const int tx = rng.randint(0, W - 1), ty = rng.randint(0, Hh - 1);
         if (!is_open(tx, ty) || (tx == ex && ty == ey) || (tx == sx && ty == sy) || ((seen[ty] >> (tx + kPad)) & 1ull)) continue;
-        kx = tx; ky = ty;
-        break;
+        kx = tx; ky = ty; kfound = true;
     }
+    for (int pass = 0; pass < 2 && !kfound; pass++)  // reference: infinite loop; same way out as the oracle
+        for (int yy = 0; yy < Hh && !kfound; yy++)
+            for (int xx = 0; xx < W && !kfound; xx++)
+                if (is_open(xx, yy) && !(xx == sx && yy == sy) && !(xx == ex && yy == ey) && (pass == 1 || !((seen[yy] >> (xx + kPad)) & 1ull))) { kx = xx; ky = yy; kfound = true; }
 
     // ---- pool entry in its final HBM form
     ulonglong2* g = pool_grid + (size_t)p * rows;

@@ -210,8 +210,16 @@ static void set_end(OMaze *m) { /* maze.py:239-250 */
     int coin = rng_randint(&m->rng, 0, 1);
     int x = coin == 0 ? 0 : m->width - 1;
     for (long tries = 0;; tries++) {
-        /* the reference loops forever on a maze with no eligible cell on that edge; the oracle gives up loudly */
-        if (tries > 1000000) { m->error |= 2; m->end_x = x; m->end_y = 0; break; }
+        /* The reference loops forever when the chosen edge has no eligible cell -- which its own generator can produce (a carve that
+         * is popped early at every frontier leaves a partial maze; seen once in 262 144 small mazes).  Oracle and K1 share a defined
+         * way out: after 4096 draws take the first open cell != start in row-major order, and raise the error flag. */
+        if (tries >= 4096) {
+            m->error |= 2; m->end_x = m->start_x; m->end_y = m->start_y;
+            for (int yy = 0, found = 0; yy < m->height && !found; yy++)
+                for (int xx = 0; xx < m->width && !found; xx++)
+                    if (LAY(m, xx, yy) == 0 && !(xx == m->start_x && yy == m->start_y)) { m->end_x = xx; m->end_y = yy; found = 1; }
+            break;
+        }
         int y = rng_randint(&m->rng, 0, m->height - 1);
         if (x == m->start_x && y == m->start_y) continue;
         if (LAY(m, x, y) == 0) { m->end_x = x; m->end_y = y; break; }
@@ -250,7 +258,17 @@ static int in_path(const OMaze *m, int x, int y) {
 }
 static void set_key(OMaze *m) { /* maze.py:252-259 */
     for (long tries = 0;; tries++) {
-        if (tries > 1000000) { m->error |= 4; m->key_x = m->start_x; m->key_y = m->start_y; m->key_present = 1; break; } /* reference: infinite loop */
+        if (tries >= 65536) { /* reference: infinite loop (no open cell off the path).  Shared way out: first open cell that is not
+                                 start / exit / on the path, else first open cell that is not start / exit, else the start. */
+            m->error |= 4; m->key_x = m->start_x; m->key_y = m->start_y; m->key_present = 1;
+            for (int pass = 0, found = 0; pass < 2 && !found; pass++)
+                for (int yy = 0; yy < m->height && !found; yy++)
+                    for (int xx = 0; xx < m->width && !found; xx++)
+                        if (LAY(m, xx, yy) == 0 && !(xx == m->start_x && yy == m->start_y) && !(xx == m->end_x && yy == m->end_y) && (pass == 1 || !in_path(m, xx, yy))) {
+                            m->key_x = xx; m->key_y = yy; found = 1;
+                        }
+            break;
+        }
         int x = rng_randint(&m->rng, 0, m->width - 1), y = rng_randint(&m->rng, 0, m->height - 1);
         if (LAY(m, x, y) == 1 || (x == m->end_x && y == m->end_y) || (x == m->start_x && y == m->start_y) || in_path(m, x, y)) continue;
         m->key_x = x; m->key_y = y; m->key_present = 1; break;

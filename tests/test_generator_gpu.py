@@ -83,3 +83,19 @@ def test_generator_regression_zero_draw_maze():
         _check_tree_properties(g)
         assert int((g["layout"] == 0).sum()) == 1249  # every room carved
     assert o.error() == 0
+
+
+def test_generator_regression_partial_maze_without_eligible_exit():
+    """A carve that is popped early at every frontier leaves a partial maze whose left edge has no open cell: the reference's
+    set_end would spin forever; K1 and the oracle must take the same documented way out (and stay in RNG lock-step afterwards)."""
+    from marl_maze_b200 import MazeEngine
+    eng = MazeEngine(4, smax=25, max_timestep=100, pool_size=8)
+    eng.generate(1000, side_range=(4, 13), difficulty=3, id_base=187600)
+    o = OracleMaze(max_timestep=10, difficulty=3, rand_start=True, rand_sizes=True, rand_range=(4, 13), default_size=(4, 4))
+    for p in range(8):
+        g = eng.pool_maze(p)
+        o.seed_philox(1000, 187600 + p); o.build(); m = o.maze()
+        assert np.array_equal(g["layout"], m["layout"])
+        assert (g["start"], g["path1"], g["end"], g["key"], g["shortest_path_len"]) == (m["start"], m["path1"], m["end"], m["key"], m["shortest_path_len"]), p
+    g = eng.pool_maze(2)
+    assert int((g["layout"] == 0).sum()) == 11 and g["layout"][g["end"][1], g["end"][0]] == 0
