@@ -153,7 +153,7 @@ int mm_critic_forward(const float* weights, const float* obs, int n_envs, float*
     if (!weights || !obs || !value || n_envs <= 0) return MM_ERR_BAD_ARG;
     return cuda_status(launch_critic(weights, obs, n_envs, value, (cudaStream_t)stream));
 }
-size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (2 * 460 + 5 * 264) * sizeof(float); }
+size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (460 + 2 * 264) * sizeof(float); }
 int mm_policy_forward(const float* weights, const float* obs, const uint8_t* masks, int n_envs, void* scratch, const uint8_t* actions_in,
                       uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter, int flags,
                       void* stream) {

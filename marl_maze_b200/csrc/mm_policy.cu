@@ -51,9 +51,7 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
 // token, 20-29 key, 30-39 query, 40-59 value) and the lane evaluates all 60 outputs with 240 FMAs instead of 80 + 800.  Keys and
 // values of the row's 23 tokens are exchanged through a small per-warp shared-memory tile (broadcast reads).
 constexpr int kTokWarps = 4;
-template <bool kSplit>  // kSplit: write x0 as the TF32 pair (hi, lo) for the tensor-core trunk
-__global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0,
-                                                         float* __restrict__ x0_lo, int R) {
+__global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int R) {
     const PolicyOffsets o = policy_offsets();
     __shared__ __align__(16) float s_m[60][kTok][4];
     __shared__ float s_b[60][kTok];
@@ -124,19 +122,9 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restri
     }
     if (on) {  // residual (networks.py:82); lane a owns columns 20a .. 20a+19 of the row
         float4* oh = reinterpret_cast<float4*>(x0 + (size_t)row * kX0 + a * kEmb);
-        float4* ol = kSplit ? reinterpret_cast<float4*>(x0_lo + (size_t)row * kX0 + a * kEmb) : nullptr;
 #pragma unroll
-        for (int d4 = 0; d4 < kEmb / 4; d4++) {
-            float v[4], hi[4], lo[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                v[c] = affine(4 * d4 + c) + ctx[4 * d4 + c];  // the token itself, evaluated last to keep it out of the register budget above
-                hi[c] = kSplit ? tf32_rn(v[c]) : v[c];
-                lo[c] = kSplit ? tf32_rn(v[c] - hi[c]) : 0.f;
-            }
-            oh[d4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            if (kSplit) ol[d4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
+        for (int d4 = 0; d4 < kEmb / 4; d4++)  // the token itself is evaluated last to keep it out of the register budget above
+            oh[d4] = make_float4(affine(4 * d4) + ctx[4 * d4], affine(4 * d4 + 1) + ctx[4 * d4 + 1], affine(4 * d4 + 2) + ctx[4 * d4 + 2], affine(4 * d4 + 3) + ctx[4 * d4 + 3]);
     }
     __syncwarp();  // the row's key / value tile is reused by the next row of this warp
     }
@@ -301,8 +289,7 @@ int policy_offsets_host(int32_t* out) {
     return 0;
 }
 
-cudaError_t launch_linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias, float* y_hi, float* y_lo, int M, int K,
-                             int split_out, cudaStream_t stream);
+cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, cudaStream_t stream);
 
 // flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
@@ -311,22 +298,17 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
     const PolicyOffsets o = policy_offsets();
     const int R = 2 * E;
     const float* h_final;
+    float* x0 = scratch;                      // [R,460]
+    float* h1 = scratch + (size_t)R * kX0;    // [R,264]
+    float* h2 = h1 + (size_t)R * kHid;        // [R,264]
+    k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
     if (flags & 1) {
-        float* x0h = scratch; float* x0l = x0h + (size_t)R * kX0;
-        float* h1h = x0l + (size_t)R * kX0; float* h1l = h1h + (size_t)R * kHid;
-        float* h2h = h1l + (size_t)R * kHid; float* h2l = h2h + (size_t)R * kHid;
-        float* h3 = h2l + (size_t)R * kHid;
-        k_tokens<true><<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0h, x0l, R);
         cudaError_t e;
-        if ((e = launch_linear_tc(x0h, x0l, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1h, h1l, R, kX0, 1, stream)) != cudaSuccess) return e;
-        if ((e = launch_linear_tc(h1h, h1l, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2h, h2l, R, kHid, 1, stream)) != cudaSuccess) return e;
-        if ((e = launch_linear_tc(h2h, h2l, wts + o.l2_whi, wts + o.l2_wlo, wts + o.l2_b, h3, h3, R, kHid, 0, stream)) != cudaSuccess) return e;
-        h_final = h3;
+        if ((e = launch_linear_tc(x0, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1, R, kX0, stream)) != cudaSuccess) return e;
+        if ((e = launch_linear_tc(h1, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2, R, kHid, stream)) != cudaSuccess) return e;
+        if ((e = launch_linear_tc(h2, wts + o.l2_whi, wts + o.l2_wlo, wts + o.l2_b, h1, R, kHid, stream)) != cudaSuccess) return e;
+        h_final = h1;
     } else {
-        float* x0 = scratch;                      // [R,460]
-        float* h1 = scratch + (size_t)R * kX0;    // [R,264]
-        float* h2 = h1 + (size_t)R * kHid;        // [R,264]
-        k_tokens<false><<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, nullptr, R);
         dim3 grid((R + BM - 1) / BM, (kHid + BN - 1) / BN);
         k_linear_relu<<<grid, 256, 0, stream>>>(x0, wts + o.l0_w, wts + o.l0_b, h1, R, kHid, kX0);
         k_linear_relu<<<grid, 256, 0, stream>>>(h1, wts + o.l1_w, wts + o.l1_b, h2, R, kHid, kHid);

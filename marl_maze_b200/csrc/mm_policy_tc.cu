@@ -1,15 +1,17 @@
 // mm_policy_tc.cu -- K4 tensor-core path: Y = relu(X W^T + b) on tcgen05 with error-compensated TF32 (3xTF32), sm_100a.
 //
-// The parity bar of the policy path is 1e-5 relative on logits / values / log-probs (BASELINE north_star), which single-pass
-// TF32/BF16 tensor-core math cannot meet.  Every operand is therefore carried as a two-term split x ~ x_hi + x_lo with
-// x_hi = tf32(x) and x_lo = tf32(x - x_hi), both rounded to nearest (|x - x_hi - x_lo| <= 2^-22 |x|, zero-mean), and each
-// k-step issues three MMAs into the same fp32 TMEM accumulator:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is ~2^-22).
+// The parity bar of the policy path is 1e-5 relative on values / log-probs (BASELINE north_star), which single-pass TF32/BF16
+// tensor-core math cannot meet.  Every operand is therefore used as a two-term split x ~ x_hi + x_lo with x_hi = tf32(x) and
+// x_lo = tf32(x - x_hi), both rounded to nearest (|x - x_hi - x_lo| <= 2^-22 |x|, zero-mean), and each k-step issues three MMAs
+// into the same fp32 TMEM accumulator:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is ~2^-22).
 //
-// One CTA = one 128-row tile of X through one layer (N = 264 outputs, padded to 272 = 144 + 128 so that each half is a legal
-// UMMA N for M = 128).  Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-5 = epilogue (TMEM -> registers -> bias + ReLU -> hi/lo split -> global).  Operands are staged by TMA
-// (cp.async.bulk.tensor, SWIZZLE_128B, K-major 128-byte rows = 32 fp32) through a 2-stage mbarrier ring; out-of-bounds rows /
-// columns (M tail, K = 460 -> 480, N = 264 -> 272) are zero-filled by TMA, so nothing is physically padded in HBM.
+// Activations travel through HBM ONCE, as plain fp32: the split of the A operand happens inside the kernel.  One CTA = one 128-row
+// tile of X through one layer (N = 264 outputs, padded to 272 = 144 + 128 so that each half is a legal UMMA N for M = 128).
+// Warp roles: warp 0 = TMA producer (one lane); warp 1 = TMEM allocator + MMA issuer (one lane); warps 2-5 = SPLITTER during the
+// main loop (turn the TMA-landed fp32 A tile into its hi tile in place and its lo tile next to it, both in the TMA's own
+// 128-byte-swizzled layout, so the transform is position-preserving) and EPILOGUE afterwards (TMEM -> registers -> bias + ReLU ->
+// shared-memory transpose -> whole 128-byte row segments to global).  Weights are pre-split on the host.  Operands are staged
+// through a 2-stage mbarrier ring; out-of-bounds rows / columns (M tail, K = 460 -> 480, N = 264 -> 272) are zero-filled by TMA.
 #include <cuda.h>
 #include <stdio.h>
 #include "mm_env.cuh"
@@ -72,16 +74,17 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 struct TcMaps {
-    CUtensorMap a_hi, a_lo, w1_hi, w2_hi, w1_lo, w2_lo;
+    CUtensorMap a, w1_hi, w2_hi, w1_lo, w2_lo;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y_hi, float* __restrict__ y_lo, int M, int K, int split_out) {
+k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y, int M, int K) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty = full + TC_STAGES;
-    uint64_t* tmem_full = empty + TC_STAGES;
+    uint64_t* split_done = empty + TC_STAGES;
+    uint64_t* tmem_full = split_done + TC_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,7 +92,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     const int nkb = (K + TC_BK - 1) / TC_BK;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split_done[s], 128); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -108,10 +111,9 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 const int s = kb % TC_STAGES;
                 mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * TC_STAGE_BYTES;
-                mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+                mbar_expect_tx(&full[s], TC_STAGE_BYTES - TC_A_BYTES);  // the A_lo slot is produced in-kernel
                 const int k0 = kb * TC_BK;
-                tma_load_2d(st, &maps.a_hi, k0, m0, &full[s]);
-                tma_load_2d(st + TC_A_BYTES, &maps.a_lo, k0, m0, &full[s]);
+                tma_load_2d(st, &maps.a, k0, m0, &full[s]);
                 tma_load_2d(st + 2 * TC_A_BYTES, &maps.w1_hi, k0, 0, &full[s]);
                 tma_load_2d(st + 2 * TC_A_BYTES + TC_B1_BYTES, &maps.w2_hi, k0, TC_N1, &full[s]);
                 tma_load_2d(st + 2 * TC_A_BYTES + TC_B1_BYTES + TC_B2_BYTES, &maps.w1_lo, k0, 0, &full[s]);
@@ -123,7 +125,8 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             constexpr uint32_t id1 = umma_idesc_tf32(TC_BM, TC_N1), id2 = umma_idesc_tf32(TC_BM, TC_N2);
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % TC_STAGES;
-                mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+                mbar_wait(&full[s], (kb / TC_STAGES) & 1);        // weight tiles landed
+                mbar_wait(&split_done[s], (kb / TC_STAGES) & 1);  // A tile rewritten as hi, lo tile written (fenced to the async proxy)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
                 const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TC_A_BYTES);
@@ -145,6 +148,25 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             umma_commit(tmem_full);      // accumulator complete
         }
     } else {
+        // ===== splitter (main loop): 128 threads turn each landed fp32 A tile into (hi in place, lo beside it)
+        const int st_tid = threadIdx.x - 64;
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % TC_STAGES;
+            mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+            float4* raw = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
+            float4* lo_t = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+            for (int q = 0; q < (int)(TC_A_BYTES / 16 / 128); q++) {
+                const int j = st_tid + 128 * q;
+                const float4 v = raw[j];
+                float4 h, l;
+                h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+                l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+                raw[j] = h; lo_t[j] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma's operand reads
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s])) : "memory");
+        }
         // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31; one thread = one output row
         const int quarter = warp & 3;
         mbar_wait(tmem_full, 0);
@@ -154,8 +176,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         // half-written sectors per instruction (measured: half of the kernel's time).  Each warp therefore transposes 32x32 blocks
         // through shared memory -- the pipeline stages are free once tmem_full has fired -- and writes whole 128-byte row segments.
         constexpr int kTP = 36;  // padded row pitch (floats): 16-byte aligned, conflict-free for the quarter-warp float4 patterns below
-        float* t_hi = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 2 * 32 * kTP;
-        float* t_lo = t_hi + 32 * kTP;
+        float* t_y = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * kTP;
         const int row0 = m0 + quarter * 32;
 #pragma unroll 1
         for (int c = 0; c < 9; c++) {  // 9 x 32 columns >= 264
@@ -169,27 +190,21 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                float hi[4], lo[4];
+                float yv[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int col = c * 32 + 4 * q + j;
-                    float yv = __uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f);
-                    yv = fmaxf(yv, 0.f);
-                    if (split_out) { hi[j] = tf32_rn(yv); lo[j] = tf32_rn(yv - hi[j]); }
-                    else { hi[j] = yv; lo[j] = 0.f; }
+                    yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f), 0.f);
                 }
-                *reinterpret_cast<float4*>(&t_hi[lane * kTP + 4 * q]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                if (split_out) *reinterpret_cast<float4*>(&t_lo[lane * kTP + 4 * q]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(&t_y[lane * kTP + 4 * q]) = make_float4(yv[0], yv[1], yv[2], yv[3]);
             }
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; it++) {  // 4 rows x 128 contiguous bytes per instruction
                 const int r = it * 4 + (lane >> 3), c4 = lane & 7;
                 const int col = c * 32 + 4 * c4;
-                if (row0 + r < M && col < TC_N) {
-                    *reinterpret_cast<float4*>(y_hi + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_hi[r * kTP + 4 * c4]);
-                    if (split_out) *reinterpret_cast<float4*>(y_lo + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_lo[r * kTP + 4 * c4]);
-                }
+                if (row0 + r < M && col < TC_N)
+                    *reinterpret_cast<float4*>(y + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_y[r * kTP + 4 * c4]);
             }
             __syncwarp();
         }
@@ -227,25 +242,24 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Y = relu(X W^T + b) with X given as (x_hi, x_lo) [M][K], W as (w_hi, w_lo) [264][K]; writes (y_hi, y_lo) or plain y into y_hi.
-cudaError_t launch_linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias, float* y_hi, float* y_lo, int M, int K,
-                             int split_out, cudaStream_t stream) {
+// Y = relu(X W^T + b) with X [M][K] plain fp32, W as the host-made split (w_hi, w_lo) [264][K]; writes plain fp32 y [M][264].
+cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, cudaStream_t stream) {
     // The rollout calls this with the same scratch / weight pointers every step: keep the encoded maps (a tensor map depends only on
-    // base pointer, extents and box) in a small per-thread cache instead of re-encoding 18 of them per policy step.
-    struct Entry { const float *xh, *xl, *wh, *wl; int M, K; TcMaps maps; };
+    // base pointer, extents and box) in a small per-thread cache instead of re-encoding 15 of them per policy step.
+    struct Entry { const float *x, *wh, *wl; int M, K; TcMaps maps; };
     static thread_local Entry cache[8];
     static thread_local int next_slot = 0;
     const TcMaps* found = nullptr;
     for (int i = 0; i < 8; i++)
-        if (cache[i].xh == x_hi && cache[i].xl == x_lo && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].M == M && cache[i].K == K) { found = &cache[i].maps; break; }
+        if (cache[i].x == x && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].M == M && cache[i].K == K) { found = &cache[i].maps; break; }
     if (!found) {
         Entry& e = cache[next_slot];
         next_slot = (next_slot + 1) % 8;
-        e.xh = nullptr;
-        if (!make_map(&e.maps.a_hi, x_hi, M, K, TC_BM) || !make_map(&e.maps.a_lo, x_lo, M, K, TC_BM) || !make_map(&e.maps.w1_hi, w_hi, TC_N, K, TC_N1) ||
-            !make_map(&e.maps.w2_hi, w_hi, TC_N, K, TC_N2) || !make_map(&e.maps.w1_lo, w_lo, TC_N, K, TC_N1) || !make_map(&e.maps.w2_lo, w_lo, TC_N, K, TC_N2))
+        e.x = nullptr;
+        if (!make_map(&e.maps.a, x, M, K, TC_BM) || !make_map(&e.maps.w1_hi, w_hi, TC_N, K, TC_N1) || !make_map(&e.maps.w2_hi, w_hi, TC_N, K, TC_N2) ||
+            !make_map(&e.maps.w1_lo, w_lo, TC_N, K, TC_N1) || !make_map(&e.maps.w2_lo, w_lo, TC_N, K, TC_N2))
             return cudaErrorInvalidValue;
-        e.xh = x_hi; e.xl = x_lo; e.wh = w_hi; e.wl = w_lo; e.M = M; e.K = K;
+        e.x = x; e.wh = w_hi; e.wl = w_lo; e.M = M; e.K = K;
         found = &e.maps;
     }
     const TcMaps& maps = *found;
@@ -255,7 +269,7 @@ cudaError_t launch_linear_tc(const float* x_hi, const float* x_lo, const float* 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_linear_tf32x3<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y_hi, y_lo, M, K, split_out);
+    k_linear_tf32x3<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K);
     return cudaGetLastError();
 }
 
