@@ -11,6 +11,7 @@
 //   k_critic   : centralised critic [E,130] -> 64 -> 64 -> 1
 // Weights arrive as ONE flat fp32 buffer laid out by mm_policy_offsets() (host packs it from the state_dict).
 #include "mm_env.cuh"
+#include "mm_policy_heads.cuh"
 
 namespace mm {
 
@@ -184,12 +185,10 @@ __global__ void __launch_bounds__(256) k_linear_relu(const float* __restrict__ X
 
 // ------------------------------------------------------------------------------------------------ heads + sampling
 // One warp per ENV (both agents), lanes split the 264-long dot products; lane 0 finishes the distribution math.
-__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ h, const float* __restrict__ wts, const uint8_t* __restrict__ masks,
-                                               const uint8_t* __restrict__ actions_in, uint8_t* __restrict__ actions_out, float* __restrict__ logp,
-                                               float* __restrict__ logits_out, int E, int env_offset, uint64_t seed, uint64_t counter) {
+__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ h, const float* __restrict__ wts, const HeadArgs ha) {
     const PolicyOffsets o = policy_offsets();
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= E) return;
+    if (w >= ha.E) return;
     float lp_env = 0.f;
     for (int a = 0; a < 2; a++) {
         const float* hr = h + ((size_t)w * 2 + a) * kHid;
@@ -202,32 +201,9 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ h, cons
             for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
             l[j] = acc + wts[o.head_b + j];
         }
-        if (lane == 0) {
-            const uint8_t* mk = masks + ((size_t)w * 2 + a) * 6;
-            if (logits_out) for (int j = 0; j < 6; j++) logits_out[((size_t)w * 2 + a) * 6 + j] = l[j];
-            // masked Categorical over the 5 moves (PPO.py:174-176)
-            float m = -INFINITY;
-            for (int j = 0; j < 5; j++) if (mk[j]) m = fmaxf(m, l[j]);
-            float p[5], s = 0.f;
-            for (int j = 0; j < 5; j++) { p[j] = mk[j] ? expf(l[j] - m) : 0.f; s += p[j]; }
-            const float p_mark = mk[5] ? 1.f / (1.f + expf(-l[5])) : 0.f;  // PPO.py:179
-            int move, mark;
-            if (actions_in) { move = actions_in[((size_t)w * 2 + a) * 2]; mark = actions_in[((size_t)w * 2 + a) * 2 + 1]; }
-            else {
-                uint32_t r[4];
-                philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)(env_offset + w) * 2u + (uint32_t)a, 0x504f4c49u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-                const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * s;  // inverse CDF over the unnormalised masses
-                float c = 0.f; move = -1; int last = 4;
-                for (int j = 0; j < 5; j++) if (mk[j]) { last = j; c += p[j]; if (move < 0 && u < c) move = j; }
-                if (move < 0) move = last;
-                mark = ((float)(r[1] >> 8) * (1.0f / 16777216.0f) < p_mark) ? 1 : 0;  // torch.bernoulli(p)
-                actions_out[((size_t)w * 2 + a) * 2] = (uint8_t)move; actions_out[((size_t)w * 2 + a) * 2 + 1] = (uint8_t)mark;
-            }
-            const float lp_move = (move < 5 && mk[move]) ? (l[move] - m) - logf(s) : -INFINITY;  // Categorical.log_prob
-            lp_env += lp_move + logf(mark ? p_mark : 1.f - p_mark);                                // PPO.py:181-184
-        }
+        if (lane == 0) lp_env += head_sample_or_eval(l, (long long)w * 2 + a, ha);
     }
-    if (lane == 0) logp[w] = lp_env;
+    if (lane == 0) ha.logp[w] = lp_env;
 }
 
 // ------------------------------------------------------------------------------------------------ critic
@@ -289,7 +265,8 @@ int policy_offsets_host(int32_t* out) {
     return 0;
 }
 
-cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, cudaStream_t stream);
+cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
+                             const float* head_b, const HeadArgs* heads, cudaStream_t stream);
 
 // flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
@@ -297,25 +274,26 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
                           int flags, cudaStream_t stream) {
     const PolicyOffsets o = policy_offsets();
     const int R = 2 * E;
-    const float* h_final;
+    HeadArgs ha;
+    ha.masks = masks; ha.actions_in = actions_in; ha.actions_out = actions_out; ha.logp = logp; ha.logits_out = logits_out;
+    ha.E = E; ha.env_offset = env_offset; ha.seed = seed; ha.counter = counter;
     float* x0 = scratch;                      // [R,460]
     float* h1 = scratch + (size_t)R * kX0;    // [R,264]
     float* h2 = h1 + (size_t)R * kHid;        // [R,264]
     k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
     if (flags & 1) {
         cudaError_t e;
-        if ((e = launch_linear_tc(x0, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1, R, kX0, stream)) != cudaSuccess) return e;
-        if ((e = launch_linear_tc(h1, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2, R, kHid, stream)) != cudaSuccess) return e;
-        if ((e = launch_linear_tc(h2, wts + o.l2_whi, wts + o.l2_wlo, wts + o.l2_b, h1, R, kHid, stream)) != cudaSuccess) return e;
-        h_final = h1;
+        if ((e = launch_linear_tc(x0, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1, R, kX0, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;
+        if ((e = launch_linear_tc(h1, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2, R, kHid, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;
+        // last layer: heads, masking, sampling and the joint log-prob run in the epilogue; the 264-wide activation never leaves the SM
+        if ((e = launch_linear_tc(h2, wts + o.l2_whi, wts + o.l2_wlo, wts + o.l2_b, nullptr, R, kHid, wts + o.head_w, wts + o.head_b, &ha, stream)) != cudaSuccess) return e;
     } else {
         dim3 grid((R + BM - 1) / BM, (kHid + BN - 1) / BN);
         k_linear_relu<<<grid, 256, 0, stream>>>(x0, wts + o.l0_w, wts + o.l0_b, h1, R, kHid, kX0);
         k_linear_relu<<<grid, 256, 0, stream>>>(h1, wts + o.l1_w, wts + o.l1_b, h2, R, kHid, kHid);
         k_linear_relu<<<grid, 256, 0, stream>>>(h2, wts + o.l2_w, wts + o.l2_b, h1, R, kHid, kHid);
-        h_final = h1;
+        k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h1, wts, ha);
     }
-    k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h_final, wts, masks, actions_in, actions_out, logp, logits_out, E, env_offset, seed, counter);
     if (value) k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
     return cudaGetLastError();
 }

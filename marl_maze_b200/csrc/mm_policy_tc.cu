@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include "mm_env.cuh"
+#include "mm_policy_heads.cuh"
 
 namespace mm {
 
@@ -77,8 +78,12 @@ struct TcMaps {
     CUtensorMap a, w1_hi, w2_hi, w1_lo, w2_lo;
 };
 
+// kHeads: this is the last trunk layer -- instead of storing y, the epilogue contracts each row with the 6 head rows (5 move logits +
+// 1 mark logit), masks, samples (or evaluates) the action and writes actions + the env's joint log-prob: "sampling fused in the epilogue".
+template <bool kHeads>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y, int M, int K) {
+k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y, int M, int K, const float* __restrict__ head_w,
+                const float* __restrict__ head_b, const HeadArgs heads) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -178,6 +183,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         constexpr int kTP = 36;  // padded row pitch (floats): 16-byte aligned, conflict-free for the quarter-warp float4 patterns below
         float* t_y = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * kTP;
         const int row0 = m0 + quarter * 32;
+        float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 9; c++) {  // 9 x 32 columns >= 264
             uint32_t v[32];
@@ -196,8 +202,19 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                     const int col = c * 32 + 4 * q + j;
                     yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f), 0.f);
                 }
-                *reinterpret_cast<float4*>(&t_y[lane * kTP + 4 * q]) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                if (kHeads) {
+                    if (c * 32 + 4 * q < TC_N) {  // TC_N is a multiple of 4: whole float4 groups are in or out
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            const float4 wv = __ldg(reinterpret_cast<const float4*>(head_w + j * TC_N + c * 32 + 4 * q));  // same address in every lane: broadcast
+                            hacc[j] = fmaf(yv[3], wv.w, fmaf(yv[2], wv.z, fmaf(yv[1], wv.y, fmaf(yv[0], wv.x, hacc[j]))));
+                        }
+                    }
+                } else {
+                    *reinterpret_cast<float4*>(&t_y[lane * kTP + 4 * q]) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                }
             }
+            if (kHeads) continue;
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; it++) {  // 4 rows x 128 contiguous bytes per instruction
@@ -207,6 +224,18 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                     *reinterpret_cast<float4*>(y + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_y[r * kTP + 4 * c4]);
             }
             __syncwarp();
+        }
+        if (kHeads) {  // one thread = one agent row; rows 2e and 2e+1 (the two agents of env e) sit in adjacent lanes
+            const long long row = (long long)row0 + lane;
+            float lp = 0.f;
+            if (row < M) {
+                float l[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) l[j] = hacc[j] + __ldg(&head_b[j]);
+                lp = head_sample_or_eval(l, row, heads);
+            }
+            const float lp_pair = lp + __shfl_xor_sync(0xffffffffu, lp, 1);
+            if (row < M && (lane & 1) == 0) heads.logp[row >> 1] = lp_pair;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -242,8 +271,10 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Y = relu(X W^T + b) with X [M][K] plain fp32, W as the host-made split (w_hi, w_lo) [264][K]; writes plain fp32 y [M][264].
-cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, cudaStream_t stream) {
+// Y = relu(X W^T + b) with X [M][K] plain fp32, W as the host-made split (w_hi, w_lo) [264][K]; writes plain fp32 y [M][264] -- or, when
+// `heads` is given (last layer), runs heads + sampling in the epilogue and writes actions / log-probs instead of y.
+cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
+                             const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
     // The rollout calls this with the same scratch / weight pointers every step: keep the encoded maps (a tensor map depends only on
     // base pointer, extents and box) in a small per-thread cache instead of re-encoding 15 of them per policy step.
     struct Entry { const float *x, *wh, *wl; int M, K; TcMaps maps; };
@@ -265,11 +296,14 @@ cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_l
     const TcMaps& maps = *found;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_linear_tf32x3<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K);
+    const int blocks = (M + TC_BM - 1) / TC_BM;
+    if (heads) k_linear_tf32x3<true><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, nullptr, M, K, head_w, head_b, *heads);
+    else k_linear_tf32x3<false><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K, nullptr, nullptr, HeadArgs{});
     return cudaGetLastError();
 }
 
