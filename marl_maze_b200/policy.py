@@ -110,5 +110,5 @@ class PolicyRunner:
         _abi.check(self.lib.mm_policy_forward(p(self.weights), p(obs), p(masks), E, p(self.scratch), p(actions_in), p(actions_out), p(logp),
                                               p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(self.counter),
                                               self.flags, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
-        self.launches += 6 if want_value else 5
+        self.launches += (4 if self.flags & 1 else 5) + (1 if want_value else 0)  # tokens + 3 trunk layers (+ heads on the SIMT path) + critic
         return (actions_in if actions_in is not None else actions_out), logp, (value if want_value else None)

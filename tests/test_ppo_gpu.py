@@ -100,3 +100,16 @@ def test_reference_checkpoint_drives_the_kernel_policy(tmp_path):
         obs, masks, r, d = maze.step(acts)
         if d:
             obs, masks = maze.reset()
+
+
+def test_reference_main_py_flow_single_env_train(tmp_path):
+    """brain.train() exactly as wired in the reference's main.py, on ONE maze (num_envs=1): rollout of batch_size+1 steps, update, checkpoint."""
+    from marl_maze_b200.PPO import PPO
+    from marl_maze_b200.maze import Maze
+    from marl_maze_b200.maze_agent import Agent
+    brain = PPO(agent_amount=2, batch_size=300, lr=0.00014, epochs=1, verbose=False, model_path=str(tmp_path / "PPO.pth"))
+    agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
+    maze = Maze(agents=agents, max_timestep=60, rand_sizes=True, rand_range=[4, 5], rand_start=True, difficulty=1, default_size=[4, 4])
+    brain.train()
+    assert brain.last_stats["env_steps"] == 301 and brain.last_stats["num_envs"] == 1 and brain.last_stats["episodes"] >= 4
+    assert (tmp_path / "PPO.pth").exists() and brain.last_update["steps"] == 25
