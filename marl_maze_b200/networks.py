@@ -86,7 +86,10 @@ class Actor(nn.Module):
             if uniq.shape[0] * 8 <= x.shape[0]:
                 xin = x.new_zeros(uniq.shape[0], OBS_SPACE)
                 xin[:, :uniq.shape[1]] = uniq
-                return self.attention(self.projection(xin)).index_select(0, inv)
+                emb = self.attention(self.projection(xin))
+                if uniq.shape[0] <= 64:  # gather as a one-hot matmul: its backward is a dense [U,B]x[B,460] GEMM instead of a scatter-add
+                    return torch.nn.functional.one_hot(inv, uniq.shape[0]).to(emb.dtype) @ emb  # into a handful of rows (atomics contention)
+                return emb.index_select(0, inv)
         return self.attention(self.projection(x))
 
     def trunk(self, x):
