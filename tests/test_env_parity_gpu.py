@@ -208,3 +208,10 @@ def test_reciprocal_division_is_ieee_exact_exhaustively():
     _abi.check(_abi.lib().mm_selftest_div(4096, 4096, C.c_void_p(cnt.data_ptr()), None), "mm_selftest_div")
     torch.cuda.synchronize()
     assert int(cnt.item()) == 0
+
+
+def test_rectangular_mazes_injected():
+    """Maze(default_size=[w, h]) with w != h (maze.py:26-27): the step kernel keeps W and H apart; layouts come from the oracle."""
+    for ds in [(4, 9), (12, 5)]:
+        cfg = dict(rand_sizes=False, rand_start=True, difficulty=2, default_size=ds)
+        _run_vs_oracle(E=96, K=10, T=260, max_t=90, cfg=cfg, p_follow=0.8, p_mark=0.4)
