@@ -52,7 +52,10 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
 // token, 20-29 key, 30-39 query, 40-59 value) and the lane evaluates all 60 outputs with 240 FMAs instead of 80 + 800.  Keys and
 // values of the row's 23 tokens are exchanged through a small per-warp shared-memory tile (broadcast reads).
 constexpr int kTokWarps = 4;
-__global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int R) {
+#ifndef MM_TOK_MINBLOCKS
+#define MM_TOK_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_MINBLOCKS) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int R) {
     const PolicyOffsets o = policy_offsets();
     __shared__ __align__(16) float s_m[60][kTok][4];
     __shared__ float s_b[60][kTok];
@@ -106,7 +109,11 @@ __global__ void __launch_bounds__(kTokWarps * 32) k_tokens(const float* __restri
     }
     float sum = 0.f;
 #pragma unroll
+#ifdef MM_TOK_FAST_EXP
+    for (int b = 0; b < kTok; b++) { p[b] = __expf(p[b] - m); sum += p[b]; }
+#else
     for (int b = 0; b < kTok; b++) { p[b] = expf(p[b] - m); sum += p[b]; }
+#endif
     const float inv = 1.f / sum;
     float ctx[kEmb];
 #pragma unroll
