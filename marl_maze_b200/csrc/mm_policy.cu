@@ -53,7 +53,7 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
 // values of the row's 23 tokens are exchanged through a small per-warp shared-memory tile (broadcast reads).
 constexpr int kTokWarps = 4;
 #ifndef MM_TOK_MINBLOCKS
-#define MM_TOK_MINBLOCKS 4
+#define MM_TOK_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_MINBLOCKS) k_tokens(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int R) {
     const PolicyOffsets o = policy_offsets();
