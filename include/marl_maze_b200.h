@@ -159,7 +159,10 @@ int mm_critic_forward(const float *weights, const float *obs, int n_envs, float 
 size_t mm_sizeof_policy_scratch(int n_envs);
 int mm_policy_forward(const float *weights, const float *obs, const uint8_t *masks, int n_envs, void *scratch, const uint8_t *actions_in,
                       uint8_t *actions_out, float *logp, float *value, float *logits_out, int env_offset, uint64_t seed, uint64_t counter,
-                      int flags, void *stream);
+                      int flags, const uint64_t *counter_dev, void *stream);
+/* counter_dev (may be NULL): device u64 added to `counter` inside the kernel, so that a captured CUDA graph of a whole rollout
+ * (counter = step index baked in, counter_dev bumped by mm_counter_add at the end of the graph) draws fresh numbers on every replay. */
+int mm_counter_add(uint64_t *counter_dev, uint64_t v, void *stream);
 #define MM_POLICY_TCGEN05 1 /* flags: trunk GEMMs as error-compensated 3xTF32 tcgen05.mma (TMA + TMEM); 0 = fp32 SIMT tiles */
 
 #ifdef __cplusplus

@@ -38,7 +38,7 @@ def _dist():
 class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
-                 verbose: bool = True, micro_batch: int = 1 << 17, update_tf32: bool = False):
+                 verbose: bool = True, micro_batch: int = 1 << 17, update_tf32: bool = False, use_cuda_graph: bool = True):
         if agent_amount != 2:
             raise NotImplementedError("two agents (README.md:34)")
         self.maze = None  # injected by Maze.__init__ (maze.py:40-42)
@@ -52,6 +52,9 @@ class PPO:
         self.updates_per_batch, self.mbatch_size, self.clip, self.max_grad = updates_per_batch, batch_size // 5, clip, max_grad
         self.horizon, self.seed, self.model_path, self.verbose, self.micro_batch = horizon, seed, model_path, verbose, micro_batch
         self.update_tf32 = update_tf32  # let cuBLAS use TF32 tensor cores in the autograd update (the reference is fp32; off by default)
+        self.use_cuda_graph = use_cuda_graph  # replay the T-step rollout (6 launches per step) as one captured CUDA graph from the 2nd rollout on
+        self._buf = None
+        self._graph = None
         self._runner: Optional[PolicyRunner] = None
         self._rollouts = 0
         self.last_stats: dict = {}
@@ -82,21 +85,37 @@ class PPO:
         if self._rollouts > 0 or maze._resets_since_fill > 0:
             maze.refill_pool()  # the reference builds a new maze for every episode (maze.py:57)
         dev = self.device
-        obs = torch.empty(T + 1, E, 2, 65, dtype=torch.float32, device=dev)
-        masks = torch.empty(T + 1, E, 2, 6, dtype=torch.uint8, device=dev)
-        actions = torch.empty(T, E, 2, 2, dtype=torch.uint8, device=dev)
-        logp = torch.empty(T, E, dtype=torch.float32, device=dev)
-        values = torch.empty(T + 1, E, dtype=torch.float32, device=dev)
-        reward = torch.empty(T, E, dtype=torch.float32, device=dev)
-        done = torch.empty(T, E, dtype=torch.uint8, device=dev)
+        key = (T, E, id(eng))
+        if self._buf is None or self._buf["key"] != key:  # rollout buffers live across rollouts (a captured graph holds their addresses)
+            self._buf = dict(key=key,
+                             obs=torch.empty(T + 1, E, 2, 65, dtype=torch.float32, device=dev), masks=torch.empty(T + 1, E, 2, 6, dtype=torch.uint8, device=dev),
+                             actions=torch.empty(T, E, 2, 2, dtype=torch.uint8, device=dev), logp=torch.empty(T, E, dtype=torch.float32, device=dev),
+                             values=torch.empty(T + 1, E, dtype=torch.float32, device=dev), reward=torch.empty(T, E, dtype=torch.float32, device=dev),
+                             done=torch.empty(T, E, dtype=torch.uint8, device=dev), adv=torch.empty(T, E, dtype=torch.float32, device=dev))
+            self._graph = None
+        b = self._buf
+        obs, masks, actions, logp, values, reward, done, adv = (b[k] for k in ("obs", "masks", "actions", "logp", "values", "reward", "done", "adv"))
         pol = self._policy()
         pol.refresh()
         maze.reset(obs=obs[0], masks=masks[0])  # PPO.py:104
-        for t in range(T):                      # PPO.py:108-141, one iteration = one step of every env
-            pol.forward(obs[t], masks[t], actions_out=actions[t], logp=logp[t], value=values[t])
-            eng.step(actions[t], auto_reset=True, obs=obs[t + 1], masks=masks[t + 1], reward=reward[t], done=done[t])
-        pol.values(obs[T], values[T])  # V(s_T) bootstraps the episodes still open at the horizon
-        adv = _gae(reward, values[:T], done, values[T], self.discount_rate, self.lam)
+
+        def body():  # launches only: no allocation, no host sync -> capturable
+            for t in range(T):  # PPO.py:108-141, one iteration = one step of every env
+                pol.forward(obs[t], masks[t], actions_out=actions[t], logp=logp[t], value=values[t], counter=t + 1)
+                eng.step(actions[t], auto_reset=True, obs=obs[t + 1], masks=masks[t + 1], reward=reward[t], done=done[t])
+            pol.values(obs[T], values[T])  # V(s_T) bootstraps the episodes still open at the horizon
+            _gae(reward, values[:T], done, values[T], self.discount_rate, self.lam, out=adv)
+            pol.bump(T)                    # next rollout / replay continues the sampling stream
+
+        if self.use_cuda_graph and T <= 2048 and self._rollouts >= 1:
+            if self._graph is None:  # the first rollout ran eagerly (lazy kernel attributes, tensor-map cache are warm): capture now
+                torch.cuda.synchronize(dev)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    body()
+            self._graph.replay()
+        else:
+            body()
         self._rollouts += 1
         maze._obs, maze._masks = obs[T], masks[T]
 

@@ -12,7 +12,7 @@ EXPORTS = [
     "mm_sizeof_env_episode", "mm_sizeof_agent_a", "mm_sizeof_agent_b", "mm_sizeof_finalize_scratch", "mm_sizeof_generate_scratch",
     "mm_init_state", "mm_load_layouts", "mm_generate", "mm_reset", "mm_step_obs",
     "mm_unpack_agents", "mm_unpack_envs", "mm_unpack_layout", "mm_unpack_pool", "mm_gae",
-    "mm_policy_offsets", "mm_sizeof_policy_scratch", "mm_policy_forward", "mm_critic_forward", "mm_selftest_div",
+    "mm_policy_offsets", "mm_sizeof_policy_scratch", "mm_policy_forward", "mm_critic_forward", "mm_selftest_div", "mm_counter_add",
 ]
 
 
@@ -69,7 +69,8 @@ def lib():
         "mm_sizeof_policy_scratch": (sz, [i32]),
         "mm_critic_forward": (i32, [vp, vp, i32, vp, vp]),
         "mm_selftest_div": (i32, [i32, i32, vp, vp]),
-        "mm_policy_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, u64, u64, i32, vp]),
+        "mm_policy_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, u64, u64, i32, vp, vp]),
+        "mm_counter_add": (i32, [vp, u64, vp]),
     }
     for name in EXPORTS:
         if not hasattr(L, name):

@@ -9,7 +9,8 @@ cudaError_t launch_gae(const float*, const float*, const uint8_t*, const float*,
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
                             uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, cudaStream_t stream);
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
-                          int, cudaStream_t);
+                          int, const uint64_t*, cudaStream_t);
+cudaError_t launch_add_u64(unsigned long long* p, unsigned long long v, cudaStream_t stream);
 int policy_offsets_host(int32_t* out);
 cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatches, cudaStream_t stream);
 cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream);
@@ -156,11 +157,15 @@ int mm_critic_forward(const float* weights, const float* obs, int n_envs, float*
 size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (460 + 2 * 264) * sizeof(float); }
 int mm_policy_forward(const float* weights, const float* obs, const uint8_t* masks, int n_envs, void* scratch, const uint8_t* actions_in,
                       uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter, int flags,
-                      void* stream) {
+                      const uint64_t* counter_dev, void* stream) {
     if (!weights || !obs || !masks || n_envs <= 0 || !scratch || !logp || (!actions_in && !actions_out)) return MM_ERR_BAD_ARG;
     if (((uintptr_t)weights & 15) || ((uintptr_t)scratch & 15)) return MM_ERR_BAD_ARG;
     return cuda_status(launch_policy(weights, obs, masks, n_envs, (float*)scratch, actions_in, actions_out, logp, value, logits_out, env_offset, seed,
-                                     counter, flags, (cudaStream_t)stream));
+                                     counter, flags, counter_dev, (cudaStream_t)stream));
+}
+int mm_counter_add(uint64_t* counter_dev, uint64_t v, void* stream) {
+    if (!counter_dev) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_add_u64((unsigned long long*)counter_dev, v, (cudaStream_t)stream));
 }
 
 }  // extern "C"

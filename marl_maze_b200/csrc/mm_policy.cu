@@ -278,10 +278,11 @@ cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_l
 // flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
                           uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter,
-                          int flags, cudaStream_t stream) {
+                          int flags, const uint64_t* counter_dev, cudaStream_t stream) {
     const PolicyOffsets o = policy_offsets();
     const int R = 2 * E;
     HeadArgs ha;
+    ha.counter_dev = counter_dev;
     ha.masks = masks; ha.actions_in = actions_in; ha.actions_out = actions_out; ha.logp = logp; ha.logits_out = logits_out;
     ha.E = E; ha.env_offset = env_offset; ha.seed = seed; ha.counter = counter;
     float* x0 = scratch;                      // [R,460]
@@ -305,4 +306,12 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
     return cudaGetLastError();
 }
 
+}  // namespace mm
+
+namespace mm {
+__global__ void k_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
+cudaError_t launch_add_u64(unsigned long long* p, unsigned long long v, cudaStream_t stream) {
+    k_add_u64<<<1, 1, 0, stream>>>(p, v);
+    return cudaGetLastError();
+}
 }  // namespace mm

@@ -14,6 +14,7 @@ struct HeadArgs {
     float* logits_out;           // [E][2][6] or nullptr
     int E, env_offset;
     uint64_t seed, counter;
+    const uint64_t* counter_dev;  // optional: the effective counter is counter + *counter_dev (lets a captured CUDA graph advance its stream)
 };
 
 // row = global agent row (2*env + agent).  Returns log pi(action | obs) for that agent; writes the sampled action / the logits.
@@ -30,7 +31,8 @@ __device__ __forceinline__ float head_sample_or_eval(const float l[6], const lon
     else {
         uint32_t r[4];
         const uint32_t env = (uint32_t)(row >> 1), a = (uint32_t)(row & 1);
-        philox4x32_10((uint32_t)h.counter, (uint32_t)(h.counter >> 32), (uint32_t)(h.env_offset + env) * 2u + a, 0x504f4c49u, (uint32_t)h.seed, (uint32_t)(h.seed >> 32), r);
+        const uint64_t ctr = h.counter + (h.counter_dev ? *h.counter_dev : 0ull);
+        philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(h.env_offset + env) * 2u + a, 0x504f4c49u, (uint32_t)h.seed, (uint32_t)(h.seed >> 32), r);
         const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * s;  // inverse CDF over the unnormalised masses
         float c = 0.f; move = -1; int last = 4;
         for (int j = 0; j < 5; j++) if (mk[j]) { last = j; c += p[j]; if (move < 0 && u < c) move = j; }

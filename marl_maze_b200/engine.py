@@ -174,11 +174,11 @@ class MazeEngine:
 
 
 def gae(reward: torch.Tensor, value: torch.Tensor, done: torch.Tensor, v_boot: Optional[torch.Tensor], gamma: float = 0.99,
-        lam: float = 0.95, with_rtg: bool = False):
+        lam: float = 0.95, with_rtg: bool = False, out: Optional[torch.Tensor] = None):
     """K3: PPO.get_GAEs over [T,E] buffers.  Returns adv (and rtg = adv + value when asked)."""
     T, E = reward.shape
     L = _abi.lib()
-    adv = torch.empty_like(reward)
+    adv = torch.empty_like(reward) if out is None else out
     rtg = torch.empty_like(reward) if with_rtg else None
     done = done.to(torch.uint8) if done.dtype != torch.uint8 else done
     for t in (reward, value, done):

@@ -79,12 +79,18 @@ class PolicyRunner:
         self.weights = pack_weights(actor, critic, self.device)
         self.scratch = torch.empty(int(self.lib.mm_sizeof_policy_scratch(self.E)), dtype=torch.uint8, device=self.device)
         self.counter = 0
+        self.counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)  # added to `counter` on the device (CUDA-graph replays)
         self.launches = 0
         self.flags = 1 if tensor_cores else 0  # MM_POLICY_TCGEN05
 
     def refresh(self):
-        """Re-pack after an optimiser step."""
-        self.weights = pack_weights(self.actor, self.critic, self.device)
+        """Re-pack after an optimiser step -- in place, so that captured CUDA graphs keep pointing at live weights."""
+        self.weights.copy_(pack_weights(self.actor, self.critic, self.device))
+
+    def bump(self, n: int):
+        """Advance the device-side counter by n (captured at the end of a rollout graph)."""
+        _abi.check(self.lib.mm_counter_add(C.c_void_p(self.counter_dev.data_ptr()), C.c_uint64(n),
+                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_counter_add")
 
     def values(self, obs: torch.Tensor, value: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Critic only (bootstrap value of the state after the last rollout step)."""
@@ -96,7 +102,8 @@ class PolicyRunner:
         return value
 
     def forward(self, obs: torch.Tensor, masks: torch.Tensor, actions_in: Optional[torch.Tensor] = None, actions_out: Optional[torch.Tensor] = None,
-                logp: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None, want_value: bool = True):
+                logp: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None, want_value: bool = True,
+                counter: Optional[int] = None):
         """Sample (actions_in None) or evaluate actions for all envs.  Returns (actions [E,2,2] u8, joint logp [E], value [E] | None)."""
         E = obs.shape[0]
         assert E <= self.E and obs.is_contiguous() and masks.is_contiguous() and obs.dtype == torch.float32 and masks.dtype == torch.uint8
@@ -106,9 +113,11 @@ class PolicyRunner:
         if want_value and value is None:
             value = torch.empty(E, dtype=torch.float32, device=self.device)
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        self.counter += 1
+        if counter is None:
+            self.counter += 1
+            counter = self.counter
         _abi.check(self.lib.mm_policy_forward(p(self.weights), p(obs), p(masks), E, p(self.scratch), p(actions_in), p(actions_out), p(logp),
-                                              p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(self.counter),
-                                              self.flags, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
+                                              p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(counter),
+                                              self.flags, p(self.counter_dev), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
         self.launches += (4 if self.flags & 1 else 5) + (1 if want_value else 0)  # tokens + 3 trunk layers (+ heads on the SIMT path) + critic
         return (actions_in if actions_in is not None else actions_out), logp, (value if want_value else None)

@@ -13,6 +13,7 @@ def _make(num_envs, tmp_path, batch_size=600, **kw):
     from marl_maze_b200.PPO import PPO
     from marl_maze_b200.maze import Maze
     from marl_maze_b200.maze_agent import Agent
+    os.makedirs(tmp_path, exist_ok=True)
     brain = PPO(agent_amount=2, batch_size=batch_size, lr=0.00014, epochs=1, verbose=False, model_path=str(tmp_path / "PPO.pth"), **kw)
     agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
     maze = Maze(agents=agents, max_timestep=120, rand_sizes=True, rand_range=[12, 13], rand_start=True, difficulty=1, default_size=[4, 4],
@@ -113,3 +114,22 @@ def test_reference_main_py_flow_single_env_train(tmp_path):
     brain.train()
     assert brain.last_stats["env_steps"] == 301 and brain.last_stats["num_envs"] == 1 and brain.last_stats["episodes"] >= 4
     assert (tmp_path / "PPO.pth").exists() and brain.last_update["steps"] == 25
+
+
+def test_cuda_graph_rollout_equals_eager_rollout(tmp_path):
+    """From the second rollout on, get_batch replays one captured CUDA graph (T x 6 launches); it must produce exactly what the
+    eager launches produce, rollout after rollout (the sampling stream advances through a device-side counter)."""
+    outs = {}
+    for mode in (False, True):
+        brain, agents, maze = _make(128, tmp_path / f"g{int(mode)}", batch_size=128 * 24 - 2, horizon=24, use_cuda_graph=mode)
+        res = []
+        for _ in range(3):
+            b = brain.get_batch()
+            res.append([b[0].clone(), b[1].clone(), b[2].clone(), b[5].clone(), b[6].clone(), b[7].clone()])
+        outs[mode] = res
+        assert int(brain._policy().counter_dev.item()) == 3 * 24
+        assert (brain._graph is not None) == mode
+    for r_e, r_g in zip(outs[False], outs[True]):
+        for x, y in zip(r_e, r_g):
+            assert torch.equal(x, y)
+    assert not torch.equal(outs[True][1][1], outs[True][2][1])  # different rollouts draw different actions
