@@ -291,8 +291,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="mazes per GPU")
     ap.add_argument("--e2e-steps", type=int, default=24)
-    ap.add_argument("--cpu-envs", type=int, default=32768)
-    ap.add_argument("--cpu-steps", type=int, default=400)
+    ap.add_argument("--cpu-envs", type=int, default=65536)
+    ap.add_argument("--cpu-steps", type=int, default=1200)  # ~10 s of CPU work on a 16-thread host
     ap.add_argument("--ref-envs", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
