@@ -398,11 +398,7 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
         if (act) {
             me.last_mask = mask6;
             // -------------------------------------------------------- observation vector (maze_agent.py:92-130)
-#ifdef MM_K2_DIRECT_STORE
-            float* so = p.obs + g * kObs;  // experiment: no shared-memory staging (uncoalesced 4-byte stores)
-#else
             float* so = stage + lane * kObs;
-#endif
             const uint32_t OWNr = __funnelshift_r(OWN32, OWN32, 8 * f), OTHr = __funnelshift_r(OTH32, OTH32, 8 * f);
             const uint32_t keyr = visK ? (1u << rK) : 0u;
 #pragma unroll
@@ -466,7 +462,6 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
     }
 
     // ---------------------------------------------------------------- observations: shared memory -> HBM, coalesced per warp
-#ifndef MM_K2_DIRECT_STORE
     __syncwarp();
     const uint32_t wmask = __ballot_sync(kFull, wrote);
     const long long gbase = g - lane;
@@ -497,7 +492,6 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
             for (int i = lane; i < kObs; i += 32) o[i] = s[i];
         }
     }
-#endif
 }
 
 // kGroups = 2: every warp carries TWO groups of 32 agents through the kernel, software-pipelined -- both groups' state loads and
