@@ -83,7 +83,7 @@ class Maze:
         if self.num_envs == 1 and not torch.is_tensor(action):
             a = torch.tensor([[int(action[0][0]), int(action[0][1])], [int(action[1][0]), int(action[1][1])]], dtype=torch.uint8).view(1, 2, 2)
             action = a.to(self.device)
-        elif torch.is_tensor(action) and (action.dtype != torch.uint8 or not action.is_contiguous() or action.device != self.device):
+        elif torch.is_tensor(action) and (action.dtype != torch.uint8 or not action.is_contiguous() or action.device.type != self.device.type):
             action = action.to(device=self.device, dtype=torch.uint8).reshape(self.num_envs, 2, 2).contiguous()  # e.g. the float [E,2,2] of PPO.get_batch
         auto = (self.num_envs > 1) if auto_reset is None else auto_reset
         self._obs, self._masks, r, d = eng.step(action, auto_reset=auto, **out)
