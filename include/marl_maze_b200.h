@@ -165,6 +165,44 @@ int mm_policy_forward(const float *weights, const float *obs, const uint8_t *mas
 int mm_counter_add(uint64_t *counter_dev, uint64_t v, void *stream);
 #define MM_POLICY_TCGEN05 1 /* flags: trunk GEMMs as error-compensated 3xTF32 tcgen05.mma (TMA + TMEM); 0 = fp32 SIMT tiles */
 
+/*
+ * K5 -- building blocks of the PPO actor update (PPO.py:58-85: loss.backward() through Actor.layers), SURVEY 8(f).1.
+ *
+ * mm_wgrad_tf32x3: weight + bias gradient of one Linear layer.  dz [rows][n_out] f32 = gradient at the layer's pre-activation, h
+ * [rows][k_in] f32 = the layer's input.  Writes `slabs` partial sums part [slabs][n_out][ld] (geometry from mm_wgrad_geometry):
+ *     sum_s part[s][n][k]    = dW[n][k] = sum_r dz[r][n] h[r][k]   for k < k_in,
+ *     sum_s part[s][n][k_in] = db[n]    = sum_r dz[r][n]
+ * computed as 3xTF32 tcgen05.mma with fp32 accumulation; n_out and k_in must be multiples of 4, base pointers 16-byte aligned.
+ */
+int mm_wgrad_geometry(int rows, int n_out, int k_in, int32_t *slabs, int32_t *ld);
+int mm_wgrad_tf32x3(const float *dz, const float *h, int rows, int n_out, int k_in, float *part, void *stream);
+
+/*
+ * mm_linear_tf32x3: the trunk GEMM of K4 as a stand-alone call, y = epi(x W^T) with x [rows][k] f32 and W [n_rows_w <= 264][k] given as
+ * its TF32 split (w_hi = tf32(W), w_lo = tf32(W - w_hi), both round-to-nearest).  Forward of a layer: mode MM_LINEAR_RELU, W = the
+ * layer's weight, y = relu(. + bias) (Actor.forward, networks.py:36-38).  Data gradient of a layer: W = the layer's weight TRANSPOSED,
+ * x = dZ, mode MM_LINEAR_GATE (y = acc where gate > 0 else 0; gate [rows][264] = the ReLU output below) or MM_LINEAR_PLAIN (y = acc).
+ * n_rows_w columns are written with row pitch ldy (floats), so a wider result (the 460-wide dX of layer 0) is made of column blocks.
+ */
+#define MM_LINEAR_RELU 0
+#define MM_LINEAR_GATE 2
+#define MM_LINEAR_PLAIN 3
+int mm_linear_tf32x3(const float *x, int rows, int k, const float *w_hi, const float *w_lo, int n_rows_w, const float *bias,
+                     const float *gate, float *y, int ldy, int mode, void *stream);
+
+/*
+ * mm_ppo_heads_loss: heads + clipped surrogate, forward and backward (PPO.get_log_probs PPO.py:154-168 for both agents; ratio, clip,
+ * loss PPO.py:66-72; autograd down to the last trunk activation).  h2 [2E][264] f32 = last trunk activation (agent rows 2e, 2e+1),
+ * head_w [6][264] (5 move rows + mark row), head_b [6], masks [2E][6] u8, actions [2E][2] u8 (move, mark), old_logp [E], adv [E].
+ *   loss   = scale * sum_e -min(ratio_e A_e, clamp(ratio_e, 1-clip, 1+clip) A_e),   ratio_e = exp(joint_e - old_logp_e)
+ * Outputs: dz2 [2E][264] = dloss/d(pre-activation of the last trunk layer); logp [E] = joint_e (may be NULL); part [blocks][ld]
+ * (mm_ppo_loss_geometry) per-block partial sums: [0, 6*264) dloss/dhead_w, [6*264, 6*264+6) dloss/dhead_b, [6*264+6] loss.
+ */
+int mm_ppo_loss_geometry(int32_t *blocks, int32_t *ld);
+int mm_ppo_heads_loss(const float *h2, const float *head_w, const float *head_b, const uint8_t *masks, const uint8_t *actions,
+                      const float *old_logp, const float *adv, int n_envs, float clip, float scale, float *dz2, float *logp,
+                      float *part, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,9 +10,12 @@ here loads in the reference.  What changes is how a batch is produced:
                                        in-launch auto-reset), writing straight into the [T+1,E,...] rollout buffers;
                                        advantages by K3 (reverse scan; episodes still open at T are bootstrapped)
 
-The update (PPO.py:46-85) stays PyTorch autograd over networks.Actor/Critic -- clipped surrogate on the JOINT ratio of
-both agents, MSE critic, grad-norm clip 0.5, two Adams, lr x0.997 per update -- with gradients averaged over ranks
-(NCCL) when torch.distributed is initialised, and advantage statistics taken over all ranks.
+The update (PPO.py:46-85) keeps the reference's schedule -- clipped surrogate on the JOINT ratio of both agents, MSE
+critic, grad-norm clip 0.5, two Adams, lr x0.997 per update -- with gradients averaged over ranks (NCCL) when
+torch.distributed is initialised and advantage statistics taken over all ranks.  The actor's trunk, heads and loss run
+forward AND backward in hand-written kernels (K5, update.py: tcgen05 3xTF32 GEMMs for the forward, data-gradient and
+weight-gradient passes); the 23-token embedding in front of it and the small critic stay PyTorch autograd
+(`fused_update=False` puts the whole update back on autograd).
 """
 from __future__ import annotations
 
@@ -23,6 +26,7 @@ from typing import Optional
 import numpy as np
 import torch
 
+from . import update as _upd
 from .engine import gae as _gae
 from .networks import Actor, Critic
 from .policy import PolicyRunner
@@ -38,7 +42,8 @@ def _dist():
 class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
-                 verbose: bool = True, micro_batch: int = 1 << 17, update_tf32: bool = False, use_cuda_graph: bool = True):
+                 verbose: bool = True, micro_batch: int = 1 << 17, update_tf32: bool = False, use_cuda_graph: bool = True,
+                 fused_update: bool = True):
         if agent_amount != 2:
             raise NotImplementedError("two agents (README.md:34)")
         self.maze = None  # injected by Maze.__init__ (maze.py:40-42)
@@ -52,6 +57,7 @@ class PPO:
         self.updates_per_batch, self.mbatch_size, self.clip, self.max_grad = updates_per_batch, batch_size // 5, clip, max_grad
         self.horizon, self.seed, self.model_path, self.verbose, self.micro_batch = horizon, seed, model_path, verbose, micro_batch
         self.update_tf32 = update_tf32  # let cuBLAS use TF32 tensor cores in the autograd update (the reference is fp32; off by default)
+        self.fused_update = fused_update  # actor trunk + heads + clipped surrogate, fwd and bwd, as hand-written tcgen05 3xTF32 kernels (update.py)
         self.use_cuda_graph = use_cuda_graph  # replay the T-step rollout (6 launches per step) as one captured CUDA graph from the 2nd rollout on
         self._buf = None
         self._graph = None
@@ -230,6 +236,7 @@ class PPO:
         used = min(self.batch_size, N)
         mb = max(1, self.mbatch_size if self.batch_size <= N else N // 5)
         stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0)
+        fused = self.fused_update and _upd.fused_available(self.actor)
         for _ in range(self.updates_per_batch):
             self.decay_lr()
             for start in range(0, used, mb):
@@ -240,10 +247,14 @@ class PPO:
                 for s0 in range(0, n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
                     j = idx[s0:s0 + self.micro_batch]
                     m_obs, m_act, m_masks = b_obs[j], b_actions[j], b_masks[j]
-                    cur = self.joint_log_probs(m_obs, m_act, m_masks)
-                    ratio = torch.exp(cur - b_log_probs[j])
                     adv = b_advs[j]
-                    loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
+                    if fused:  # K5: trunk + heads + clipped surrogate, forward and backward, in hand-written kernels (update.py)
+                        loss, _ = _upd.actor_loss(self.actor, m_obs.reshape(-1, m_obs.shape[-1]), m_masks.reshape(-1, 6), m_act.reshape(-1, 2),
+                                                  b_log_probs[j], adv, self.clip, 1.0 / n)
+                    else:
+                        cur = self.joint_log_probs(m_obs, m_act, m_masks)
+                        ratio = torch.exp(cur - b_log_probs[j])
+                        loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
                     loss.backward()
                     a_loss += float(loss.detach())
                 self._allreduce_grads(self.actor)

@@ -13,6 +13,7 @@ EXPORTS = [
     "mm_init_state", "mm_load_layouts", "mm_generate", "mm_reset", "mm_step_obs",
     "mm_unpack_agents", "mm_unpack_envs", "mm_unpack_layout", "mm_unpack_pool", "mm_gae",
     "mm_policy_offsets", "mm_sizeof_policy_scratch", "mm_policy_forward", "mm_critic_forward", "mm_selftest_div", "mm_counter_add",
+    "mm_wgrad_geometry", "mm_wgrad_tf32x3", "mm_linear_tf32x3", "mm_ppo_loss_geometry", "mm_ppo_heads_loss",
 ]
 
 
@@ -71,6 +72,11 @@ def lib():
         "mm_selftest_div": (i32, [i32, i32, vp, vp]),
         "mm_policy_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, u64, u64, i32, vp, vp]),
         "mm_counter_add": (i32, [vp, u64, vp]),
+        "mm_wgrad_geometry": (i32, [i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "mm_wgrad_tf32x3": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+        "mm_linear_tf32x3": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp]),
+        "mm_ppo_loss_geometry": (i32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "mm_ppo_heads_loss": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]),
     }
     for name in EXPORTS:
         if not hasattr(L, name):

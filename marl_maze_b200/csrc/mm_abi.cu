@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <string.h>
 #include "mm_env.cuh"
+#include "mm_update.cuh"
 
 namespace mm {
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream);
@@ -166,6 +167,40 @@ int mm_policy_forward(const float* weights, const float* obs, const uint8_t* mas
 int mm_counter_add(uint64_t* counter_dev, uint64_t v, void* stream) {
     if (!counter_dev) return MM_ERR_BAD_ARG;
     return cuda_status(launch_add_u64((unsigned long long*)counter_dev, v, (cudaStream_t)stream));
+}
+
+int mm_wgrad_geometry(int rows, int n_out, int k_in, int32_t* slabs, int32_t* ld) {
+    if (rows <= 0 || n_out <= 0 || k_in <= 0 || !slabs || !ld) return MM_ERR_BAD_ARG;
+    int s, l, per;
+    wgrad_geometry(rows, n_out, k_in, &s, &l, &per);
+    *slabs = s; *ld = l;
+    return MM_OK;
+}
+int mm_wgrad_tf32x3(const float* dz, const float* h, int rows, int n_out, int k_in, float* part, void* stream) {
+    if (!dz || !h || !part || rows <= 0 || n_out <= 0 || k_in <= 0 || (n_out & 3) || (k_in & 3)) return MM_ERR_BAD_ARG;
+    if (((uintptr_t)dz & 15) || ((uintptr_t)h & 15) || ((uintptr_t)part & 15)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_wgrad_tc(dz, h, rows, n_out, k_in, part, (cudaStream_t)stream));
+}
+
+int mm_linear_tf32x3(const float* x, int rows, int k, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, const float* gate, float* y,
+                     int ldy, int mode, void* stream) {
+    if (!x || !w_hi || !w_lo || !y || rows <= 0 || k <= 0 || n_rows_w <= 0 || n_rows_w > 264 || ldy < n_rows_w) return MM_ERR_BAD_ARG;
+    if (mode != MM_LINEAR_RELU && mode != MM_LINEAR_GATE && mode != MM_LINEAR_PLAIN) return MM_ERR_BAD_ARG;
+    if ((mode == MM_LINEAR_RELU && !bias) || (mode == MM_LINEAR_GATE && (!gate || n_rows_w != 264))) return MM_ERR_BAD_ARG;
+    if (((uintptr_t)x & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15) || ((uintptr_t)y & 15) || ((uintptr_t)gate & 15) || (k & 3) || (ldy & 3) || (n_rows_w & 3))
+        return MM_ERR_BAD_ARG;
+    return cuda_status(launch_linear_tc_ex(x, w_hi, w_lo, n_rows_w, bias, y, ldy, rows, k, mode, gate, nullptr, nullptr, nullptr, (cudaStream_t)stream));
+}
+int mm_ppo_loss_geometry(int32_t* blocks, int32_t* ld) {
+    if (!blocks || !ld) return MM_ERR_BAD_ARG;
+    *blocks = ppo_loss_blocks(); *ld = ppo_loss_part_ld();
+    return MM_OK;
+}
+int mm_ppo_heads_loss(const float* h2, const float* head_w, const float* head_b, const uint8_t* masks, const uint8_t* actions, const float* old_logp,
+                      const float* adv, int n_envs, float clip, float scale, float* dz2, float* logp, float* part, void* stream) {
+    if (!h2 || !head_w || !head_b || !masks || !actions || !old_logp || !adv || !dz2 || !part || n_envs <= 0) return MM_ERR_BAD_ARG;
+    PpoLossArgs a{h2, head_w, head_b, masks, actions, old_logp, adv, clip, scale, dz2, logp, part, n_envs};
+    return cuda_status(launch_ppo_heads_loss(a, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include "mm_env.cuh"
 #include "mm_policy_heads.cuh"
+#include "mm_tc.cuh"
 
 namespace mm {
 
@@ -37,53 +38,27 @@ constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_TMEM_COLS = 512;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait(b, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(map),
-                 "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 1024 bytes.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(TC_ATOM_BYTES >> 4) << 32) | ((uint64_t)1 << 46) | (TC_LAYOUT << 61);
 }
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc),
-                 "r"(accumulate)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 struct TcMaps {
     CUtensorMap a, w1_hi, w2_hi, w1_lo, w2_lo;
 };
 
-// kHeads: this is the last trunk layer -- instead of storing y, the epilogue contracts each row with the 6 head rows (5 move logits +
-// 1 mark logit), masks, samples (or evaluates) the action and writes actions + the env's joint log-prob: "sampling fused in the epilogue".
-template <bool kHeads>
+// Epilogue modes.  TC_EPI_RELU: y = relu(acc + bias).  TC_EPI_HEADS: this is the last trunk layer -- instead of storing y, the epilogue
+// contracts each row with the 6 head rows (5 move logits + 1 mark logit), masks, samples (or evaluates) the action and writes actions +
+// the env's joint log-prob: "sampling fused in the epilogue".  TC_EPI_GATE / TC_EPI_PLAIN are the backward (data-gradient) uses of the
+// same GEMM, dH = dZ W: y = acc * (gate > 0) with gate = the ReLU output the gradient flows back through, or y = acc; n_valid columns
+// are stored with row pitch ldy (the 460-wide dX of the first layer is produced as two column blocks).
+enum { TC_EPI_RELU = 0, TC_EPI_HEADS = 1, TC_EPI_GATE = 2, TC_EPI_PLAIN = 3 };
+template <int kMode>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y, int M, int K, const float* __restrict__ head_w,
-                const float* __restrict__ head_b, const HeadArgs heads) {
+                const float* __restrict__ head_b, const HeadArgs heads, const float* __restrict__ gate, int n_valid, int ldy) {
+    constexpr bool kHeads = kMode == TC_EPI_HEADS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -186,6 +161,14 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 9; c++) {  // 9 x 32 columns >= 264
+            float4 gt[8];  // TC_EPI_GATE: the gate values of this chunk's store pattern, requested before the TMEM load so their latency overlaps it
+            if (kMode == TC_EPI_GATE) {
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int r = it * 4 + (lane >> 3), col = c * 32 + 4 * (lane & 7);
+                    gt[it] = (row0 + r < M && col < n_valid) ? __ldg(reinterpret_cast<const float4*>(gate + (size_t)(row0 + r) * TC_N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             uint32_t v[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -200,7 +183,8 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int col = c * 32 + 4 * q + j;
-                    yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f), 0.f);
+                    if (kMode == TC_EPI_RELU || kMode == TC_EPI_HEADS) yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f), 0.f);
+                    else yv[j] = __uint_as_float(v[4 * q + j]);
                 }
                 if (kHeads) {
                     if (c * 32 + 4 * q < TC_N) {  // TC_N is a multiple of 4: whole float4 groups are in or out
@@ -220,8 +204,14 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             for (int it = 0; it < 8; it++) {  // 4 rows x 128 contiguous bytes per instruction
                 const int r = it * 4 + (lane >> 3), c4 = lane & 7;
                 const int col = c * 32 + 4 * c4;
-                if (row0 + r < M && col < TC_N)
-                    *reinterpret_cast<float4*>(y + (size_t)(row0 + r) * TC_N + col) = *reinterpret_cast<const float4*>(&t_y[r * kTP + 4 * c4]);
+                if (row0 + r < M && col < n_valid) {
+                    float4 o = *reinterpret_cast<const float4*>(&t_y[r * kTP + 4 * c4]);
+                    if (kMode == TC_EPI_GATE) {
+                        const float4 g = gt[it];
+                        o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(y + (size_t)(row0 + r) * ldy + col) = o;
+                }
             }
             __syncwarp();
         }
@@ -247,17 +237,6 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
 // fp32 row-major [rows][cols] with a {32 cols x box_rows} box, 128-byte swizzle, zero fill out of bounds
 static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int box_rows) {
     PFN_encodeTiled enc = get_encode();
@@ -271,40 +250,64 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Y = relu(X W^T + b) with X [M][K] plain fp32, W as the host-made split (w_hi, w_lo) [264][K]; writes plain fp32 y [M][264] -- or, when
-// `heads` is given (last layer), runs heads + sampling in the epilogue and writes actions / log-probs instead of y.
-cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
-                             const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
+// Y = epi(X W^T) with X [M][K] plain fp32 and W given as the split (w_hi, w_lo) [n_rows_w][K], n_rows_w <= 264.  mode TC_EPI_RELU writes
+// y = relu(. + bias) [M][264]; TC_EPI_HEADS (last layer, `heads` given) runs heads + sampling in the epilogue and writes actions / log-probs
+// instead of y; TC_EPI_GATE / TC_EPI_PLAIN write n_rows_w columns with row pitch ldy (gate [M][264]).
+cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, float* y, int ldy, int M, int K, int mode,
+                                const float* gate, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
     // The rollout calls this with the same scratch / weight pointers every step: keep the encoded maps (a tensor map depends only on
     // base pointer, extents and box) in a small per-thread cache instead of re-encoding 15 of them per policy step.
-    struct Entry { const float *x, *wh, *wl; int M, K; TcMaps maps; };
+    struct Entry { const float *x, *wh, *wl; int M, K, nw; TcMaps maps; };
     static thread_local Entry cache[8];
     static thread_local int next_slot = 0;
+    if (n_rows_w <= 0 || n_rows_w > TC_N || (n_rows_w & 3) || (ldy & 3) || (K & 3)) return cudaErrorInvalidValue;
     const TcMaps* found = nullptr;
     for (int i = 0; i < 8; i++)
-        if (cache[i].x == x && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].M == M && cache[i].K == K) { found = &cache[i].maps; break; }
+        if (cache[i].x == x && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].M == M && cache[i].K == K && cache[i].nw == n_rows_w) { found = &cache[i].maps; break; }
     if (!found) {
         Entry& e = cache[next_slot];
         next_slot = (next_slot + 1) % 8;
         e.x = nullptr;
-        if (!make_map(&e.maps.a, x, M, K, TC_BM) || !make_map(&e.maps.w1_hi, w_hi, TC_N, K, TC_N1) || !make_map(&e.maps.w2_hi, w_hi, TC_N, K, TC_N2) ||
-            !make_map(&e.maps.w1_lo, w_lo, TC_N, K, TC_N1) || !make_map(&e.maps.w2_lo, w_lo, TC_N, K, TC_N2))
+        if (!make_map(&e.maps.a, x, M, K, TC_BM) || !make_map(&e.maps.w1_hi, w_hi, n_rows_w, K, TC_N1) || !make_map(&e.maps.w2_hi, w_hi, n_rows_w, K, TC_N2) ||
+            !make_map(&e.maps.w1_lo, w_lo, n_rows_w, K, TC_N1) || !make_map(&e.maps.w2_lo, w_lo, n_rows_w, K, TC_N2))
             return cudaErrorInvalidValue;
-        e.x = x; e.wh = w_hi; e.wl = w_lo; e.M = M; e.K = K;
+        e.x = x; e.wh = w_hi; e.wl = w_lo; e.M = M; e.K = K; e.nw = n_rows_w;
         found = &e.maps;
     }
     const TcMaps& maps = *found;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int blocks = (M + TC_BM - 1) / TC_BM;
-    if (heads) k_linear_tf32x3<true><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, nullptr, M, K, head_w, head_b, *heads);
-    else k_linear_tf32x3<false><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K, nullptr, nullptr, HeadArgs{});
+    switch (mode) {
+    case TC_EPI_HEADS:
+        if (!heads) return cudaErrorInvalidValue;
+        k_linear_tf32x3<TC_EPI_HEADS><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, nullptr, M, K, head_w, head_b, *heads, nullptr, TC_N, TC_N);
+        break;
+    case TC_EPI_RELU:
+        k_linear_tf32x3<TC_EPI_RELU><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, n_rows_w, ldy);
+        break;
+    case TC_EPI_GATE:
+        if (!gate || n_rows_w != TC_N) return cudaErrorInvalidValue;
+        k_linear_tf32x3<TC_EPI_GATE><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, gate, n_rows_w, ldy);
+        break;
+    case TC_EPI_PLAIN:
+        k_linear_tf32x3<TC_EPI_PLAIN><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, n_rows_w, ldy);
+        break;
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
+}
+
+cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
+                             const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
+    return launch_linear_tc_ex(x, w_hi, w_lo, TC_N, bias, y, TC_N, M, K, heads ? TC_EPI_HEADS : TC_EPI_RELU, nullptr, head_w, head_b, heads, stream);
 }
 
 }  // namespace mm

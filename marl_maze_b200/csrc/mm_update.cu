@@ -1,0 +1,149 @@
+// mm_update.cu -- K5: heads + clipped-surrogate loss of the PPO actor update, forward AND backward in one pass (PPO.py:58-76:
+// get_log_probs for both agents, ratio, min(ratio*A, clip(ratio)*A), loss.backward() down to the last trunk activation).
+//
+// Per env e (agent rows 2e, 2e+1 of the last trunk activation H2 [2E][264]):
+//     logits = H2 Wh^T + bh            (5 move logits + 1 mark logit per agent)
+//     joint  = sum_agents  log softmax_masked(move logits)[move] + log(mark ? p : 1-p),  p = sigmoid(mark logit) if mask[5] else 0
+//     ratio  = exp(joint - old_logp[e]);  loss_e = -min(ratio*A, clamp(ratio, 1-c, 1+c)*A) * scale
+// and, with G = dloss/djoint = -[ratio within the clip range or ratio*A < clamp(ratio)*A] * A * ratio * scale (torch's minimum /
+// clamp sub-gradients), the gradient at the logits is G*(onehot - softmax) on legal moves and G*(mark - p) on an enabled mark logit.
+// The kernel writes dZ2 = (dlogits Wh) * (H2 > 0) -- the gradient at the last trunk layer's pre-activation -- and per-block partial sums
+// of dWh = dlogits^T H2, dbh = sum dlogits and the loss; the host adds the partials (deterministic, no atomics).
+// One warp walks envs; a lane owns columns lane, lane+32, ... of the 264-wide rows (coalesced 128-byte segments).
+#include "mm_env.cuh"
+#include "mm_update.cuh"
+
+namespace mm {
+
+constexpr int UL_HID = 264, UL_CPL = 9 /* columns per lane, the 9th only for lanes 0-7 */, UL_WARPS = 4;
+constexpr int UL_PART_LD = 6 * UL_HID + 8;  // dWh [6][264], dbh [6], loss, unused
+
+__global__ void __launch_bounds__(UL_WARPS * 32, 3) k_ppo_heads_loss(const PpoLossArgs a) {
+    __shared__ float s_w[6][UL_HID];
+    __shared__ float s_acc[6 * UL_HID + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 6 * UL_HID; i += blockDim.x) s_w[i / UL_HID][i % UL_HID] = a.head_w[i];
+    for (int i = threadIdx.x; i < 6 * UL_HID + 8; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    float bh[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) bh[j] = __ldg(&a.head_b[j]);
+
+    float accw[6][UL_CPL], accb[6], loss_acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        accb[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < UL_CPL; i++) accw[j][i] = 0.f;
+    }
+    const bool tail = lane < UL_HID - 8 * 32;  // lanes 0-7 own a 9th column
+    const int wglobal = blockIdx.x * UL_WARPS + warp, wstride = gridDim.x * UL_WARPS;
+    for (int e = wglobal; e < a.E; e += wstride) {
+        float hv[2][UL_CPL], l[2][6];
+#pragma unroll
+        for (int ag = 0; ag < 2; ag++) {
+            const float* hr = a.h2 + (size_t)(2 * e + ag) * UL_HID;
+#pragma unroll
+            for (int i = 0; i < 8; i++) hv[ag][i] = __ldg(hr + lane + 32 * i);
+            hv[ag][8] = tail ? __ldg(hr + lane + 256) : 0.f;
+        }
+#pragma unroll
+        for (int ag = 0; ag < 2; ag++)
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) s = fmaf(hv[ag][i], s_w[j][lane + 32 * i], s);
+                if (tail) s = fmaf(hv[ag][8], s_w[j][lane + 256], s);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                l[ag][j] = s + bh[j];
+            }
+        // ---- distribution math, identical on every lane (PPO.py:154-168)
+        float dl[2][6], joint = 0.f, pm[2], inv_s[2], pk[2][5];
+        int mv[2], mkb[2];
+        bool legal[2][6];
+#pragma unroll
+        for (int ag = 0; ag < 2; ag++) {
+            const uint8_t* mk = a.masks + (size_t)(2 * e + ag) * 6;
+#pragma unroll
+            for (int j = 0; j < 6; j++) legal[ag][j] = mk[j] != 0;
+            mv[ag] = a.actions[(size_t)(2 * e + ag) * 2];
+            mkb[ag] = a.actions[(size_t)(2 * e + ag) * 2 + 1] != 0;
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 5; j++) if (legal[ag][j]) m = fmaxf(m, l[ag][j]);
+            float s = 0.f, lsel = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                pk[ag][j] = legal[ag][j] ? expf(l[ag][j] - m) : 0.f;
+                s += pk[ag][j];
+                if (j == mv[ag] && legal[ag][j]) lsel = l[ag][j];
+            }
+            inv_s[ag] = 1.f / s;
+            pm[ag] = legal[ag][5] ? 1.f / (1.f + expf(-l[ag][5])) : 0.f;
+            joint += ((lsel - m) - logf(s)) + logf(mkb[ag] ? pm[ag] : 1.f - pm[ag]);
+        }
+        const float A = __ldg(&a.adv[e]);
+        const float ratio = expf(joint - __ldg(&a.old_logp[e]));
+        const float lo = 1.f - a.clip, hi = 1.f + a.clip;
+        const float s1 = ratio * A, s2 = fminf(fmaxf(ratio, lo), hi) * A;
+        const bool pass = (ratio >= lo && ratio <= hi) || s1 < s2;
+        const float G = pass ? -A * ratio * a.scale : 0.f;
+        loss_acc += -fminf(s1, s2) * a.scale;
+        if (lane == 0 && a.logp) a.logp[e] = joint;
+#pragma unroll
+        for (int ag = 0; ag < 2; ag++) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) dl[ag][j] = legal[ag][j] ? G * ((j == mv[ag] ? 1.f : 0.f) - pk[ag][j] * inv_s[ag]) : 0.f;
+            dl[ag][5] = legal[ag][5] ? G * ((mkb[ag] ? 1.f : 0.f) - pm[ag]) : 0.f;
+        }
+        // ---- backward through the heads and the last ReLU; head weight / bias gradient partial sums
+#pragma unroll
+        for (int ag = 0; ag < 2; ag++) {
+            float* zr = a.dz2 + (size_t)(2 * e + ag) * UL_HID;
+#pragma unroll
+            for (int i = 0; i < UL_CPL; i++) {
+                if (i == 8 && !tail) break;
+                const int c = lane + 32 * i;
+                float g = 0.f;
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    g = fmaf(dl[ag][j], s_w[j][c], g);
+                    accw[j][i] = fmaf(dl[ag][j], hv[ag][i], accw[j][i]);
+                }
+                zr[c] = hv[ag][i] > 0.f ? g : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; j++) accb[j] += dl[ag][j];
+        }
+    }
+    // ---- block reduction in a fixed warp order (deterministic), then one partial row per block
+    for (int w = 0; w < UL_WARPS; w++) {
+        if (warp == w) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) s_acc[j * UL_HID + lane + 32 * i] += accw[j][i];
+                if (tail) s_acc[j * UL_HID + lane + 256] += accw[j][8];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) s_acc[6 * UL_HID + j] += accb[j];
+                s_acc[6 * UL_HID + 6] += loss_acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < UL_PART_LD; i += blockDim.x) a.part[(size_t)blockIdx.x * UL_PART_LD + i] = s_acc[i];
+}
+
+int ppo_loss_blocks() { return 3 * 148; }
+int ppo_loss_part_ld() { return UL_PART_LD; }
+
+cudaError_t launch_ppo_heads_loss(const PpoLossArgs& a, cudaStream_t stream) {
+    k_ppo_heads_loss<<<ppo_loss_blocks(), UL_WARPS * 32, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mm

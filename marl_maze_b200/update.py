@@ -1,0 +1,137 @@
+"""Host side of the PPO actor update kernels (K5; PPO.py:58-85 of the reference = loss.backward() through the actor + the clipped
+surrogate).  Thin wrappers over the C ABI: torch owns every buffer, the library borrows pointers for the duration of a call."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def wgrad(dz: torch.Tensor, h: torch.Tensor):
+    """(dW [n_out,k_in], db [n_out]) = (dz^T h, column sums of dz) for one Linear layer, 3xTF32 on tcgen05 (mm_wgrad_tf32x3)."""
+    assert dz.is_cuda and h.is_cuda and dz.dtype == h.dtype == torch.float32 and dz.is_contiguous() and h.is_contiguous()
+    R, n_out = dz.shape
+    k_in = h.shape[1]
+    assert h.shape[0] == R
+    L = _abi.lib()
+    slabs, ld = C.c_int32(), C.c_int32()
+    _abi.check(L.mm_wgrad_geometry(R, n_out, k_in, C.byref(slabs), C.byref(ld)), "mm_wgrad_geometry")
+    part = torch.empty(slabs.value, n_out, ld.value, device=dz.device, dtype=torch.float32)
+    _abi.check(L.mm_wgrad_tf32x3(_ptr(dz), _ptr(h), R, n_out, k_in, _ptr(part), _stream(dz)), "mm_wgrad_tf32x3")
+    tot = part.sum(0)
+    return tot[:, :k_in], tot[:, k_in]
+
+
+MM_LINEAR_RELU, MM_LINEAR_GATE, MM_LINEAR_PLAIN = 0, 2, 3
+
+
+def tf32_split(w: torch.Tensor):
+    """w = hi + lo with hi = tf32(w), lo = tf32(w - hi), round-to-nearest (the operand form mm_linear_tf32x3 takes)."""
+    w = w.detach().contiguous()
+    hi = ((w.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    r = w - hi
+    return hi, ((r.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
+def linear_tc(x, w_split, mode, bias=None, gate=None, out=None, col0=0):
+    """out[:, col0:col0+n] = epi(x @ W^T) for W [n<=264, k] given as tf32_split(W); out defaults to a fresh [rows, n] tensor."""
+    w_hi, w_lo = w_split
+    rows, k = x.shape
+    n = w_hi.shape[0]
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w_hi.shape == w_lo.shape == (n, k) and w_hi.is_contiguous() and w_lo.is_contiguous()
+    if out is None:
+        out = torch.empty(rows, n, device=x.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.shape[0] == rows and col0 + n <= out.shape[1]
+    y = C.c_void_p(out.data_ptr() + 4 * col0)
+    _abi.check(_abi.lib().mm_linear_tf32x3(_ptr(x), rows, k, _ptr(w_hi), _ptr(w_lo), n, _ptr(bias), _ptr(gate), y, out.shape[1], mode, _stream(x)),
+               "mm_linear_tf32x3")
+    return out
+
+
+def ppo_heads_loss(h2, head_w, head_b, masks, actions, old_logp, adv, clip, scale):
+    """-> (loss [] , joint log-prob [E], dz2 [2E,264], dhead_w [6,264], dhead_b [6]); see mm_ppo_heads_loss in the header."""
+    E = old_logp.shape[0]
+    assert h2.shape == (2 * E, 264) and h2.is_contiguous() and masks.dtype == torch.uint8 and actions.dtype == torch.uint8
+    assert masks.is_contiguous() and actions.is_contiguous() and masks.numel() == 12 * E and actions.numel() == 4 * E
+    L = _abi.lib()
+    blocks, ld = C.c_int32(), C.c_int32()
+    _abi.check(L.mm_ppo_loss_geometry(C.byref(blocks), C.byref(ld)), "mm_ppo_loss_geometry")
+    part = torch.empty(blocks.value, ld.value, device=h2.device, dtype=torch.float32)
+    dz2 = torch.empty_like(h2)
+    logp = torch.empty(E, device=h2.device, dtype=torch.float32)
+    head_w, head_b = head_w.detach().contiguous(), head_b.detach().contiguous()
+    _abi.check(L.mm_ppo_heads_loss(_ptr(h2), _ptr(head_w), _ptr(head_b), _ptr(masks), _ptr(actions), _ptr(old_logp.contiguous()), _ptr(adv.contiguous()), E,
+                                   float(clip), float(scale), _ptr(dz2), _ptr(logp), _ptr(part), _stream(h2)), "mm_ppo_heads_loss")
+    tot = part.sum(0)
+    return tot[6 * 264 + 6], logp, dz2, tot[:6 * 264].view(6, 264), tot[6 * 264:6 * 264 + 6]
+
+
+class _ActorTrunkLoss(torch.autograd.Function):
+    """PPO actor loss as ONE autograd node from the embedding output x0 [2E,460] down: three Linear+ReLU layers, the two heads, masked
+    Categorical / Bernoulli log-probs of the recorded actions, ratio, clipped surrogate (Actor.forward networks.py:36-41,
+    PPO.get_log_probs PPO.py:154-168, PPO.train PPO.py:66-72).  The loss is a scalar, so the whole backward is evaluated inside
+    forward() (no activation outlives the call) and backward() only scales the stored gradients."""
+
+    @staticmethod
+    def forward(ctx, x0, w0, b0, w1, b1, w2, b2, wh, bh, masks, actions, old_logp, adv, clip, scale):
+        x0 = x0.detach().contiguous()
+        ws = [w.detach() for w in (w0, w1, w2)]
+        fwd = [tf32_split(w) for w in ws]
+        h0 = linear_tc(x0, fwd[0], MM_LINEAR_RELU, bias=b0.detach().contiguous())
+        h1 = linear_tc(h0, fwd[1], MM_LINEAR_RELU, bias=b1.detach().contiguous())
+        h2 = linear_tc(h1, fwd[2], MM_LINEAR_RELU, bias=b2.detach().contiguous())
+        loss, logp, dz2, dwh, dbh = ppo_heads_loss(h2, wh, bh, masks, actions, old_logp, adv, clip, scale)
+        del h2
+        dw2, db2 = wgrad(dz2, h1)
+        dz1 = linear_tc(dz2, tf32_split(ws[2].t()), MM_LINEAR_GATE, gate=h1)
+        del dz2, h1
+        dw1, db1 = wgrad(dz1, h0)
+        dz0 = linear_tc(dz1, tf32_split(ws[1].t()), MM_LINEAR_GATE, gate=h0)
+        del dz1, h0
+        dw0, db0 = wgrad(dz0, x0)
+        dx0 = None
+        if ctx.needs_input_grad[0]:
+            w0t = ws[0].t().contiguous()  # [460, 264]: the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
+            dx0 = torch.empty_like(x0)
+            for c0 in range(0, w0t.shape[0], 264):
+                linear_tc(dz0, tf32_split(w0t[c0:c0 + 264]), MM_LINEAR_PLAIN, out=dx0, col0=c0)
+        ctx.grads = (dx0, dw0, db0, dw1, db1, dw2, db2, dwh, dbh)
+        ctx.mark_non_differentiable(logp)
+        return loss, logp
+
+    @staticmethod
+    def backward(ctx, g, _g_logp):
+        grads = tuple(None if t is None else g * t for t in ctx.grads)
+        ctx.grads = None
+        return grads + (None,) * 6
+
+
+def fused_available(actor) -> bool:
+    """The fused update is built for the reference architecture (460 -> 264 -> 264 -> 264 -> 5+1, ReLU) on a CUDA device."""
+    import torch.nn as nn
+    ls = actor.layers
+    return (len(ls) == 3 and tuple(l.out_features for l in ls) == (264, 264, 264) and ls[0].in_features == 460 and actor.activation is nn.ReLU
+            and ls[0].weight.is_cuda)
+
+
+def actor_loss(actor, obs2, masks2, actions2, old_logp, adv, clip, scale):
+    """scale * sum_e -min(ratio_e A_e, clip(ratio_e) A_e) over E envs, and the new joint log-probs [E] (no grad).
+    obs2 [2E,65] f32 (agent rows 2e, 2e+1), masks2 [2E,6] bool/u8, actions2 [2E,2] (move, mark) any integer/float dtype."""
+    x0 = actor.embed(obs2)
+    ls = actor.layers
+    wh = torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)
+    bh = torch.cat([actor.move_head.bias, actor.mark_head.bias], 0)
+    masks = masks2.contiguous().view(torch.uint8) if masks2.dtype == torch.bool else masks2.to(torch.uint8).contiguous()
+    actions = actions2.to(torch.uint8).contiguous()
+    return _ActorTrunkLoss.apply(x0, ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, wh, bh, masks, actions,
+                                 old_logp, adv, float(clip), float(scale))

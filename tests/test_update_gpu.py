@@ -1,0 +1,186 @@
+"""K5 (PPO actor update kernels) against torch fp64 autograd / matmul on the same inputs.  The kernels compute in 3xTF32 with fp32
+accumulation, i.e. fp32-grade results with a different summation order: tolerances are relative to the magnitude of the result."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("R,k_in", [(32, 264), (1000, 264), (4096 + 17, 460), (70000, 264), (70000, 460)])
+def test_wgrad_matches_fp64(R, k_in):
+    from marl_maze_b200.update import wgrad
+    g = torch.Generator(device="cuda"); g.manual_seed(R + k_in)
+    dz = torch.randn(R, 264, device="cuda", generator=g) * (torch.rand(R, 264, device="cuda", generator=g) < 0.5)   # relu-gated gradient: half zeros
+    h = torch.relu(torch.randn(R, k_in, device="cuda", generator=g)) + 0.25
+    dW, db = wgrad(dz, h)
+    ref_W = dz.double().t() @ h.double(); ref_b = dz.double().sum(0)
+    assert dW.shape == (264, k_in) and db.shape == (264,)
+    # the tensor core truncates when it accumulates: a slab of n rows sums ~n/3 MMA results into fp32, each rounded toward zero
+    tol = 2e-6 + 3e-10 * R
+    assert _rel(dW, ref_W) < tol, _rel(dW, ref_W)
+    assert _rel(db, ref_b) < tol, _rel(db, ref_b)
+    # a single-pass TF32 product would sit at ~3e-4: make sure the compensation terms are really there
+    fp32 = dz.t() @ h
+    assert _rel(dW, ref_W) < 4 * _rel(fp32, ref_W) + tol
+
+
+def test_linear_modes_match_fp64():
+    """mm_linear_tf32x3: forward (bias + ReLU), gated data gradient, and the 460-wide plain data gradient made of two column blocks."""
+    from marl_maze_b200.update import linear_tc, tf32_split, MM_LINEAR_RELU, MM_LINEAR_GATE, MM_LINEAR_PLAIN
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    R = 1000
+    x = torch.randn(R, 460, device="cuda", generator=g)
+    w0 = torch.randn(264, 460, device="cuda", generator=g) / 20; b0 = torch.randn(264, device="cuda", generator=g)
+    y = linear_tc(x, tf32_split(w0), MM_LINEAR_RELU, bias=b0)
+    ref = torch.relu(x.double() @ w0.double().t() + b0.double())
+    assert _rel(y, ref) < 5e-6   # K = 460 products summed by the tensor core with truncation (cf. TOL_LOGITS in test_policy_gpu.py)
+    dz = torch.randn(R, 264, device="cuda", generator=g)
+    w1 = torch.randn(264, 264, device="cuda", generator=g) / 16
+    gate = torch.relu(torch.randn(R, 264, device="cuda", generator=g))
+    dh = linear_tc(dz, tf32_split(w1.t()), MM_LINEAR_GATE, gate=gate)
+    ref = (dz.double() @ w1.double()) * (gate > 0)
+    assert _rel(dh, ref) < 5e-6
+    assert bool(((gate > 0) | (dh == 0)).all())
+    dx = torch.full((R, 460), float("nan"), device="cuda")
+    w0t = w0.t().contiguous()
+    for c0 in (0, 264):
+        linear_tc(dz, tf32_split(w0t[c0:c0 + 264]), MM_LINEAR_PLAIN, out=dx, col0=c0)
+    assert _rel(dx, dz.double() @ w0.double()) < 5e-6
+
+
+def _loss_inputs(E, g, wide_ratio=True):
+    masks = torch.rand(2 * E, 6, device="cuda", generator=g) < 0.6
+    masks[torch.arange(2 * E, device="cuda"), torch.randint(0, 5, (2 * E,), device="cuda", generator=g)] = True      # at least one legal move
+    moves = torch.multinomial(masks[:, :5].float(), 1, generator=g).squeeze(1)                                      # a legal move
+    marks = (torch.rand(2 * E, device="cuda", generator=g) < 0.5) & masks[:, 5]
+    actions = torch.stack([moves, marks.long()], 1).to(torch.uint8)
+    adv = torch.randn(E, device="cuda", generator=g)
+    return masks, actions, adv
+
+
+def test_ppo_heads_loss_matches_autograd():
+    """Loss, joint log-probs and every gradient of mm_ppo_heads_loss against the reference formulas under torch fp64 autograd, with
+    ratios on both sides of (and exactly inside) the clip range."""
+    from marl_maze_b200.update import ppo_heads_loss
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    E = 5000
+    z2 = torch.randn(2 * E, 264, device="cuda", generator=g)
+    wh = torch.randn(6, 264, device="cuda", generator=g) / 8; bh = torch.randn(6, device="cuda", generator=g) / 4
+    masks, actions, adv = _loss_inputs(E, g)
+
+    def reference(z2, wh, bh, old=None):
+        h2 = torch.relu(z2)
+        logits = h2 @ wh.t() + bh
+        mv = logits[:, :5].masked_fill(~masks[:, :5], float("-inf"))
+        lp = torch.log_softmax(mv, -1).gather(1, actions[:, 0:1].long()).squeeze(1)
+        p = torch.sigmoid(logits[:, 5].masked_fill(~masks[:, 5], float("-inf")))
+        lp = lp + torch.log(torch.where(actions[:, 1].bool(), p, 1 - p))
+        return lp.view(E, 2).sum(1)
+
+    with torch.no_grad():
+        joint0 = reference(z2.double(), wh.double(), bh.double())
+    old = (joint0 + 0.35 * torch.randn(E, device="cuda", generator=g).double()).float()   # ratios from ~0.4 to ~2.5
+    old[:100] = joint0[:100].float()                                                      # ratio == 1 up to rounding: inside the range
+    clip, scale = 0.2, 1.0 / E
+    zd, wd, bd = z2.double().requires_grad_(), wh.double().requires_grad_(), bh.double().requires_grad_()
+    joint = reference(zd, wd, bd)
+    ratio = torch.exp(joint - old.double())
+    ref_loss = -(torch.min(ratio * adv.double(), torch.clamp(ratio, 1 - clip, 1 + clip) * adv.double())).sum() * scale
+    ref_loss.backward()
+    frac_clipped = float(((ratio < 1 - clip) | (ratio > 1 + clip)).float().mean())
+    assert 0.2 < frac_clipped < 0.9
+    loss, logp, dz2, dwh, dbh = ppo_heads_loss(torch.relu(z2), wh, bh, masks.view(torch.uint8), actions, old, adv, clip, scale)
+    assert torch.allclose(logp.double(), joint.detach(), rtol=1e-5, atol=1e-5)
+    assert abs(float(loss) - float(ref_loss.detach())) < 1e-5 * max(1.0, abs(float(ref_loss.detach())))
+    # envs whose fp32 ratio lands on the other side of a clip boundary than the fp64 one would flip a whole gradient row: none expected
+    assert _rel(dz2, zd.grad) < 2e-5, _rel(dz2, zd.grad)
+    assert _rel(dwh, wd.grad) < 2e-5, _rel(dwh, wd.grad)
+    assert _rel(dbh, bd.grad) < 2e-5, _rel(dbh, bd.grad)
+
+
+@pytest.mark.parametrize("faithful", [True, False], ids=["column0_projection", "indexed_projection"])
+def test_fused_actor_loss_gradients_match_autograd(faithful):
+    """Every actor parameter gradient of the fused K5 path against the reference formulas under torch autograd in fp64.  The yardstick
+    is the fp32 autograd path it replaces (PPO.joint_log_probs): log(1 - sigmoid(l)) in fp32 makes that path itself ~1e-4 off on
+    saturated mark logits, so the fused gradients must be within 1e-5 of fp64 OR as close to it as fp32 autograd is (x4)."""
+    import copy
+    from marl_maze_b200.networks import Actor
+    from marl_maze_b200.update import actor_loss, fused_available
+    torch.manual_seed(21)
+    actor = Actor([264, 264, 264], faithful_projection=faithful).cuda()
+    with torch.no_grad():
+        actor.move_head.weight.mul_(10); actor.mark_head.weight.mul_(10)   # un-do most of the 0.01 head scaling: non-trivial distributions
+    assert fused_available(actor)
+    g = torch.Generator(device="cuda"); g.manual_seed(22)
+    E = 6000
+    obs = torch.rand(2 * E, 65, device="cuda", generator=g)
+    obs[:, :4] = torch.nn.functional.one_hot(torch.randint(0, 4, (2 * E,), device="cuda", generator=g), 4).float()
+    masks, _, adv = _loss_inputs(E, g)
+    ref_actor, a32 = copy.deepcopy(actor).double(), copy.deepcopy(actor)
+    with torch.no_grad():   # actions SAMPLED from the policy, as in a rollout (a mark the policy gives probability ~0 would make log(1 - p) ill-conditioned in fp32)
+        hh = ref_actor.attention(ref_actor.projection(obs.double()))
+        for lin in ref_actor.layers:
+            hh = torch.relu(lin(hh))
+        pmove = torch.softmax(ref_actor.move_head(hh).masked_fill(~masks[:, :5], float("-inf")), -1)
+        pmark = torch.sigmoid(ref_actor.mark_head(hh).reshape(-1)) * masks[:, 5]
+        actions = torch.stack([torch.multinomial(pmove.float(), 1, generator=g).squeeze(1),
+                               (torch.rand(2 * E, device="cuda", generator=g) < pmark.float()).long()], 1).to(torch.uint8)
+
+    kept = {}
+    # ReLU'(0): an fp32 pre-activation within rounding of zero may land on the other side than the fp64 one, and that single (row, unit)
+    # then carries a gradient in one computation and none in the other -- a legitimate difference between ANY two float evaluations, as
+    # large as the gradient element itself.  Take it out of the comparison: every reference below uses the fused forward's own gates.
+    from marl_maze_b200.update import linear_tc, tf32_split, MM_LINEAR_RELU
+    with torch.no_grad():
+        hf, gates = actor.embed(obs).contiguous(), []
+        for lin in actor.layers:
+            hf = linear_tc(hf, tf32_split(lin.weight), MM_LINEAR_RELU, bias=lin.bias.detach().contiguous())
+            gates.append(hf > 0)
+
+    def loss_ref(a, dt, old):   # Actor.forward + PPO.get_log_probs + the clipped surrogate in dtype dt (Actor.trunk itself casts to fp32)
+        h = a.attention(a.projection(obs.to(dt)))
+        if old is not None:
+            h.retain_grad(); kept[dt] = h
+        for lin, gate in zip(a.layers, gates):
+            h = lin(h) * gate
+        ml, kl = a.move_head(h), a.mark_head(h)
+        lp = torch.log_softmax(ml.masked_fill(~masks[:, :5], float("-inf")), -1).gather(1, actions[:, 0:1].long()).squeeze(1)
+        p = torch.sigmoid(kl.reshape(-1).masked_fill(~masks[:, 5], float("-inf")))
+        joint = (lp + torch.log(torch.where(actions[:, 1].bool(), p, 1 - p))).view(E, 2).sum(1)
+        if old is None:
+            return joint
+        ratio = torch.exp(joint - old.to(dt))
+        return -(torch.min(ratio * adv.to(dt), torch.clamp(ratio, 0.8, 1.2) * adv.to(dt))).sum() / E
+
+    with torch.no_grad():
+        old = (loss_ref(ref_actor, torch.float64, None) + 0.3 * torch.randn(E, device="cuda", generator=g).double()).float()
+    ref_loss = loss_ref(ref_actor, torch.float64, old); ref_loss.backward()
+    loss_ref(a32, torch.float32, old).backward()
+    embed = actor.embed
+
+    def embed_kept(x):
+        out = embed(x)
+        out.retain_grad(); kept["fused"] = out
+        return out
+
+    actor.embed = embed_kept
+    loss, logp = actor_loss(actor, obs, masks, actions, old, adv, 0.2, 1.0 / E)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) < 2e-5 * max(1.0, abs(float(ref_loss.detach())))
+    # the gradient handed back to autograd at the embedding output (element-wise, against the largest element)
+    r_dx0, r32_dx0 = _rel(kept["fused"].grad, kept[torch.float64].grad), _rel(kept[torch.float32].grad, kept[torch.float64].grad)
+    assert r_dx0 < max(2e-5, 4 * r32_dx0), (r_dx0, r32_dx0)
+    worst = 0.0
+    for (name, p), (_, q), (_, t) in zip(actor.named_parameters(), ref_actor.named_parameters(), a32.named_parameters()):
+        if q.grad is None or float(q.grad.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-9, name
+            continue
+        assert p.grad is not None, name
+        r, r32 = _rel(p.grad, q.grad), _rel(t.grad, q.grad)
+        worst = max(worst, r)
+        assert r < max(2e-5, 4 * r32), (name, r, r32)
+    print("worst relative gradient error", worst, "dX0", r_dx0, r32_dx0)
