@@ -74,7 +74,7 @@ def lib():
         "mm_counter_add": (i32, [vp, u64, vp]),
         "mm_wgrad_geometry": (i32, [i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "mm_wgrad_tf32x3": (i32, [vp, vp, i32, i32, i32, vp, vp]),
-        "mm_linear_tf32x3": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp]),
+        "mm_linear_tf32x3": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp, vp]),
         "mm_ppo_loss_geometry": (i32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "mm_ppo_heads_loss": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]),
     }

@@ -182,14 +182,16 @@ int mm_wgrad_tf32x3(const float* dz, const float* h, int rows, int n_out, int k_
     return cuda_status(launch_wgrad_tc(dz, h, rows, n_out, k_in, part, (cudaStream_t)stream));
 }
 
-int mm_linear_tf32x3(const float* x, int rows, int k, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, const float* gate, float* y,
-                     int ldy, int mode, void* stream) {
+int mm_linear_tf32x3(const float* x, int rows, int k, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, const uint32_t* gate_bits,
+                     float* y, int ldy, int mode, uint32_t* gate_bits_out, void* stream) {
     if (!x || !w_hi || !w_lo || !y || rows <= 0 || k <= 0 || n_rows_w <= 0 || n_rows_w > 264 || ldy < n_rows_w) return MM_ERR_BAD_ARG;
     if (mode != MM_LINEAR_RELU && mode != MM_LINEAR_GATE && mode != MM_LINEAR_PLAIN) return MM_ERR_BAD_ARG;
-    if ((mode == MM_LINEAR_RELU && !bias) || (mode == MM_LINEAR_GATE && (!gate || n_rows_w != 264))) return MM_ERR_BAD_ARG;
-    if (((uintptr_t)x & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15) || ((uintptr_t)y & 15) || ((uintptr_t)gate & 15) || (k & 3) || (ldy & 3) || (n_rows_w & 3))
+    if ((mode == MM_LINEAR_RELU && !bias) || (mode == MM_LINEAR_GATE && (!gate_bits || n_rows_w != 264)) || (gate_bits_out && (mode != MM_LINEAR_RELU || n_rows_w != 264)))
         return MM_ERR_BAD_ARG;
-    return cuda_status(launch_linear_tc_ex(x, w_hi, w_lo, n_rows_w, bias, y, ldy, rows, k, mode, gate, nullptr, nullptr, nullptr, (cudaStream_t)stream));
+    if (((uintptr_t)x & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15) || ((uintptr_t)y & 15) || ((uintptr_t)gate_bits & 3) || ((uintptr_t)gate_bits_out & 3) ||
+        (k & 3) || (ldy & 3) || (n_rows_w & 3))
+        return MM_ERR_BAD_ARG;
+    return cuda_status(launch_linear_tc_ex(x, w_hi, w_lo, n_rows_w, bias, y, ldy, rows, k, mode, gate_bits, gate_bits_out, nullptr, nullptr, nullptr, (cudaStream_t)stream));
 }
 int mm_ppo_loss_geometry(int32_t* blocks, int32_t* ld) {
     if (!blocks || !ld) return MM_ERR_BAD_ARG;

@@ -51,13 +51,15 @@ struct TcMaps {
 // Epilogue modes.  TC_EPI_RELU: y = relu(acc + bias).  TC_EPI_HEADS: this is the last trunk layer -- instead of storing y, the epilogue
 // contracts each row with the 6 head rows (5 move logits + 1 mark logit), masks, samples (or evaluates) the action and writes actions +
 // the env's joint log-prob: "sampling fused in the epilogue".  TC_EPI_GATE / TC_EPI_PLAIN are the backward (data-gradient) uses of the
-// same GEMM, dH = dZ W: y = acc * (gate > 0) with gate = the ReLU output the gradient flows back through, or y = acc; n_valid columns
-// are stored with row pitch ldy (the 460-wide dX of the first layer is produced as two column blocks).
+// same GEMM, dH = dZ W: y = acc where the ReLU the gradient flows back through was open, else 0 -- or y = acc; n_valid columns are stored
+// with row pitch ldy (the 460-wide dX of the first layer is produced as two column blocks).  The ReLU pattern travels as BITS: a forward
+// launch (TC_EPI_RELU) can emit gate_out [M][9] u32 (bit b of word c = y[row][32c+b] > 0, 36 bytes per row instead of 1056), and the
+// TC_EPI_GATE epilogue reads its row's 9 words before the main loop, so the gate costs neither bandwidth nor exposed latency.
 enum { TC_EPI_RELU = 0, TC_EPI_HEADS = 1, TC_EPI_GATE = 2, TC_EPI_PLAIN = 3 };
 template <int kMode>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ bias, float* __restrict__ y, int M, int K, const float* __restrict__ head_w,
-                const float* __restrict__ head_b, const HeadArgs heads, const float* __restrict__ gate, int n_valid, int ldy) {
+                const float* __restrict__ head_b, const HeadArgs heads, const uint32_t* __restrict__ gate, uint32_t* __restrict__ gate_out, int n_valid, int ldy) {
     constexpr bool kHeads = kMode == TC_EPI_HEADS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -130,6 +132,12 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     } else {
         // ===== splitter (main loop): 128 threads turn each landed fp32 A tile into (hi in place, lo beside it)
         const int st_tid = threadIdx.x - 64;
+        uint32_t gbits[9];
+        if (kMode == TC_EPI_GATE) {
+            const long long grow = (long long)m0 + (warp & 3) * 32 + lane;  // the output row this thread owns in the epilogue
+#pragma unroll
+            for (int c = 0; c < 9; c++) gbits[c] = grow < M ? __ldg(&gate[grow * 9 + c]) : 0u;
+        }
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % TC_STAGES;
             mbar_wait(&full[s], (kb / TC_STAGES) & 1);
@@ -161,13 +169,10 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 9; c++) {  // 9 x 32 columns >= 264
-            float4 gt[8];  // TC_EPI_GATE: the gate values of this chunk's store pattern, requested before the TMEM load so their latency overlaps it
-            if (kMode == TC_EPI_GATE) {
+            uint32_t gword = 0;
+            if (kMode == TC_EPI_GATE) {  // gbits[c] with a rolled loop: select without dynamic register indexing
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int r = it * 4 + (lane >> 3), col = c * 32 + 4 * (lane & 7);
-                    gt[it] = (row0 + r < M && col < n_valid) ? __ldg(reinterpret_cast<const float4*>(gate + (size_t)(row0 + r) * TC_N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int i = 0; i < 9; i++) gword = (i == c) ? gbits[i] : gword;
             }
             uint32_t v[32];
             asm volatile(
@@ -177,6 +182,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                   "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr + (uint32_t)(c * 32)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint32_t word = 0;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 float yv[4];
@@ -184,7 +190,9 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 for (int j = 0; j < 4; j++) {
                     const int col = c * 32 + 4 * q + j;
                     if (kMode == TC_EPI_RELU || kMode == TC_EPI_HEADS) yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f), 0.f);
+                    else if (kMode == TC_EPI_GATE) yv[j] = ((gword >> (4 * q + j)) & 1u) ? __uint_as_float(v[4 * q + j]) : 0.f;
                     else yv[j] = __uint_as_float(v[4 * q + j]);
+                    if (kMode == TC_EPI_RELU) word |= (yv[j] > 0.f ? 1u : 0u) << (4 * q + j);
                 }
                 if (kHeads) {
                     if (c * 32 + 4 * q < TC_N) {  // TC_N is a multiple of 4: whole float4 groups are in or out
@@ -199,6 +207,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 }
             }
             if (kHeads) continue;
+            if (kMode == TC_EPI_RELU && gate_out && row0 + lane < M) gate_out[(size_t)(row0 + lane) * 9 + c] = word;
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; it++) {  // 4 rows x 128 contiguous bytes per instruction
@@ -206,10 +215,6 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 const int col = c * 32 + 4 * c4;
                 if (row0 + r < M && col < n_valid) {
                     float4 o = *reinterpret_cast<const float4*>(&t_y[r * kTP + 4 * c4]);
-                    if (kMode == TC_EPI_GATE) {
-                        const float4 g = gt[it];
-                        o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
-                    }
                     *reinterpret_cast<float4*>(y + (size_t)(row0 + r) * ldy + col) = o;
                 }
             }
@@ -252,9 +257,9 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
 
 // Y = epi(X W^T) with X [M][K] plain fp32 and W given as the split (w_hi, w_lo) [n_rows_w][K], n_rows_w <= 264.  mode TC_EPI_RELU writes
 // y = relu(. + bias) [M][264]; TC_EPI_HEADS (last layer, `heads` given) runs heads + sampling in the epilogue and writes actions / log-probs
-// instead of y; TC_EPI_GATE / TC_EPI_PLAIN write n_rows_w columns with row pitch ldy (gate [M][264]).
+// instead of y; TC_EPI_GATE / TC_EPI_PLAIN write n_rows_w columns with row pitch ldy (gate = ReLU bit words [M][9], as emitted through gate_out by a TC_EPI_RELU launch).
 cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, float* y, int ldy, int M, int K, int mode,
-                                const float* gate, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
+                                const uint32_t* gate, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
     // The rollout calls this with the same scratch / weight pointers every step: keep the encoded maps (a tensor map depends only on
     // base pointer, extents and box) in a small per-thread cache instead of re-encoding 15 of them per policy step.
     struct Entry { const float *x, *wh, *wl; int M, K, nw; TcMaps maps; };
@@ -288,17 +293,17 @@ cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* 
     switch (mode) {
     case TC_EPI_HEADS:
         if (!heads) return cudaErrorInvalidValue;
-        k_linear_tf32x3<TC_EPI_HEADS><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, nullptr, M, K, head_w, head_b, *heads, nullptr, TC_N, TC_N);
+        k_linear_tf32x3<TC_EPI_HEADS><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, nullptr, M, K, head_w, head_b, *heads, nullptr, nullptr, TC_N, TC_N);
         break;
     case TC_EPI_RELU:
-        k_linear_tf32x3<TC_EPI_RELU><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, n_rows_w, ldy);
+        k_linear_tf32x3<TC_EPI_RELU><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, gate_out, n_rows_w, ldy);
         break;
     case TC_EPI_GATE:
         if (!gate || n_rows_w != TC_N) return cudaErrorInvalidValue;
-        k_linear_tf32x3<TC_EPI_GATE><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, gate, n_rows_w, ldy);
+        k_linear_tf32x3<TC_EPI_GATE><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, gate, nullptr, n_rows_w, ldy);
         break;
     case TC_EPI_PLAIN:
-        k_linear_tf32x3<TC_EPI_PLAIN><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, n_rows_w, ldy);
+        k_linear_tf32x3<TC_EPI_PLAIN><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, nullptr, n_rows_w, ldy);
         break;
     default: return cudaErrorInvalidValue;
     }
@@ -307,7 +312,7 @@ cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* 
 
 cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
                              const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
-    return launch_linear_tc_ex(x, w_hi, w_lo, TC_N, bias, y, TC_N, M, K, heads ? TC_EPI_HEADS : TC_EPI_RELU, nullptr, head_w, head_b, heads, stream);
+    return launch_linear_tc_ex(x, w_hi, w_lo, TC_N, bias, y, TC_N, M, K, heads ? TC_EPI_HEADS : TC_EPI_RELU, nullptr, nullptr, head_w, head_b, heads, stream);
 }
 
 }  // namespace mm

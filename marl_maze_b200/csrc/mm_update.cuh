@@ -21,6 +21,6 @@ cudaError_t launch_wgrad_tc(const float* dz, const float* h, int R, int n_out, i
 void wgrad_geometry(int R, int n_out, int k_in, int* slabs, int* ld, int* kb_per);
 struct HeadArgs;
 cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, float* y, int ldy, int M, int K, int mode,
-                                const float* gate, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream);
+                                const uint32_t* gate, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream);
 
 }  // namespace mm

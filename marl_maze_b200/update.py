@@ -43,8 +43,10 @@ def tf32_split(w: torch.Tensor):
     return hi, ((r.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
 
 
-def linear_tc(x, w_split, mode, bias=None, gate=None, out=None, col0=0):
-    """out[:, col0:col0+n] = epi(x @ W^T) for W [n<=264, k] given as tf32_split(W); out defaults to a fresh [rows, n] tensor."""
+def linear_tc(x, w_split, mode, bias=None, gate_bits=None, out=None, col0=0, want_bits=False):
+    """out[:, col0:col0+n] = epi(x @ W^T) for W [n<=264, k] given as tf32_split(W); out defaults to a fresh [rows, n] tensor.
+    MM_LINEAR_RELU with want_bits=True also returns the ReLU pattern as bit words [rows, 9] int32 -- the `gate_bits` a later
+    MM_LINEAR_GATE call (the data gradient through that ReLU) takes."""
     w_hi, w_lo = w_split
     rows, k = x.shape
     n = w_hi.shape[0]
@@ -52,10 +54,12 @@ def linear_tc(x, w_split, mode, bias=None, gate=None, out=None, col0=0):
     if out is None:
         out = torch.empty(rows, n, device=x.device, dtype=torch.float32)
     assert out.is_contiguous() and out.shape[0] == rows and col0 + n <= out.shape[1]
+    bits = torch.empty(rows, 9, device=x.device, dtype=torch.int32) if want_bits else None
+    assert gate_bits is None or (gate_bits.shape == (rows, 9) and gate_bits.dtype == torch.int32 and gate_bits.is_contiguous())
     y = C.c_void_p(out.data_ptr() + 4 * col0)
-    _abi.check(_abi.lib().mm_linear_tf32x3(_ptr(x), rows, k, _ptr(w_hi), _ptr(w_lo), n, _ptr(bias), _ptr(gate), y, out.shape[1], mode, _stream(x)),
-               "mm_linear_tf32x3")
-    return out
+    _abi.check(_abi.lib().mm_linear_tf32x3(_ptr(x), rows, k, _ptr(w_hi), _ptr(w_lo), n, _ptr(bias), _ptr(gate_bits), y, out.shape[1], mode, _ptr(bits),
+                                           _stream(x)), "mm_linear_tf32x3")
+    return (out, bits) if want_bits else out
 
 
 def ppo_heads_loss(h2, head_w, head_b, masks, actions, old_logp, adv, clip, scale):
@@ -76,6 +80,22 @@ def ppo_heads_loss(h2, head_w, head_b, masks, actions, old_logp, adv, clip, scal
     return tot[6 * 264 + 6], logp, dz2, tot[:6 * 264].view(6, 264), tot[6 * 264:6 * 264 + 6]
 
 
+def trunk_splits(actor):
+    """TF32 splits of the three trunk weights, plain (forward) and transposed (data gradient; W0^T as two blocks of <= 264 rows), cached
+    on the module until an optimizer step changes a weight (tensor._version)."""
+    ws = [l.weight for l in actor.layers]
+    key = tuple((w.data_ptr(), w._version) for w in ws)
+    cached = getattr(actor, "_k5_splits", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            w0t = ws[0].t().contiguous()
+            data = dict(fwd=[tf32_split(w) for w in ws], t1=tf32_split(ws[1].t()), t2=tf32_split(ws[2].t()),
+                        t0=[tf32_split(w0t[c0:c0 + 264]) for c0 in range(0, w0t.shape[0], 264)])
+        cached = (key, data)
+        actor._k5_splits = cached
+    return cached[1]
+
+
 class _ActorTrunkLoss(torch.autograd.Function):
     """PPO actor loss as ONE autograd node from the embedding output x0 [2E,460] down: three Linear+ReLU layers, the two heads, masked
     Categorical / Bernoulli log-probs of the recorded actions, ratio, clipped surrogate (Actor.forward networks.py:36-41,
@@ -83,37 +103,35 @@ class _ActorTrunkLoss(torch.autograd.Function):
     forward() (no activation outlives the call) and backward() only scales the stored gradients."""
 
     @staticmethod
-    def forward(ctx, x0, w0, b0, w1, b1, w2, b2, wh, bh, masks, actions, old_logp, adv, clip, scale):
+    def forward(ctx, x0, w0, b0, w1, b1, w2, b2, wh, bh, sp, masks, actions, old_logp, adv, clip, scale):
         x0 = x0.detach().contiguous()
-        ws = [w.detach() for w in (w0, w1, w2)]
-        fwd = [tf32_split(w) for w in ws]
-        h0 = linear_tc(x0, fwd[0], MM_LINEAR_RELU, bias=b0.detach().contiguous())
-        h1 = linear_tc(h0, fwd[1], MM_LINEAR_RELU, bias=b1.detach().contiguous())
-        h2 = linear_tc(h1, fwd[2], MM_LINEAR_RELU, bias=b2.detach().contiguous())
+        h0, bits0 = linear_tc(x0, sp["fwd"][0], MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
+        h1, bits1 = linear_tc(h0, sp["fwd"][1], MM_LINEAR_RELU, bias=b1.detach().contiguous(), want_bits=True)
+        h2 = linear_tc(h1, sp["fwd"][2], MM_LINEAR_RELU, bias=b2.detach().contiguous())
         loss, logp, dz2, dwh, dbh = ppo_heads_loss(h2, wh, bh, masks, actions, old_logp, adv, clip, scale)
         del h2
         dw2, db2 = wgrad(dz2, h1)
-        dz1 = linear_tc(dz2, tf32_split(ws[2].t()), MM_LINEAR_GATE, gate=h1)
+        dz1 = linear_tc(dz2, sp["t2"], MM_LINEAR_GATE, gate_bits=bits1)
         del dz2, h1
         dw1, db1 = wgrad(dz1, h0)
-        dz0 = linear_tc(dz1, tf32_split(ws[1].t()), MM_LINEAR_GATE, gate=h0)
+        dz0 = linear_tc(dz1, sp["t1"], MM_LINEAR_GATE, gate_bits=bits0)
         del dz1, h0
         dw0, db0 = wgrad(dz0, x0)
         dx0 = None
-        if ctx.needs_input_grad[0]:
-            w0t = ws[0].t().contiguous()  # [460, 264]: the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
+        if ctx.needs_input_grad[0]:  # the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
             dx0 = torch.empty_like(x0)
-            for c0 in range(0, w0t.shape[0], 264):
-                linear_tc(dz0, tf32_split(w0t[c0:c0 + 264]), MM_LINEAR_PLAIN, out=dx0, col0=c0)
+            for i, blk in enumerate(sp["t0"]):
+                linear_tc(dz0, blk, MM_LINEAR_PLAIN, out=dx0, col0=264 * i)
         ctx.grads = (dx0, dw0, db0, dw1, db1, dw2, db2, dwh, dbh)
         ctx.mark_non_differentiable(logp)
         return loss, logp
 
     @staticmethod
     def backward(ctx, g, _g_logp):
-        grads = tuple(None if t is None else g * t for t in ctx.grads)
-        ctx.grads = None
-        return grads + (None,) * 6
+        grads, ctx.grads = ctx.grads, None
+        if float(g) != 1.0:  # loss.backward() arrives with 1: do not spend a pass over the [2E,460] dX0 on multiplying by it
+            grads = tuple(None if t is None else g * t for t in grads)
+        return grads + (None,) * 7
 
 
 def fused_available(actor) -> bool:
@@ -133,5 +151,5 @@ def actor_loss(actor, obs2, masks2, actions2, old_logp, adv, clip, scale):
     bh = torch.cat([actor.move_head.bias, actor.mark_head.bias], 0)
     masks = masks2.contiguous().view(torch.uint8) if masks2.dtype == torch.bool else masks2.to(torch.uint8).contiguous()
     actions = actions2.to(torch.uint8).contiguous()
-    return _ActorTrunkLoss.apply(x0, ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, wh, bh, masks, actions,
-                                 old_logp, adv, float(clip), float(scale))
+    return _ActorTrunkLoss.apply(x0, ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, wh, bh, trunk_splits(actor), masks,
+                                 actions, old_logp, adv, float(clip), float(scale))

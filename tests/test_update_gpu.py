@@ -40,8 +40,10 @@ def test_linear_modes_match_fp64():
     assert _rel(y, ref) < 5e-6   # K = 460 products summed by the tensor core with truncation (cf. TOL_LOGITS in test_policy_gpu.py)
     dz = torch.randn(R, 264, device="cuda", generator=g)
     w1 = torch.randn(264, 264, device="cuda", generator=g) / 16
-    gate = torch.relu(torch.randn(R, 264, device="cuda", generator=g))
-    dh = linear_tc(dz, tf32_split(w1.t()), MM_LINEAR_GATE, gate=gate)
+    gate, bits = linear_tc(torch.randn(R, 264, device="cuda", generator=g), tf32_split(w1), MM_LINEAR_RELU, bias=b0, want_bits=True)
+    unpacked = ((bits.unsqueeze(-1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(R, 288)[:, :264].bool()
+    assert bool((unpacked == (gate > 0)).all()) and 0.3 < float(unpacked.float().mean()) < 0.7
+    dh = linear_tc(dz, tf32_split(w1.t()), MM_LINEAR_GATE, gate_bits=bits)
     ref = (dz.double() @ w1.double()) * (gate > 0)
     assert _rel(dh, ref) < 5e-6
     assert bool(((gate > 0) | (dh == 0)).all())

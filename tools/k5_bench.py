@@ -30,10 +30,10 @@ s0, s1, s1t = U.tf32_split(w0), U.tf32_split(w1), U.tf32_split(w1.t())
 y = torch.empty(R, 264, device=dev)
 out["fwd_460_ms"] = timeit(lambda: U.linear_tc(x0, s0, U.MM_LINEAR_RELU, bias=b, out=y))
 out["fwd_264_ms"] = timeit(lambda: U.linear_tc(h, s1, U.MM_LINEAR_RELU, bias=b, out=y))
-out["dgrad_264_ms"] = timeit(lambda: U.linear_tc(dz, s1t, U.MM_LINEAR_GATE, gate=h, out=y))
+_, bits = U.linear_tc(h, s1, U.MM_LINEAR_RELU, bias=b, want_bits=True)
+out["dgrad_264_ms"] = timeit(lambda: U.linear_tc(dz, s1t, U.MM_LINEAR_GATE, gate_bits=bits, out=y))
 out["plain_264_dz_ms"] = timeit(lambda: U.linear_tc(dz, s1t, U.MM_LINEAR_PLAIN, out=y))
 out["relu_264_dz_ms"] = timeit(lambda: U.linear_tc(dz, s1t, U.MM_LINEAR_RELU, bias=b, out=y))
-out["gate_264_h_ms"] = timeit(lambda: U.linear_tc(h, s1t, U.MM_LINEAR_GATE, gate=h, out=y))
 out["wgrad_264_ms"] = timeit(lambda: U.wgrad(dz, h))
 out["wgrad_460_ms"] = timeit(lambda: U.wgrad(dz, x0))
 out["torch_wgrad_264_fp32_ms"] = timeit(lambda: dz.t() @ h)
