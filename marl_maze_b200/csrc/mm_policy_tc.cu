@@ -36,6 +36,16 @@ constexpr uint32_t TC_B2_BYTES = TC_N2 * TC_BK * 4;   // 16384
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * (TC_B1_BYTES + TC_B2_BYTES);  // 102400
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 192;
+// MM_TC_A_TMEM: the activation operand reaches the tensor core through TENSOR MEMORY instead of shared memory.  An SS-form tf32 MMA of
+// M = 128, N = 144 reads (128 + 144) * 32 bytes of shared memory for 78 clocks of math -- 111 of the SM's 128 bytes/clock -- and the 3xTF32
+// scheme issues three of them per k-step on top of the TMA writes and the splitter's own traffic: the SS kernel is shared-memory-bandwidth
+// bound at ~42 % tensor activity.  With A in TMEM the splitter reads each landed fp32 row once and writes hi / lo with tcgen05.st, and the
+// MMAs read only the weight tiles from shared memory.
+#ifndef MM_TC_A_TMEM
+#define MM_TC_A_TMEM 1
+#endif
+static_assert(!MM_TC_A_TMEM || MM_TC_BK == 32, "the TMEM-A splitter addresses the 128-byte swizzle");
+constexpr uint32_t TC_TMEM_A_COL = 288;  // D occupies columns 0..271; A stages: [hi 32 | lo 32] per pipeline stage from column 288
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 1024 bytes.
@@ -118,12 +128,22 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 for (int k = 0; k < TC_BK / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the 128-byte swizzle row
                     const uint64_t o = (uint64_t)(k * 2);
                     const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+#if MM_TC_A_TMEM
+                    const uint32_t ta_hi = tmem_base + TC_TMEM_A_COL + (uint32_t)(s * 64 + k * 8), ta_lo = ta_hi + 32;
+                    umma_tf32_ts(tmem_base, ta_hi, b1_hi + o, id1, first);
+                    umma_tf32_ts(tmem_base, ta_lo, b1_hi + o, id1, 1u);
+                    umma_tf32_ts(tmem_base, ta_hi, b1_lo + o, id1, 1u);
+                    umma_tf32_ts(tmem_base + TC_N1, ta_hi, b2_hi + o, id2, first);
+                    umma_tf32_ts(tmem_base + TC_N1, ta_lo, b2_hi + o, id2, 1u);
+                    umma_tf32_ts(tmem_base + TC_N1, ta_hi, b2_lo + o, id2, 1u);
+#else
                     umma_tf32(tmem_base, a_hi + o, b1_hi + o, id1, first);
                     umma_tf32(tmem_base, a_lo + o, b1_hi + o, id1, 1u);
                     umma_tf32(tmem_base, a_hi + o, b1_lo + o, id1, 1u);
                     umma_tf32(tmem_base + TC_N1, a_hi + o, b2_hi + o, id2, first);
                     umma_tf32(tmem_base + TC_N1, a_lo + o, b2_hi + o, id2, 1u);
                     umma_tf32(tmem_base + TC_N1, a_hi + o, b2_lo + o, id2, 1u);
+#endif
                 }
                 umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
             }
@@ -141,6 +161,27 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % TC_STAGES;
             mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+#if MM_TC_A_TMEM
+            // thread = row (its TMEM lane): logical 16-byte chunk c of row r sits at physical chunk c ^ (r & 7) of the 128-byte swizzled row
+            const int arow = (warp & 3) * 32 + lane;
+            const float4* rowp = reinterpret_cast<const float4*>(smem + s * TC_STAGE_BYTES + arow * 128);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float4 v = rowp[c ^ (arow & 7)];
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    hi[4 * c + j] = tf32_rn_bits(e[j]);
+                    lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
+                }
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TC_TMEM_A_COL + (uint32_t)(s * 64);
+            tmem_st_32x32(ta, hi);
+            tmem_st_32x32(ta + 32, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#else
             float4* raw = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
             float4* lo_t = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_A_BYTES);
 #pragma unroll
@@ -152,6 +193,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
                 raw[j] = h; lo_t[j] = l;
             }
+#endif
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma's operand reads
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s])) : "memory");
         }
