@@ -8,8 +8,11 @@
 // {32 columns x 32 rows} with the 32-byte-chunk 128-byte swizzle lands exactly as canonical MN-major SWIZZLE_128B_BASE32B atoms, no
 // transposition anywhere.  One CTA owns a [128 x 288] tile of dW (m-tile of dZ columns x n-tile of H columns) and a contiguous slab of
 // rows; it accumulates in TMEM over its slab and writes ONE partial tile (plain stores -- the sum over slabs is a tiny second pass, so
-// the result is deterministic).  Warp roles as in mm_policy_tc.cu: warp 0 = TMA, warp 1 = MMA issue, warps 2-5 = split every landed
-// fp32 tile (both operands are activations here) into tf32 hi (in place) + lo (beside it), then epilogue.
+// the result is deterministic).  Warp roles as in mm_policy_tc.cu: warp 0 = TMA, warp 1 = MMA issue, warps 2-5 = splitter, then epilogue.
+// Both operands are activations, so both are split in the kernel: the H tile in shared memory (hi in place, lo beside it); the dZ tile
+// goes to TENSOR MEMORY -- thread m reads column m of the landed boxes (conflict-free: a warp reads one 128-byte row per step), and
+// writes its hi / lo rows with tcgen05.st, which makes dZ^T the K-major TMEM A operand of a TS-form MMA and keeps its three reads per
+// k-step off the shared-memory port (the SS form of this kernel was shared-memory-bandwidth bound).
 #include <cuda.h>
 #include <stdio.h>
 #include "mm_env.cuh"
@@ -24,9 +27,9 @@ constexpr int WG_STAGES = 2;
 constexpr uint32_t WG_BOX_BYTES = 32 * WG_BK * 4;                          // 4096: one {32 col x 32 row} box
 constexpr uint32_t WG_A_BYTES = (WG_M / 32) * WG_BOX_BYTES;                // 16384
 constexpr uint32_t WG_B_BYTES = (WG_N / 32) * WG_BOX_BYTES;                // 36864
-constexpr uint32_t WG_RAW_BYTES = WG_A_BYTES + WG_B_BYTES;                 // 53248: TMA-landed fp32 -> hi in place
-constexpr uint32_t WG_STAGE_BYTES = 2 * WG_RAW_BYTES;                      // + lo copy
+constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + 2 * WG_B_BYTES;           // dZ boxes (fp32, read once by the splitter) | H hi (in place) | H lo
 constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t WG_TMEM_A_COL = 288;   // D occupies TMEM columns 0..287; dZ^T stages [hi 32 | lo 32] per pipeline stage from column 288
 constexpr int WG_THREADS = 192;
 constexpr uint32_t WG_TMEM_COLS = 512;
 
@@ -37,9 +40,9 @@ constexpr uint32_t WG_TMEM_COLS = 512;
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(WG_BOX_BYTES >> 4) << 16) | ((uint64_t)(512u >> 4) << 32) | ((uint64_t)1 << 46) | (1ull << 61);
 }
-// as umma_idesc_tf32 (mm_policy_tc.cu) with a_major = b_major = MN (bits 15, 16)
+// as umma_idesc_tf32 (mm_policy_tc.cu) with b_major = MN (bit 16); A comes from tensor memory, K-major by construction
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ float tf32_rn_i(float x) {  // cvt.rna.tf32.f32 on finite values, on the integer pipe
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -88,7 +91,7 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
                 const int s = kb % WG_STAGES;
                 mbar_wait(&empty[s], ((kb / WG_STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * WG_STAGE_BYTES;
-                mbar_expect_tx(&full[s], WG_RAW_BYTES);
+                mbar_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
                 const int r0 = (kb0 + kb) * WG_BK;
 #pragma unroll
                 for (int j = 0; j < WG_M / 32; j++) tma_load_2d(st + j * WG_BOX_BYTES, &maps.dz, mt * WG_M + 32 * j, r0, &full[s]);
@@ -107,39 +110,53 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
 #pragma unroll
                 for (int g = 0; g < WG_BK / 8; g++) {  // UMMA_K = 8 rows = 1024 bytes down every box
                     const uint32_t o = g * 1024u;
-                    const uint64_t a_hi = umma_desc_mn(st + o), a_lo = umma_desc_mn(st + WG_RAW_BYTES + o);
-                    const uint64_t b1_hi = umma_desc_mn(st + WG_A_BYTES + o), b1_lo = umma_desc_mn(st + WG_RAW_BYTES + WG_A_BYTES + o);
+                    const uint32_t ta_hi = tmem_base + WG_TMEM_A_COL + (uint32_t)(s * 64 + g * 8), ta_lo = ta_hi + 32;
+                    const uint64_t b1_hi = umma_desc_mn(st + WG_A_BYTES + o), b1_lo = umma_desc_mn(st + WG_A_BYTES + WG_B_BYTES + o);
                     const uint64_t b2_hi = umma_desc_mn(st + WG_A_BYTES + (WG_N1 / 32) * WG_BOX_BYTES + o);
-                    const uint64_t b2_lo = umma_desc_mn(st + WG_RAW_BYTES + WG_A_BYTES + (WG_N1 / 32) * WG_BOX_BYTES + o);
+                    const uint64_t b2_lo = umma_desc_mn(st + WG_A_BYTES + WG_B_BYTES + (WG_N1 / 32) * WG_BOX_BYTES + o);
                     const uint32_t first = (kb == 0 && g == 0) ? 0u : 1u;
-                    umma_tf32(tmem_base, a_hi, b1_hi, id1, first);
-                    umma_tf32(tmem_base, a_lo, b1_hi, id1, 1u);
-                    umma_tf32(tmem_base, a_hi, b1_lo, id1, 1u);
-                    umma_tf32(tmem_base + WG_N1, a_hi, b2_hi, id2, first);
-                    umma_tf32(tmem_base + WG_N1, a_lo, b2_hi, id2, 1u);
-                    umma_tf32(tmem_base + WG_N1, a_hi, b2_lo, id2, 1u);
+                    umma_tf32_ts(tmem_base, ta_hi, b1_hi, id1, first);
+                    umma_tf32_ts(tmem_base, ta_lo, b1_hi, id1, 1u);
+                    umma_tf32_ts(tmem_base, ta_hi, b1_lo, id1, 1u);
+                    umma_tf32_ts(tmem_base + WG_N1, ta_hi, b2_hi, id2, first);
+                    umma_tf32_ts(tmem_base + WG_N1, ta_lo, b2_hi, id2, 1u);
+                    umma_tf32_ts(tmem_base + WG_N1, ta_hi, b2_lo, id2, 1u);
                 }
                 umma_commit(&empty[s]);
             }
             umma_commit(tmem_full);
         }
     } else {
-        // ===== splitter: 3328 float4 per stage over 128 threads.  Thread t owns float4 t + 128 q; in a box, float4 i is row i/8 and
+        // ===== splitter.  H boxes: 2304 float4 per stage over 128 threads; thread t owns float4 t + 128 q; in a box, float4 i is row i/8 and
         // physical 16-byte slot i%8 of that row; logical column c of row r sits in slot (((c>>3) ^ (r&3)) << 1) | ((c>>2)&1).
         const int st_tid = threadIdx.x - 64;
         // the ones column: box ones_col/32; its rows r and r+16 belong to the thread with (t>>3) == r%16 and (t&7) == slot(r), at
-        // q = 8 + 2*box (+1 for the upper 16 rows)
+        // q = 2*box (+1 for the upper 16 rows)
         const bool has_ones = ones_col >= 0 && ones_col < WG_N;
         const int ones_cb = ones_col & 31, ones_e = ones_col & 3;
         const bool ones_owner = has_ones && ((st_tid & 7) == ((((ones_cb >> 3) ^ ((st_tid >> 3) & 3)) << 1) | ((ones_cb >> 2) & 1)));
-        const int ones_q = has_ones ? (int)(WG_A_BYTES / 16 / 128) + 2 * (ones_col >> 5) : -1;
+        const int ones_q = has_ones ? 2 * (ones_col >> 5) : -1;
+        const int quarter_a = warp & 3;  // this warp's TMEM lane quarter = dZ box: thread = dZ column quarter_a*32 + lane
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % WG_STAGES;
             mbar_wait(&full[s], (kb / WG_STAGES) & 1);
-            float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
-            float4* lo_t = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_RAW_BYTES);
+            {   // dZ^T -> TMEM: element (row k, column lane) of box quarter_a is at k*128 + (((lane>>3) ^ (k&3)) << 5) + (lane&7)*4
+                const uint8_t* box = smem + s * WG_STAGE_BYTES + quarter_a * WG_BOX_BYTES;
+                uint32_t hi[32], lo[32];
 #pragma unroll
-            for (int q = 0; q < (int)(WG_RAW_BYTES / 16 / 128); q++) {
+                for (int k = 0; k < 32; k++) {
+                    const float v = *reinterpret_cast<const float*>(box + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
+                    hi[k] = tf32_rn_bits(v);
+                    lo[k] = tf32_rn_bits(v - __uint_as_float(hi[k]));
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter_a * 32) << 16) + WG_TMEM_A_COL + (uint32_t)(s * 64);
+                tmem_st_32x32(ta, hi);
+                tmem_st_32x32(ta + 32, lo);
+            }
+            float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_A_BYTES);
+            float4* lo_t = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_A_BYTES + WG_B_BYTES);
+#pragma unroll
+            for (int q = 0; q < (int)(WG_B_BYTES / 16 / 128); q++) {
                 const int j = st_tid + 128 * q;
                 const float4 v = raw[j];
                 float4 h, l;
@@ -151,6 +168,8 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
                 }
                 raw[j] = h; lo_t[j] = l;
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s])) : "memory");
         }
