@@ -133,3 +133,38 @@ def test_cuda_graph_rollout_equals_eager_rollout(tmp_path):
         for x, y in zip(r_e, r_g):
             assert torch.equal(x, y)
     assert not torch.equal(outs[True][1][1], outs[True][2][1])  # different rollouts draw different actions
+
+
+@pytest.mark.parametrize("faithful", [True, False], ids=["column0_projection", "indexed_projection"])
+def test_fused_update_tracks_autograd_update(tmp_path, faithful):
+    """PPO.update with the K5 kernels (fused_update=True, default) against the same schedule on PyTorch autograd: same rollout, same
+    minibatch permutation, two optimiser epochs.  Losses agree to 1e-5 and the actors move together.  Gradient parity proper is
+    tests/test_update_gpu.py; here Adam sits in between, and Adam's first steps are lr * sign(g): an element whose gradient is zero up to
+    rounding (or carries a ReLU-gate flip, see that file) steps +-lr in either implementation -- so the check is the direction of the
+    whole update and the share of far-apart elements, not their size."""
+    import copy
+    a, _, maze_a = _make(256, tmp_path / "a", batch_size=256 * 40 // 5 * 5, horizon=40, faithful_projection=faithful, use_cuda_graph=False)
+    b, _, _ = _make(256, tmp_path / "b", batch_size=256 * 40 // 5 * 5, horizon=40, faithful_projection=faithful, use_cuda_graph=False, fused_update=False)
+    b.actor.load_state_dict(a.actor.state_dict()); b.critic.load_state_dict(a.critic.state_dict())
+    b.actor_optim = torch.optim.Adam(b.actor.parameters(), lr=0.00014); b.critic_optim = torch.optim.Adam(b.critic.parameters(), lr=0.00014)
+    a.actor_optim = torch.optim.Adam(a.actor.parameters(), lr=0.00014); a.critic_optim = torch.optim.Adam(a.critic.parameters(), lr=0.00014)
+    batch = a.get_batch()
+    b._rollouts = a._rollouts
+    a.updates_per_batch = b.updates_per_batch = 2
+    before = copy.deepcopy(a.actor.state_dict())
+    sa, sb = a.update(batch), b.update(batch)
+    assert sa["steps"] == sb["steps"] == 10
+    assert abs(sa["actor_loss"] - sb["actor_loss"]) < 1e-5 * max(1.0, abs(sb["actor_loss"])) + 1e-7
+    assert abs(sa["critic_loss"] - sb["critic_loss"]) < 1e-4 * abs(sb["critic_loss"]) + 1e-7
+    moved = moved_ref = far = total = 0
+    da, db = [], []
+    for (name, p), (_, q) in zip(a.actor.state_dict().items(), b.actor.state_dict().items()):
+        moved += int((p != before[name]).sum()); moved_ref += int((q != before[name]).sum()); total += p.numel()
+        far += int(((p - q).abs() > 2e-5).sum())
+        da.append((p - before[name]).flatten().double()); db.append((q - before[name]).flatten().double())
+        assert bool((p != before[name]).any()), name    # the fused path trained every block of the actor
+    assert moved > 0.5 * total and abs(moved - moved_ref) < 0.01 * total, (moved, moved_ref, total)   # (dead ReLU units never move, in either path)
+    da, db = torch.cat(da), torch.cat(db)
+    cos = float((da @ db) / (da.norm() * db.norm()))
+    assert cos > (0.999 if faithful else 0.98), cos
+    assert far < (2e-3 if faithful else 0.15) * total, (far, total)
