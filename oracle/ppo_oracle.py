@@ -130,3 +130,68 @@ def seeded_state_dicts(seed: int):
     for l in range(3):
         critic[f"layers.{l}.weight"], critic[f"layers.{l}.bias"] = lin(cd[l + 1], cd[l])
     return actor, critic
+
+
+def actor_update(sd: dict, obs, masks, actions, old_logp, adv, clip=0.2, faithful: bool = True):
+    """Actor half of PPO.train's inner loop (PPO.py:58-76) with its backward pass written out by hand, in float64:
+        joint_e = sum_i get_log_probs(i)           (PPO.py:65-67, 154-168)
+        ratio   = exp(joint - old_logp);  loss = -mean(min(ratio*A, clamp(ratio, 1-clip, 1+clip)*A))     (PPO.py:68-74)
+    and d loss / d (every actor parameter) -- what actor_loss.backward() leaves in .grad (PPO.py:76).  The reference's backward is torch
+    autograd; this restates the chain rule through the heads, the three Linear+ReLU layers, the residual single-head attention
+    (networks.py:75-82) and the 23 projections (networks.py:58-65), with torch's sub-gradient conventions: minimum() splits a tie evenly,
+    clamp() passes the gradient on its closed range, relu'(0) = 0.  obs [E,2,65], masks [E,2,6], actions [E,2,2] (move, mark).
+    Returns (loss, joint [E], grads: dict name -> array)."""
+    D = np.float64
+    P = {k: np.asarray(v, D) for k, v in sd.items()}
+    x = np.asarray(obs, D).reshape(-1, OBS_SPACE); B = x.shape[0]; E = B // 2
+    mk = np.asarray(masks).reshape(B, 6).astype(bool); act = np.asarray(actions).reshape(B, 2).astype(np.int64)
+    # ---- forward
+    sl, index = [], 0
+    for d in FEATURE_DIMS:
+        sl.append((0, d) if faithful else (index, index + d)); index += d
+    tok = np.stack([x[:, a:b] @ P[f"projection.layers.{i}.weight"].T + P[f"projection.layers.{i}.bias"] for i, (a, b) in enumerate(sl)], 1)
+    Wk, Wq, Wv = P["attention.keys.weight"], P["attention.querys.weight"], P["attention.values.weight"]
+    k, q, v = tok @ Wk.T, tok @ Wq.T, tok @ Wv.T
+    S = np.einsum("bij,bkj->bik", q, k) / np.sqrt(10.0)
+    Pm = np.exp(S - S.max(-1, keepdims=True)); Pm /= Pm.sum(-1, keepdims=True)
+    hs = [(tok + np.einsum("bij,bjk->bik", Pm, v)).reshape(B, FEATURE_AMOUNT * EMBEDDING_DIM)]
+    zs = []
+    for l in range(3):
+        zs.append(hs[-1] @ P[f"layers.{l}.weight"].T + P[f"layers.{l}.bias"]); hs.append(np.maximum(zs[-1], 0))
+    ml = hs[-1] @ P["move_head.weight"].T + P["move_head.bias"]
+    kl = (hs[-1] @ P["mark_head.weight"].T + P["mark_head.bias"]).reshape(B)
+    mlm = np.where(mk[:, :5], ml, -np.inf)
+    sm = np.exp(mlm - mlm.max(-1, keepdims=True)); sm /= sm.sum(-1, keepdims=True)
+    p = np.where(mk[:, 5], 1.0 / (1.0 + np.exp(-kl)), 0.0)
+    rows = np.arange(B)
+    with np.errstate(divide="ignore"):
+        lp = np.log(sm[rows, act[:, 0]]) + np.log(np.where(act[:, 1] == 1, p, 1.0 - p))
+    joint = lp.reshape(E, 2).sum(1)
+    A = np.asarray(adv, D); ratio = np.exp(joint - np.asarray(old_logp, D))
+    s1, s2 = ratio * A, np.clip(ratio, 1 - clip, 1 + clip) * A
+    loss = -np.minimum(s1, s2).mean()
+    # ---- backward
+    inside = (ratio >= 1 - clip) & (ratio <= 1 + clip)
+    g1 = np.where(s1 < s2, 1.0, np.where(s1 == s2, 0.5, 0.0))     # share of min()'s gradient that goes to surrogate1
+    dratio = -(g1 * A + (1.0 - g1) * A * inside) / E
+    dlp = np.repeat(dratio * ratio, 2)                             # d loss / d (each agent row's log-prob)
+    onehot = np.zeros((B, 5)); onehot[rows, act[:, 0]] = 1.0
+    dml = np.where(mk[:, :5], dlp[:, None] * (onehot - sm), 0.0)
+    dkl = np.where(mk[:, 5], dlp * (act[:, 1] - p), 0.0)
+    G = {"move_head.weight": dml.T @ hs[-1], "move_head.bias": dml.sum(0), "mark_head.weight": (dkl[:, None] * hs[-1]).sum(0, keepdims=True),
+         "mark_head.bias": dkl.sum(keepdims=True)}
+    dh = dml @ P["move_head.weight"] + dkl[:, None] * P["mark_head.weight"]
+    for l in (2, 1, 0):
+        dz = dh * (zs[l] > 0)
+        G[f"layers.{l}.weight"], G[f"layers.{l}.bias"] = dz.T @ hs[l], dz.sum(0)
+        dh = dz @ P[f"layers.{l}.weight"]
+    dctx = dh.reshape(B, FEATURE_AMOUNT, EMBEDDING_DIM)
+    dPm = np.einsum("bik,bjk->bij", dctx, v); dv = np.einsum("bij,bik->bjk", Pm, dctx)
+    dS = Pm * (dPm - (dPm * Pm).sum(-1, keepdims=True)) / np.sqrt(10.0)
+    dq, dk = np.einsum("bij,bjk->bik", dS, k), np.einsum("bij,bik->bjk", dS, q)
+    G["attention.querys.weight"] = np.einsum("bik,bij->kj", dq, tok); G["attention.keys.weight"] = np.einsum("bik,bij->kj", dk, tok)
+    G["attention.values.weight"] = np.einsum("bik,bij->kj", dv, tok)
+    dtok = dctx + dq @ Wq + dk @ Wk + dv @ Wv
+    for i, (a, b) in enumerate(sl):
+        G[f"projection.layers.{i}.weight"], G[f"projection.layers.{i}.bias"] = dtok[:, i].T @ x[:, a:b], dtok[:, i].sum(0)
+    return loss, joint, G

@@ -186,3 +186,37 @@ def test_fused_actor_loss_gradients_match_autograd(faithful):
         worst = max(worst, r)
         assert r < max(2e-5, 4 * r32), (name, r, r32)
     print("worst relative gradient error", worst, "dX0", r_dx0, r32_dx0)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_fused_actor_loss_matches_reference_golden(seed):
+    """The K5 path on the committed reference fixture (tests/golden/upd_kats.npz: the reference's own get_log_probs + actor_loss.backward(),
+    torch CPU fp32, 384 envs of a recorded trace): loss, joint log-probs, every actor parameter gradient."""
+    import os
+    import numpy as np
+    from golden_util import GOLDEN
+    from oracle import ppo_oracle as po
+    from marl_maze_b200.networks import Actor
+    from marl_maze_b200.update import actor_loss
+    Z = np.load(os.path.join(GOLDEN, "upd_kats.npz"))
+    asd, _ = po.seeded_state_dicts(seed)
+    actor = Actor([264, 264, 264]).cuda()
+    actor.load_state_dict({k: torch.from_numpy(v) for k, v in asd.items()})
+    obs = torch.from_numpy(Z["upd/obs"]).cuda().reshape(-1, 65); masks = torch.from_numpy(Z["upd/masks"]).cuda().reshape(-1, 6)
+    acts = torch.from_numpy(Z["upd/actions"]).cuda().reshape(-1, 2)
+    old = torch.from_numpy(Z[f"upd/{seed}/old"]).cuda(); adv = torch.from_numpy(Z[f"upd/{seed}/adv"]).cuda()
+    E = old.shape[0]
+    loss, logp = actor_loss(actor, obs, masks, acts, old, adv, float(Z["upd/clip"]), 1.0 / E)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(Z[f"upd/{seed}/loss"])) < 1e-5 * max(1.0, abs(float(Z[f"upd/{seed}/loss"])))
+    assert np.allclose(logp.cpu().numpy(), Z[f"upd/{seed}/joint"], rtol=1e-5, atol=1e-5)
+    stride, worst = int(Z["upd/stride"]), 0.0
+    for name, p in actor.named_parameters():
+        ref = Z[f"upd/{seed}/grad/{name}"]
+        got = p.grad.cpu().numpy()
+        if name in ("layers.0.weight", "layers.1.weight", "layers.2.weight"):
+            got = got.reshape(-1)[::stride]
+        err = float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max())
+        worst = max(worst, err)
+        assert err < 2e-5, (name, err)
+    print("worst relative gradient error vs the reference", worst)

@@ -142,7 +142,7 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__" and "--ppo" not in sys.argv:
+if __name__ == "__main__" and "--ppo" not in sys.argv and "--upd" not in sys.argv:
     main()
 
 
@@ -202,5 +202,64 @@ def make_ppo_kats():
     print("ppo_kats.npz", os.path.getsize(os.path.join(OUT, "ppo_kats.npz")))
 
 
+def make_upd_kats():
+    """Actor-update known answers from the reference's own PPO.py:58-76 (get_log_probs for both agents, ratio, clipped surrogate,
+    actor_loss.backward()) on torch CPU fp32: loss, joint log-probs and the gradient of every actor parameter (the three trunk
+    weight matrices as every 5th element of the flattened gradient, to keep the fixture small)."""
+    import contextlib, io
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import ppo_oracle as po
+    rh.load_reference()
+    sys.path.insert(0, rh.REFERENCE_DIR)
+    cwd = os.getcwd(); os.chdir("/tmp")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import PPO as ref_ppo, networks as ref_net
+    finally:
+        os.chdir(cwd); sys.path.remove(rh.REFERENCE_DIR)
+    z = np.load(os.path.join(OUT, "env_traces.npz"))
+    n = 384
+    obs = z["guided_a/step_obs"][:n]; masks = z["guided_a/step_masks"][:n].astype(bool)
+    rng = np.random.default_rng(77)
+    acts = np.zeros((n, 2, 2), np.uint8)     # mask-legal actions (an action the mask forbids has log-prob -inf and makes the ratio NaN)
+    for e in range(n):
+        for a in range(2):
+            acts[e, a, 0] = rng.choice(np.flatnonzero(masks[e, a, :5]))
+            acts[e, a, 1] = rng.integers(0, 2) if masks[e, a, 5] else 0
+    out = {"upd/obs": obs, "upd/masks": masks.astype(np.uint8), "upd/actions": acts, "upd/clip": np.float32(0.2), "upd/stride": np.int32(5)}
+
+    class Holder:
+        pass
+    for seed in (11, 12):
+        asd, _ = po.seeded_state_dicts(seed)
+        actor = ref_net.Actor([264, 264, 264]); actor.load_state_dict({k: torch.from_numpy(v) for k, v in asd.items()})
+        h = Holder(); h.actor = actor
+        t_obs, t_act, t_masks = torch.from_numpy(obs), torch.from_numpy(acts.astype(np.float32)), torch.from_numpy(masks)
+        with torch.no_grad():
+            base = sum(ref_ppo.PPO.get_log_probs(h, i, t_obs, t_act, t_masks) for i in range(2))
+        old = (base.numpy() + 0.3 * rng.standard_normal(n)).astype(np.float32)      # ratios on both sides of the clip range
+        adv = rng.standard_normal(n).astype(np.float32)
+        m_log_probs, m_advantage, clip = torch.from_numpy(old), torch.from_numpy(adv), 0.2
+        current_log_prob = 0
+        for i in range(2):                                                            # PPO.py:65-67
+            current_log_prob += ref_ppo.PPO.get_log_probs(h, i, t_obs, t_act, t_masks)
+        prob_ratios = torch.exp(current_log_prob - m_log_probs)                       # PPO.py:68
+        surrogate1 = prob_ratios * m_advantage
+        surrogate2 = torch.clamp(prob_ratios, 1 - clip, 1 + clip) * m_advantage
+        actor_loss = -torch.mean(torch.min(surrogate1, surrogate2))                   # PPO.py:74
+        actor.zero_grad(); actor_loss.backward()
+        out[f"upd/{seed}/old"] = old; out[f"upd/{seed}/adv"] = adv
+        out[f"upd/{seed}/loss"] = np.float32(actor_loss.item()); out[f"upd/{seed}/joint"] = current_log_prob.detach().numpy()
+        out[f"upd/{seed}/frac_clipped"] = np.float32(((prob_ratios < 0.8) | (prob_ratios > 1.2)).float().mean().item())
+        for name, p in actor.named_parameters():
+            g = p.grad.numpy()
+            out[f"upd/{seed}/grad/{name}"] = g.reshape(-1)[::5].copy() if name in ("layers.0.weight", "layers.1.weight", "layers.2.weight") else g
+    np.savez_compressed(os.path.join(OUT, "upd_kats.npz"), **out)
+    print("upd_kats.npz", os.path.getsize(os.path.join(OUT, "upd_kats.npz")))
+
+
 if __name__ == "__main__" and "--ppo" in sys.argv:
     make_ppo_kats()
+if __name__ == "__main__" and "--upd" in sys.argv:
+    make_upd_kats()
