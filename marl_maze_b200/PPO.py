@@ -42,7 +42,7 @@ def _dist():
 class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
-                 verbose: bool = True, micro_batch: int = 1 << 17, update_tf32: bool = False, use_cuda_graph: bool = True,
+                 verbose: bool = True, micro_batch: int = 1 << 20, update_tf32: bool = False, use_cuda_graph: bool = True,
                  fused_update: bool = True):
         if agent_amount != 2:
             raise NotImplementedError("two agents (README.md:34)")

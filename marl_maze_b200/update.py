@@ -17,6 +17,9 @@ def _stream(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+WGRAD_MAX_ROWS = 1 << 18  # rows per mm_wgrad_tf32x3 launch: bounds how many MMA results one TMEM accumulator sums (the tensor core truncates)
+
+
 def wgrad(dz: torch.Tensor, h: torch.Tensor):
     """(dW [n_out,k_in], db [n_out]) = (dz^T h, column sums of dz) for one Linear layer, 3xTF32 on tcgen05 (mm_wgrad_tf32x3)."""
     assert dz.is_cuda and h.is_cuda and dz.dtype == h.dtype == torch.float32 and dz.is_contiguous() and h.is_contiguous()
@@ -24,11 +27,15 @@ def wgrad(dz: torch.Tensor, h: torch.Tensor):
     k_in = h.shape[1]
     assert h.shape[0] == R
     L = _abi.lib()
-    slabs, ld = C.c_int32(), C.c_int32()
-    _abi.check(L.mm_wgrad_geometry(R, n_out, k_in, C.byref(slabs), C.byref(ld)), "mm_wgrad_geometry")
-    part = torch.empty(slabs.value, n_out, ld.value, device=dz.device, dtype=torch.float32)
-    _abi.check(L.mm_wgrad_tf32x3(_ptr(dz), _ptr(h), R, n_out, k_in, _ptr(part), _stream(dz)), "mm_wgrad_tf32x3")
-    tot = part.sum(0)
+    tot = None
+    for r0 in range(0, R, WGRAD_MAX_ROWS):
+        r = min(WGRAD_MAX_ROWS, R - r0)
+        slabs, ld = C.c_int32(), C.c_int32()
+        _abi.check(L.mm_wgrad_geometry(r, n_out, k_in, C.byref(slabs), C.byref(ld)), "mm_wgrad_geometry")
+        part = torch.empty(slabs.value, n_out, ld.value, device=dz.device, dtype=torch.float32)
+        _abi.check(L.mm_wgrad_tf32x3(_ptr(dz[r0:r0 + r]), _ptr(h[r0:r0 + r]), r, n_out, k_in, _ptr(part), _stream(dz)), "mm_wgrad_tf32x3")
+        t = part.sum(0)
+        tot = t if tot is None else tot + t
     return tot[:, :k_in], tot[:, k_in]
 
 
