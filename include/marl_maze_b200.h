@@ -169,12 +169,13 @@ int mm_counter_add(uint64_t *counter_dev, uint64_t v, void *stream);
  * K5 -- building blocks of the PPO actor update (PPO.py:58-85: loss.backward() through Actor.layers), SURVEY 8(f).1.
  *
  * mm_wgrad_tf32x3: weight + bias gradient of one Linear layer.  dz [rows][n_out] f32 = gradient at the layer's pre-activation, h
- * [rows][k_in] f32 = the layer's input.  Writes `slabs` partial sums part [slabs][n_out][ld] (geometry from mm_wgrad_geometry):
- *     sum_s part[s][n][k]    = dW[n][k] = sum_r dz[r][n] h[r][k]   for k < k_in,
- *     sum_s part[s][n][k_in] = db[n]    = sum_r dz[r][n]
+ * [rows][k_in] f32 = the layer's input.  Writes `slabs` partial sums (geometry from mm_wgrad_geometry) of dW[n][k] = sum_r dz[r][n]
+ * h[r][k] and db[n] = sum_r dz[r][n], in whichever orientation needs fewer 128 x 288 output tiles:
+ *     transposed == 0: part [slabs][out_rows = n_out][ld]:     sum_s part[s][n][k] = dW[n][k] (k < k_in),  sum_s part[s][n][k_in] = db[n]
+ *     transposed == 1: part [slabs][out_rows = k_in + 1][ld]:  sum_s part[s][k][n] = dW[n][k] (k < k_in),  sum_s part[s][k_in][n] = db[n]
  * computed as 3xTF32 tcgen05.mma with fp32 accumulation; n_out and k_in must be multiples of 4, base pointers 16-byte aligned.
  */
-int mm_wgrad_geometry(int rows, int n_out, int k_in, int32_t *slabs, int32_t *ld);
+int mm_wgrad_geometry(int rows, int n_out, int k_in, int32_t *slabs, int32_t *ld, int32_t *out_rows, int32_t *transposed);
 int mm_wgrad_tf32x3(const float *dz, const float *h, int rows, int n_out, int k_in, float *part, void *stream);
 
 /*
@@ -204,6 +205,14 @@ int mm_ppo_loss_geometry(int32_t *blocks, int32_t *ld);
 int mm_ppo_heads_loss(const float *h2, const float *head_w, const float *head_b, const uint8_t *masks, const uint8_t *actions,
                       const float *old_logp, const float *adv, int n_envs, float clip, float scale, float *dz2, float *logp,
                       float *part, void *stream);
+
+/*
+ * mm_segment_sum: part [blocks][n_seg][cols] <- per-block partial sums of out[s][c] = sum over rows r with seg[r] == s of x[r][c]
+ * (n_seg <= 8, cols a multiple of 4, blocks = mm_segment_sum_blocks(rows)).  The backward of gathering the embedding of each agent row
+ * from the few distinct (projection + attention) outputs that `Actor.embed` evaluates (networks.py:31-35 fed identical prefixes).
+ */
+int mm_segment_sum_blocks(int rows);
+int mm_segment_sum(const float *x, const int64_t *seg, int rows, int cols, int n_seg, float *part, void *stream);
 
 #ifdef __cplusplus
 }

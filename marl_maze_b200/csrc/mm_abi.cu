@@ -169,11 +169,11 @@ int mm_counter_add(uint64_t* counter_dev, uint64_t v, void* stream) {
     return cuda_status(launch_add_u64((unsigned long long*)counter_dev, v, (cudaStream_t)stream));
 }
 
-int mm_wgrad_geometry(int rows, int n_out, int k_in, int32_t* slabs, int32_t* ld) {
-    if (rows <= 0 || n_out <= 0 || k_in <= 0 || !slabs || !ld) return MM_ERR_BAD_ARG;
-    int s, l, per;
-    wgrad_geometry(rows, n_out, k_in, &s, &l, &per);
-    *slabs = s; *ld = l;
+int mm_wgrad_geometry(int rows, int n_out, int k_in, int32_t* slabs, int32_t* ld, int32_t* out_rows, int32_t* transposed) {
+    if (rows <= 0 || n_out <= 0 || k_in <= 0 || !slabs || !ld || !out_rows || !transposed) return MM_ERR_BAD_ARG;
+    int s, l, per, orows, tr;
+    wgrad_geometry(rows, n_out, k_in, &s, &l, &per, &orows, &tr);
+    *slabs = s; *ld = l; *out_rows = orows; *transposed = tr;
     return MM_OK;
 }
 int mm_wgrad_tf32x3(const float* dz, const float* h, int rows, int n_out, int k_in, float* part, void* stream) {
@@ -203,6 +203,12 @@ int mm_ppo_heads_loss(const float* h2, const float* head_w, const float* head_b,
     if (!h2 || !head_w || !head_b || !masks || !actions || !old_logp || !adv || !dz2 || !part || n_envs <= 0) return MM_ERR_BAD_ARG;
     PpoLossArgs a{h2, head_w, head_b, masks, actions, old_logp, adv, clip, scale, dz2, logp, part, n_envs};
     return cuda_status(launch_ppo_heads_loss(a, (cudaStream_t)stream));
+}
+
+int mm_segment_sum_blocks(int rows) { return rows > 0 ? segment_sum_blocks(rows) : 0; }
+int mm_segment_sum(const float* x, const int64_t* seg, int rows, int cols, int n_seg, float* part, void* stream) {
+    if (!x || !seg || !part || rows <= 0 || cols <= 0 || (cols & 3) || n_seg < 1 || n_seg > 8 || ((uintptr_t)x & 15) || ((uintptr_t)part & 15)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_segment_sum(x, (const long long*)seg, rows, cols, n_seg, part, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -35,7 +35,12 @@ constexpr uint32_t TC_B1_BYTES = TC_N1 * TC_BK * 4;   // 18432
 constexpr uint32_t TC_B2_BYTES = TC_N2 * TC_BK * 4;   // 16384
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * (TC_B1_BYTES + TC_B2_BYTES);  // 102400
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 192;
+#ifndef MM_TC_SPLIT_WARPS
+#define MM_TC_SPLIT_WARPS 8   // splitter / epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, i.e. two per scheduler)
+#endif
+constexpr int TC_SPLIT_WARPS = MM_TC_SPLIT_WARPS;
+static_assert(TC_SPLIT_WARPS == 4 || TC_SPLIT_WARPS == 8, "one or two warps per TMEM lane quarter");
+constexpr int TC_THREADS = 64 + 32 * TC_SPLIT_WARPS;
 // MM_TC_A_TMEM: the activation operand reaches the tensor core through TENSOR MEMORY instead of shared memory.  An SS-form tf32 MMA of
 // M = 128, N = 144 reads (128 + 144) * 32 bytes of shared memory for 78 clocks of math -- 111 of the SM's 128 bytes/clock -- and the 3xTF32
 // scheme issues three of them per k-step on top of the TMA writes and the splitter's own traffic: the SS kernel is shared-memory-bandwidth
@@ -84,7 +89,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     const int nkb = (K + TC_BK - 1) / TC_BK;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split_done[s], 128); }
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split_done[s], 32 * TC_SPLIT_WARPS); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -152,6 +157,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     } else {
         // ===== splitter (main loop): 128 threads turn each landed fp32 A tile into (hi in place, lo beside it)
         const int st_tid = threadIdx.x - 64;
+        const int whalf = (warp - 2) >> 2;  // 0 for the first warp of a TMEM lane quarter, 1 for the second (8-warp build)
         uint32_t gbits[9];
         if (kMode == TC_EPI_GATE) {
             const long long grow = (long long)m0 + (warp & 3) * 32 + lane;  // the output row this thread owns in the epilogue
@@ -165,28 +171,44 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             // thread = row (its TMEM lane): logical 16-byte chunk c of row r sits at physical chunk c ^ (r & 7) of the 128-byte swizzled row
             const int arow = (warp & 3) * 32 + lane;
             const float4* rowp = reinterpret_cast<const float4*>(smem + s * TC_STAGE_BYTES + arow * 128);
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const float4 v = rowp[c ^ (arow & 7)];
-                const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    hi[4 * c + j] = tf32_rn_bits(e[j]);
-                    lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
-                }
-            }
             const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TC_TMEM_A_COL + (uint32_t)(s * 64);
-            tmem_st_32x32(ta, hi);
-            tmem_st_32x32(ta + 32, lo);
+            if (TC_SPLIT_WARPS == 4) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float4 v = rowp[c ^ (arow & 7)];
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        hi[4 * c + j] = tf32_rn_bits(e[j]);
+                        lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
+                    }
+                }
+                tmem_st_32x32(ta, hi);
+                tmem_st_32x32(ta + 32, lo);
+            } else {  // the two warps of a quarter take k-columns 0..15 and 16..31 of the row
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float4 v = rowp[(c + 4 * whalf) ^ (arow & 7)];
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        hi[4 * c + j] = tf32_rn_bits(e[j]);
+                        lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
+                    }
+                }
+                tmem_st_32x16(ta + 16 * whalf, hi);
+                tmem_st_32x16(ta + 32 + 16 * whalf, lo);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #else
             float4* raw = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
             float4* lo_t = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_A_BYTES);
 #pragma unroll
-            for (int q = 0; q < (int)(TC_A_BYTES / 16 / 128); q++) {
-                const int j = st_tid + 128 * q;
+            for (int q = 0; q < (int)(TC_A_BYTES / 16 / (32 * TC_SPLIT_WARPS)); q++) {
+                const int j = st_tid + 32 * TC_SPLIT_WARPS * q;
                 const float4 v = raw[j];
                 float4 h, l;
                 h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
@@ -209,8 +231,9 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         float* t_y = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * kTP;
         const int row0 = m0 + quarter * 32;
         float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int c_lo = (TC_SPLIT_WARPS == 8 && whalf) ? 5 : 0, c_hi = (TC_SPLIT_WARPS == 8 && !whalf) ? 5 : 9;  // a quarter's two warps share the chunks
 #pragma unroll 1
-        for (int c = 0; c < 9; c++) {  // 9 x 32 columns >= 264
+        for (int c = c_lo; c < c_hi; c++) {  // 9 x 32 columns >= 264
             uint32_t gword = 0;
             if (kMode == TC_EPI_GATE) {  // gbits[c] with a rolled loop: select without dynamic register indexing
 #pragma unroll
@@ -262,7 +285,19 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             }
             __syncwarp();
         }
-        if (kHeads) {  // one thread = one agent row; rows 2e and 2e+1 (the two agents of env e) sit in adjacent lanes
+        if (kHeads && TC_SPLIT_WARPS == 8) {  // add the partner warp's partial head dot products (same rows, the other column chunks)
+            float* xch = reinterpret_cast<float*>(smem) + (size_t)TC_SPLIT_WARPS * 32 * kTP + (size_t)(quarter * 32 + lane) * 6;
+            if (whalf) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) xch[j] = hacc[j];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (!whalf) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) hacc[j] += xch[j];
+            }
+        }
+        if (kHeads && !(TC_SPLIT_WARPS == 8 && whalf)) {  // one thread = one agent row; rows 2e and 2e+1 (the two agents of env e) sit in adjacent lanes
             const long long row = (long long)row0 + lane;
             float lp = 0.f;
             if (row < M) {

@@ -147,3 +147,47 @@ cudaError_t launch_ppo_heads_loss(const PpoLossArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace mm
+
+// ------------------------------------------------------------------------------------------------ segment sum
+// out[s][c] = sum over rows r with seg[r] == s of x[r][c], for a handful of segments (n_seg <= 8): the backward of gathering [rows][cols]
+// activations from n_seg distinct source rows (Actor.embed evaluates projection + attention once per distinct observation prefix).
+// A scatter-add would funnel every row into n_seg addresses; here each block walks a contiguous row range with one float4 column group
+// per thread and keeps the n_seg running sums in registers; per-block partials are added by the host (deterministic).
+namespace mm {
+
+constexpr int SS_MAX_SEG = 8, SS_THREADS = 128;
+
+__global__ void __launch_bounds__(SS_THREADS) k_segment_sum(const float* __restrict__ x, const long long* __restrict__ seg, int rows, int cols, int n_seg,
+                                                            int rows_per_block, float* __restrict__ part) {
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int c4 = threadIdx.x; c4 * 4 < cols; c4 += SS_THREADS) {
+        float4 acc[SS_MAX_SEG];
+#pragma unroll
+        for (int s = 0; s < SS_MAX_SEG; s++) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = r0; r < r1; r++) {
+            const int sg = (int)__ldg(&seg[r]);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * cols) + c4);
+#pragma unroll
+            for (int s = 0; s < SS_MAX_SEG; s++)
+                if (s == sg) { acc[s].x += v.x; acc[s].y += v.y; acc[s].z += v.z; acc[s].w += v.w; }
+        }
+#pragma unroll
+        for (int s = 0; s < SS_MAX_SEG; s++)
+            if (s < n_seg) *(reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * n_seg + s) * cols) + c4) = acc[s];
+    }
+}
+
+int segment_sum_blocks(int rows) {
+    const int want = 148 * 8;
+    return rows < want ? (rows > 0 ? rows : 1) : want;
+}
+
+cudaError_t launch_segment_sum(const float* x, const long long* seg, int rows, int cols, int n_seg, float* part, cudaStream_t stream) {
+    if (n_seg < 1 || n_seg > SS_MAX_SEG || (cols & 3) || rows <= 0) return cudaErrorInvalidValue;
+    const int blocks = segment_sum_blocks(rows);
+    const int per = (rows + blocks - 1) / blocks;
+    k_segment_sum<<<blocks, SS_THREADS, 0, stream>>>(x, seg, rows, cols, n_seg, per, part);
+    return cudaGetLastError();
+}
+
+}  // namespace mm

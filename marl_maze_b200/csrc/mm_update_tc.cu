@@ -30,7 +30,8 @@ constexpr uint32_t WG_B_BYTES = (WG_N / 32) * WG_BOX_BYTES;                // 36
 constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + 2 * WG_B_BYTES;           // dZ boxes (fp32, read once by the splitter) | H hi (in place) | H lo
 constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t WG_TMEM_A_COL = 288;   // D occupies TMEM columns 0..287; dZ^T stages [hi 32 | lo 32] per pipeline stage from column 288
-constexpr int WG_THREADS = 192;
+constexpr int WG_SPLIT_WARPS = 8;                         // two per scheduler: one warp alone cannot cover its own shared-memory / TMEM latencies
+constexpr int WG_THREADS = 64 + 32 * WG_SPLIT_WARPS;
 constexpr uint32_t WG_TMEM_COLS = 512;
 
 // MN-major operands of 32-bit elements have exactly one legal shared-memory layout, SWIZZLE_128B_BASE32B (cute::UMMA::LayoutType 1,
@@ -49,11 +50,11 @@ __device__ __forceinline__ float tf32_rn_i(float x) {  // cvt.rna.tf32.f32 on fi
 }
 
 struct WgMaps {
-    CUtensorMap dz, h;
+    CUtensorMap a, b;  // A: the operand whose columns become rows of the result (through TMEM); B: columns of the result (shared memory)
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, int R, int n_out, int k_in, int n_mt, int n_nt, int kb_per, int ld) {
+k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, int R, int a_cols, int b_cols, int ones_on_a, int n_mt, int n_nt, int kb_per, int ld) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -69,10 +70,13 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
     const int nkb_total = (R + WG_BK - 1) / WG_BK;
     const int kb0 = slab * kb_per;
     const int nkb = min(kb_per, nkb_total - kb0);  // >= 1 by construction of the grid
-    const int ones_col = k_in - nt * WG_N;         // local column of H's appended ones (bias gradient), if it falls into this n-tile
+    // the appended column of ones (bias gradient) lives on whichever operand is H: as local column ones_col of this n-tile's B boxes, or as
+    // row a_cols of the A operand
+    const int ones_col = ones_on_a ? -1 : b_cols - nt * WG_N;
+    const int out_rows = a_cols + (ones_on_a ? 1 : 0);
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < WG_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split_done[s], 128); }
+        for (int s = 0; s < WG_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split_done[s], 32 * WG_SPLIT_WARPS); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -94,9 +98,9 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
                 mbar_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
                 const int r0 = (kb0 + kb) * WG_BK;
 #pragma unroll
-                for (int j = 0; j < WG_M / 32; j++) tma_load_2d(st + j * WG_BOX_BYTES, &maps.dz, mt * WG_M + 32 * j, r0, &full[s]);
+                for (int j = 0; j < WG_M / 32; j++) tma_load_2d(st + j * WG_BOX_BYTES, &maps.a, mt * WG_M + 32 * j, r0, &full[s]);
 #pragma unroll
-                for (int j = 0; j < WG_N / 32; j++) tma_load_2d(st + WG_A_BYTES + j * WG_BOX_BYTES, &maps.h, nt * WG_N + 32 * j, r0, &full[s]);
+                for (int j = 0; j < WG_N / 32; j++) tma_load_2d(st + WG_A_BYTES + j * WG_BOX_BYTES, &maps.b, nt * WG_N + 32 * j, r0, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -127,42 +131,43 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
             umma_commit(tmem_full);
         }
     } else {
-        // ===== splitter.  H boxes: 2304 float4 per stage over 128 threads; thread t owns float4 t + 128 q; in a box, float4 i is row i/8 and
-        // physical 16-byte slot i%8 of that row; logical column c of row r sits in slot (((c>>3) ^ (r&3)) << 1) | ((c>>2)&1).
+        // ===== splitter, 8 warps.  H boxes: 2304 float4 per stage over 256 threads; thread t owns float4 t + 256 q, i.e. box q, row t/8,
+        // physical 16-byte slot t%8 of that row; logical column c of row r sits in slot (((c>>3) ^ (r&3)) << 1) | ((c>>2)&1).
         const int st_tid = threadIdx.x - 64;
-        // the ones column: box ones_col/32; its rows r and r+16 belong to the thread with (t>>3) == r%16 and (t&7) == slot(r), at
-        // q = 2*box (+1 for the upper 16 rows)
+        // the ones column: box ones_col/32 (= its q); row r of it belongs to the thread with t/8 == r and t%8 == slot(r)
         const bool has_ones = ones_col >= 0 && ones_col < WG_N;
         const int ones_cb = ones_col & 31, ones_e = ones_col & 3;
         const bool ones_owner = has_ones && ((st_tid & 7) == ((((ones_cb >> 3) ^ ((st_tid >> 3) & 3)) << 1) | ((ones_cb >> 2) & 1)));
-        const int ones_q = has_ones ? 2 * (ones_col >> 5) : -1;
-        const int quarter_a = warp & 3;  // this warp's TMEM lane quarter = dZ box: thread = dZ column quarter_a*32 + lane
+        const int ones_q = has_ones ? (ones_col >> 5) : -1;
+        const int quarter_a = warp & 3;           // this warp's TMEM lane quarter = dZ box: thread = dZ column quarter_a*32 + lane
+        const int khalf = ((warp - 2) >> 2) * 16;  // the two warps of a quarter take k-rows 0..15 and 16..31 of the stage
+        const bool a_is_ones = ones_on_a && (mt * WG_M + quarter_a * 32 + lane == a_cols);
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % WG_STAGES;
             mbar_wait(&full[s], (kb / WG_STAGES) & 1);
             {   // dZ^T -> TMEM: element (row k, column lane) of box quarter_a is at k*128 + (((lane>>3) ^ (k&3)) << 5) + (lane&7)*4
-                const uint8_t* box = smem + s * WG_STAGE_BYTES + quarter_a * WG_BOX_BYTES;
-                uint32_t hi[32], lo[32];
+                const uint8_t* box = smem + s * WG_STAGE_BYTES + quarter_a * WG_BOX_BYTES + khalf * 128;
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int k = 0; k < 32; k++) {
+                for (int k = 0; k < 16; k++) {  // khalf is a multiple of 4: (khalf + k) & 3 == k & 3
                     const float v = *reinterpret_cast<const float*>(box + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
-                    hi[k] = tf32_rn_bits(v);
-                    lo[k] = tf32_rn_bits(v - __uint_as_float(hi[k]));
+                    hi[k] = a_is_ones ? 0x3F800000u : tf32_rn_bits(v);
+                    lo[k] = a_is_ones ? 0u : tf32_rn_bits(v - __uint_as_float(hi[k]));
                 }
-                const uint32_t ta = tmem_base + ((uint32_t)(quarter_a * 32) << 16) + WG_TMEM_A_COL + (uint32_t)(s * 64);
-                tmem_st_32x32(ta, hi);
-                tmem_st_32x32(ta + 32, lo);
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter_a * 32) << 16) + WG_TMEM_A_COL + (uint32_t)(s * 64 + khalf);
+                tmem_st_32x16(ta, hi);
+                tmem_st_32x16(ta + 32, lo);
             }
             float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_A_BYTES);
             float4* lo_t = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_A_BYTES + WG_B_BYTES);
 #pragma unroll
-            for (int q = 0; q < (int)(WG_B_BYTES / 16 / 128); q++) {
-                const int j = st_tid + 128 * q;
+            for (int q = 0; q < (int)(WG_B_BYTES / 16 / (32 * WG_SPLIT_WARPS)); q++) {
+                const int j = st_tid + 32 * WG_SPLIT_WARPS * q;
                 const float4 v = raw[j];
                 float4 h, l;
                 h.x = tf32_rn_i(v.x); h.y = tf32_rn_i(v.y); h.z = tf32_rn_i(v.z); h.w = tf32_rn_i(v.w);
                 l.x = tf32_rn_i(v.x - h.x); l.y = tf32_rn_i(v.y - h.y); l.z = tf32_rn_i(v.z - h.z); l.w = tf32_rn_i(v.w - h.w);
-                if (ones_owner && (q == ones_q || q == ones_q + 1)) {
+                if (ones_owner && q == ones_q) {
                     if (ones_e == 0) { h.x = 1.0f; l.x = 0.0f; } else if (ones_e == 1) { h.y = 1.0f; l.y = 0.0f; }
                     else if (ones_e == 2) { h.z = 1.0f; l.z = 0.0f; } else { h.w = 1.0f; l.w = 0.0f; }
                 }
@@ -179,9 +184,9 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int n = mt * WG_M + quarter * 32 + lane;
-        float* dst = part + ((size_t)slab * n_out + n) * ld + nt * WG_N;
+        float* dst = part + ((size_t)slab * out_rows + n) * ld + nt * WG_N;
 #pragma unroll 1
-        for (int c = 0; c < WG_N / 32; c++) {
+        for (int c = (khalf ? 5 : 0); c < (khalf ? WG_N / 32 : 5); c++) {  // the two warps of a quarter share the 9 column chunks
             uint32_t v[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -190,7 +195,7 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
                   "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr + (uint32_t)(c * 32)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (n < n_out) {
+            if (n < out_rows) {
 #pragma unroll
                 for (int q = 0; q < 8; q++)
                     *reinterpret_cast<float4*>(dst + c * 32 + 4 * q) =
@@ -218,34 +223,42 @@ static bool make_map_mn(CUtensorMap* m, const float* base, int rows, int cols) {
                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Geometry of the partial buffer for (R, n_out, k_in): ld = n-tiles * 288 columns per row (column k_in holds db), `slabs` row slabs.
-void wgrad_geometry(int R, int n_out, int k_in, int* slabs, int* ld, int* kb_per) {
-    const int n_mt = (n_out + WG_M - 1) / WG_M, n_nt = (k_in + 1 + WG_N - 1) / WG_N;
+// Geometry for (R, n_out, k_in).  The result tile grid is 128 rows (A operand columns) x 288 columns (B operand columns); dZ^T [H | 1] can be
+// laid out either way round, and the orientation with fewer tiles wins: 264 x 461 is 3 x 2 tiles as dZ^T [H|1] but 4 x 1 as [H|1]^T dZ.
+// transposed = 0: part [slabs][n_out][ld], column k_in = db.   transposed = 1: part [slabs][k_in + 1][ld], row k_in = db.
+void wgrad_geometry(int R, int n_out, int k_in, int* slabs, int* ld, int* kb_per, int* out_rows, int* transposed) {
+    const int t0 = ((n_out + WG_M - 1) / WG_M) * ((k_in + 1 + WG_N - 1) / WG_N), t1 = ((k_in + 1 + WG_M - 1) / WG_M) * ((n_out + WG_N - 1) / WG_N);
+    const int tr = t1 < t0 ? 1 : 0;
+    const int tiles = tr ? t1 : t0;
+    const int n_nt = tr ? (n_out + WG_N - 1) / WG_N : (k_in + 1 + WG_N - 1) / WG_N;
     const int nkb_total = (R + WG_BK - 1) / WG_BK;
-    int want = 148 / (n_mt * n_nt);  // one CTA per SM
+    int want = 148 / tiles;  // one CTA per SM
     if (want < 1) want = 1;
     int per = (nkb_total + want - 1) / want;
     if (per < 1) per = 1;
     *slabs = (nkb_total + per - 1) / per;
     *ld = n_nt * WG_N;
     *kb_per = per;
+    *out_rows = tr ? k_in + 1 : n_out;
+    *transposed = tr;
 }
 
-// part [slabs][n_out][ld] <- per-slab partial sums of dZ^T [H | 1]
+// per-slab partial sums of dZ^T [H | 1] (or its transpose, see wgrad_geometry)
 cudaError_t launch_wgrad_tc(const float* dz, const float* h, int R, int n_out, int k_in, float* part, cudaStream_t stream) {
     if (R <= 0 || (n_out & 3) || (k_in & 3)) return cudaErrorInvalidValue;
-    int slabs, ld, kb_per;
-    wgrad_geometry(R, n_out, k_in, &slabs, &ld, &kb_per);
-    const int n_mt = (n_out + WG_M - 1) / WG_M, n_nt = ld / WG_N;
+    int slabs, ld, kb_per, out_rows, tr;
+    wgrad_geometry(R, n_out, k_in, &slabs, &ld, &kb_per, &out_rows, &tr);
+    const int a_cols = tr ? k_in : n_out, b_cols = tr ? n_out : k_in;
+    const int n_mt = (out_rows + WG_M - 1) / WG_M, n_nt = ld / WG_N;
     WgMaps maps;
-    if (!make_map_mn(&maps.dz, dz, R, n_out) || !make_map_mn(&maps.h, h, R, k_in)) return cudaErrorInvalidValue;
+    if (!make_map_mn(&maps.a, tr ? h : dz, R, a_cols) || !make_map_mn(&maps.b, tr ? dz : h, R, b_cols)) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_wgrad_tf32x3<<<slabs * n_mt * n_nt, WG_THREADS, WG_SMEM_BYTES, stream>>>(maps, part, R, n_out, k_in, n_mt, n_nt, kb_per, ld);
+    k_wgrad_tf32x3<<<slabs * n_mt * n_nt, WG_THREADS, WG_SMEM_BYTES, stream>>>(maps, part, R, a_cols, b_cols, tr, n_mt, n_nt, kb_per, ld);
     return cudaGetLastError();
 }
 

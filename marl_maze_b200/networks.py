@@ -87,6 +87,9 @@ class Actor(nn.Module):
                 xin = x.new_zeros(uniq.shape[0], OBS_SPACE)
                 xin[:, :uniq.shape[1]] = uniq
                 emb = self.attention(self.projection(xin))
+                if uniq.shape[0] <= 8 and x.is_cuda and x.dtype == torch.float32:  # backward = one streaming segment-sum kernel (update.GatherRows)
+                    from .update import GatherRows
+                    return GatherRows.apply(emb, inv)
                 if uniq.shape[0] <= 64:  # gather as a one-hot matmul: its backward is a dense [U,B]x[B,460] GEMM instead of a scatter-add
                     return torch.nn.functional.one_hot(inv, uniq.shape[0]).to(emb.dtype) @ emb  # into a handful of rows (atomics contention)
                 return emb.index_select(0, inv)

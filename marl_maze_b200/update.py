@@ -27,16 +27,37 @@ def wgrad(dz: torch.Tensor, h: torch.Tensor):
     k_in = h.shape[1]
     assert h.shape[0] == R
     L = _abi.lib()
-    tot = None
+    tot = tr = None
     for r0 in range(0, R, WGRAD_MAX_ROWS):
         r = min(WGRAD_MAX_ROWS, R - r0)
-        slabs, ld = C.c_int32(), C.c_int32()
-        _abi.check(L.mm_wgrad_geometry(r, n_out, k_in, C.byref(slabs), C.byref(ld)), "mm_wgrad_geometry")
-        part = torch.empty(slabs.value, n_out, ld.value, device=dz.device, dtype=torch.float32)
+        slabs, ld, out_rows, transposed = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _abi.check(L.mm_wgrad_geometry(r, n_out, k_in, C.byref(slabs), C.byref(ld), C.byref(out_rows), C.byref(transposed)), "mm_wgrad_geometry")
+        part = torch.empty(slabs.value, out_rows.value, ld.value, device=dz.device, dtype=torch.float32)
         _abi.check(L.mm_wgrad_tf32x3(_ptr(dz[r0:r0 + r]), _ptr(h[r0:r0 + r]), r, n_out, k_in, _ptr(part), _stream(dz)), "mm_wgrad_tf32x3")
         t = part.sum(0)
-        tot = t if tot is None else tot + t
+        tot, tr = (t if tot is None else tot + t), transposed.value  # the orientation depends on (n_out, k_in) only
+    if tr:  # [k_in + 1][ld]: rows = input columns (+ the bias row), columns = output units
+        return tot[:k_in, :n_out].t().contiguous(), tot[k_in, :n_out]
     return tot[:, :k_in], tot[:, k_in]
+
+
+class GatherRows(torch.autograd.Function):
+    """src[inv] for a handful (<= 8) of distinct source rows; the backward is mm_segment_sum instead of a scatter-add into those rows."""
+
+    @staticmethod
+    def forward(ctx, src, inv):
+        ctx.save_for_backward(inv)
+        ctx.n = src.shape[0]
+        return src.index_select(0, inv)
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv,) = ctx.saved_tensors
+        g = g.contiguous()
+        L = _abi.lib()
+        part = torch.empty(L.mm_segment_sum_blocks(g.shape[0]), ctx.n, g.shape[1], device=g.device, dtype=torch.float32)
+        _abi.check(L.mm_segment_sum(_ptr(g), _ptr(inv), g.shape[0], g.shape[1], ctx.n, _ptr(part), _stream(g)), "mm_segment_sum")
+        return part.sum(0), None
 
 
 MM_LINEAR_RELU, MM_LINEAR_GATE, MM_LINEAR_PLAIN = 0, 2, 3

@@ -220,3 +220,17 @@ def test_fused_actor_loss_matches_reference_golden(seed):
         worst = max(worst, err)
         assert err < 2e-5, (name, err)
     print("worst relative gradient error vs the reference", worst)
+
+
+@pytest.mark.parametrize("rows,n_seg", [(1, 1), (1000, 4), (200001, 8)])
+def test_gather_rows_backward_is_segment_sum(rows, n_seg):
+    from marl_maze_b200.update import GatherRows
+    g = torch.Generator(device="cuda"); g.manual_seed(rows)
+    src = torch.randn(n_seg, 460, device="cuda", generator=g, requires_grad=True)
+    inv = torch.randint(0, n_seg, (rows,), device="cuda", generator=g)
+    up = torch.randn(rows, 460, device="cuda", generator=g)
+    out = GatherRows.apply(src, inv)
+    assert torch.equal(out, src.detach()[inv])
+    out.backward(up)
+    ref = torch.zeros(n_seg, 460, device="cuda", dtype=torch.float64).index_add_(0, inv, up.double())
+    assert _rel(src.grad, ref) < 2e-6
