@@ -164,6 +164,7 @@ int mm_policy_forward(const float *weights, const float *obs, const uint8_t *mas
  * (counter = step index baked in, counter_dev bumped by mm_counter_add at the end of the graph) draws fresh numbers on every replay. */
 int mm_counter_add(uint64_t *counter_dev, uint64_t v, void *stream);
 #define MM_POLICY_TCGEN05 1 /* flags: trunk GEMMs as error-compensated 3xTF32 tcgen05.mma (TMA + TMEM); 0 = fp32 SIMT tiles */
+#define MM_POLICY_OVERLAP_CRITIC 2 /* flags: run the critic on an internal side stream forked from / joined to `stream` (capturable) */
 
 /*
  * K5 -- building blocks of the PPO actor update (PPO.py:58-85: loss.backward() through Actor.layers), SURVEY 8(f).1.

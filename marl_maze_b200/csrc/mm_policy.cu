@@ -275,7 +275,7 @@ int policy_offsets_host(int32_t* out) {
 cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
                              const float* head_b, const HeadArgs* heads, cudaStream_t stream);
 
-// flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles
+// flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles; bit 1: critic on a forked side stream
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
                           uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter,
                           int flags, const uint64_t* counter_dev, cudaStream_t stream) {
@@ -288,6 +288,25 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
     float* x0 = scratch;                      // [R,460]
     float* h1 = scratch + (size_t)R * kX0;    // [R,264]
     float* h2 = h1 + (size_t)R * kHid;        // [R,264]
+    // flags bit 1: the critic only reads obs, so it runs on a side stream forked from / joined to `stream` by events (legal inside a
+    // stream capture, where it becomes a parallel branch of the graph) and overlaps the actor's token + trunk kernels.  The stream and
+    // the two events are created once per host thread, on the first (eager) call.
+    static thread_local cudaStream_t side = nullptr;
+    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    const bool overlap = value && (flags & 2);
+    if (overlap) {
+        if (!side) {
+            cudaError_t e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaEventRecord(ev_fork, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev_fork, 0);
+        if (e != cudaSuccess) return e;
+        k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, side>>>(obs, wts, value, E);
+        if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
+    }
     k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
     if (flags & 1) {
         cudaError_t e;
@@ -302,7 +321,10 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         k_linear_relu<<<grid, 256, 0, stream>>>(h2, wts + o.l2_w, wts + o.l2_b, h1, R, kHid, kHid);
         k_heads<<<(E * 32 + 127) / 128, 128, 0, stream>>>(h1, wts, ha);
     }
-    if (value) k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
+    if (overlap) {
+        cudaError_t e = cudaStreamWaitEvent(stream, ev_join, 0);
+        if (e != cudaSuccess) return e;
+    } else if (value) k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
     return cudaGetLastError();
 }
 

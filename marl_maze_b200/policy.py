@@ -72,7 +72,7 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
 
 
 class PolicyRunner:
-    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0, tensor_cores: bool = True):
+    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0, tensor_cores: bool = True, overlap_critic: bool = True):
         self.lib = _abi.lib()
         self.E, self.device, self.env_offset, self.seed = int(num_envs), torch.device(device), int(env_offset), int(seed) & (2**64 - 1)
         self.actor, self.critic = actor, critic
@@ -81,7 +81,7 @@ class PolicyRunner:
         self.counter = 0
         self.counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)  # added to `counter` on the device (CUDA-graph replays)
         self.launches = 0
-        self.flags = 1 if tensor_cores else 0  # MM_POLICY_TCGEN05
+        self.flags = (1 if tensor_cores else 0) | (2 if overlap_critic else 0)  # MM_POLICY_TCGEN05 | MM_POLICY_OVERLAP_CRITIC
 
     def refresh(self):
         """Re-pack after an optimiser step -- in place, so that captured CUDA graphs keep pointing at live weights."""

@@ -4,10 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from marl_maze_b200.networks import Actor, Critic
 from marl_maze_b200.policy import PolicyRunner
-ap = argparse.ArgumentParser(); ap.add_argument("--envs", type=int, default=65536); ap.add_argument("--simt", action="store_true"); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--envs", type=int, default=65536); ap.add_argument("--simt", action="store_true"); ap.add_argument("--no-overlap", action="store_true"); a = ap.parse_args()
 E = a.envs
 actor = Actor([264, 264, 264]).cuda(); critic = Critic(2, hidden_sizes=[64, 64]).cuda()
-run = PolicyRunner(actor, critic, E, "cuda", tensor_cores=not a.simt)
+run = PolicyRunner(actor, critic, E, "cuda", tensor_cores=not a.simt, overlap_critic=not a.no_overlap)
 obs = torch.rand(E, 2, 65, device="cuda"); masks = torch.ones(E, 2, 6, dtype=torch.uint8, device="cuda")
 for _ in range(5): run.forward(obs, masks)
 torch.cuda.synchronize()
