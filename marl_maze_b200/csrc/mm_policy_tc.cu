@@ -23,8 +23,11 @@ namespace mm {
 #ifndef MM_TC_BK
 #define MM_TC_BK 32
 #endif
+#ifndef MM_TC_A_TMEM
+#define MM_TC_A_TMEM 1
+#endif
 #ifndef MM_TC_STAGES
-#define MM_TC_STAGES 2
+#define MM_TC_STAGES (MM_TC_A_TMEM ? 3 : 2)
 #endif
 constexpr int TC_BM = 128, TC_BK = MM_TC_BK, TC_N1 = 144, TC_N2 = 128, TC_N = 264, TC_STAGES = MM_TC_STAGES;
 constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                       // one K-block row: 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
@@ -33,8 +36,21 @@ constexpr uint64_t TC_LAYOUT = TC_BK == 32 ? 2ull : 4ull;          // cute::UMMA
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
 constexpr uint32_t TC_B1_BYTES = TC_N1 * TC_BK * 4;   // 18432
 constexpr uint32_t TC_B2_BYTES = TC_N2 * TC_BK * 4;   // 16384
-constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * (TC_B1_BYTES + TC_B2_BYTES);  // 102400
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr uint32_t TC_W_BYTES = 2 * (TC_B1_BYTES + TC_B2_BYTES);   // 69632: [W1 hi | W2 hi | W1 lo | W2 lo]
+#if MM_TC_A_TMEM
+// TMEM-operand build: the pipeline ring holds WEIGHT tiles only (3 stages); the activation tile passes through a single 16 KB slot of its
+// own -- the splitter frees it as soon as it has read its rows, long before the MMAs of that k-block run -- and through a 3-stage ring of
+// [hi 32 | lo 32] TMEM columns.
+constexpr uint32_t TC_W_OFF = 0, TC_STAGE_BYTES = TC_W_BYTES;
+constexpr uint32_t TC_A_SLOT_OFF = TC_STAGES * TC_STAGE_BYTES;
+constexpr uint32_t TC_RING_BYTES = TC_A_SLOT_OFF + TC_A_BYTES;
+static_assert(TC_STAGES <= 3, "TMEM columns 288 + 64 * stages must stay below 512");
+#else
+constexpr uint32_t TC_W_OFF = 2 * TC_A_BYTES, TC_STAGE_BYTES = 2 * TC_A_BYTES + TC_W_BYTES;  // [A hi | A lo | weights] per stage: 102400
+constexpr uint32_t TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;
+#endif
+constexpr uint32_t TC_SMEM_BYTES = TC_RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static_assert(TC_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 #ifndef MM_TC_SPLIT_WARPS
 #define MM_TC_SPLIT_WARPS 8   // splitter / epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, i.e. two per scheduler)
 #endif
@@ -46,9 +62,6 @@ constexpr int TC_THREADS = 64 + 32 * TC_SPLIT_WARPS;
 // scheme issues three of them per k-step on top of the TMA writes and the splitter's own traffic: the SS kernel is shared-memory-bandwidth
 // bound at ~42 % tensor activity.  With A in TMEM the splitter reads each landed fp32 row once and writes hi / lo with tcgen05.st, and the
 // MMAs read only the weight tiles from shared memory.
-#ifndef MM_TC_A_TMEM
-#define MM_TC_A_TMEM 1
-#endif
 static_assert(!MM_TC_A_TMEM || MM_TC_BK == 32, "the TMEM-A splitter addresses the 128-byte swizzle");
 constexpr uint32_t TC_TMEM_A_COL = 288;  // D occupies columns 0..271; A stages: [hi 32 | lo 32] per pipeline stage from column 288
 constexpr uint32_t TC_TMEM_COLS = 512;
@@ -78,11 +91,13 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     constexpr bool kHeads = kMode == TC_EPI_HEADS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* split_done = empty + TC_STAGES;
     uint64_t* tmem_full = split_done + TC_STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* a_full = tmem_full + 1;   // TMEM-operand build: the activation slot has landed / has been read by every splitter thread
+    uint64_t* a_free = a_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
@@ -91,6 +106,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split_done[s], 32 * TC_SPLIT_WARPS); }
         mbar_init(tmem_full, 1);
+        mbar_init(a_full, 1); mbar_init(a_free, 32 * TC_SPLIT_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -106,15 +122,23 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         if (lane == 0) {  // ===== TMA producer
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % TC_STAGES;
-                mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
-                uint8_t* st = smem + s * TC_STAGE_BYTES;
-                mbar_expect_tx(&full[s], TC_STAGE_BYTES - TC_A_BYTES);  // the A_lo slot is produced in-kernel
                 const int k0 = kb * TC_BK;
+                uint8_t* st = smem + s * TC_STAGE_BYTES;
+#if MM_TC_A_TMEM
+                mbar_wait(a_free, (kb & 1) ^ 1);              // the splitter has read the previous activation tile out of the slot
+                mbar_expect_tx(a_full, TC_A_BYTES);
+                tma_load_2d(smem + TC_A_SLOT_OFF, &maps.a, k0, m0, a_full);
+                mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], TC_W_BYTES);
+#else
+                mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], TC_STAGE_BYTES - TC_A_BYTES);  // the A_lo slot is produced in-kernel
                 tma_load_2d(st, &maps.a, k0, m0, &full[s]);
-                tma_load_2d(st + 2 * TC_A_BYTES, &maps.w1_hi, k0, 0, &full[s]);
-                tma_load_2d(st + 2 * TC_A_BYTES + TC_B1_BYTES, &maps.w2_hi, k0, TC_N1, &full[s]);
-                tma_load_2d(st + 2 * TC_A_BYTES + TC_B1_BYTES + TC_B2_BYTES, &maps.w1_lo, k0, 0, &full[s]);
-                tma_load_2d(st + 2 * TC_A_BYTES + 2 * TC_B1_BYTES + TC_B2_BYTES, &maps.w2_lo, k0, TC_N1, &full[s]);
+#endif
+                tma_load_2d(st + TC_W_OFF, &maps.w1_hi, k0, 0, &full[s]);
+                tma_load_2d(st + TC_W_OFF + TC_B1_BYTES, &maps.w2_hi, k0, TC_N1, &full[s]);
+                tma_load_2d(st + TC_W_OFF + TC_B1_BYTES + TC_B2_BYTES, &maps.w1_lo, k0, 0, &full[s]);
+                tma_load_2d(st + TC_W_OFF + 2 * TC_B1_BYTES + TC_B2_BYTES, &maps.w2_lo, k0, TC_N1, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -126,9 +150,11 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 mbar_wait(&split_done[s], (kb / TC_STAGES) & 1);  // A tile rewritten as hi, lo tile written (fenced to the async proxy)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
+#if !MM_TC_A_TMEM
                 const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TC_A_BYTES);
-                const uint64_t b1_hi = umma_desc(st + 2 * TC_A_BYTES), b2_hi = umma_desc(st + 2 * TC_A_BYTES + TC_B1_BYTES);
-                const uint64_t b1_lo = umma_desc(st + 2 * TC_A_BYTES + TC_B1_BYTES + TC_B2_BYTES), b2_lo = umma_desc(st + 2 * TC_A_BYTES + 2 * TC_B1_BYTES + TC_B2_BYTES);
+#endif
+                const uint64_t b1_hi = umma_desc(st + TC_W_OFF), b2_hi = umma_desc(st + TC_W_OFF + TC_B1_BYTES);
+                const uint64_t b1_lo = umma_desc(st + TC_W_OFF + TC_B1_BYTES + TC_B2_BYTES), b2_lo = umma_desc(st + TC_W_OFF + 2 * TC_B1_BYTES + TC_B2_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the 128-byte swizzle row
                     const uint64_t o = (uint64_t)(k * 2);
@@ -166,44 +192,41 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         }
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % TC_STAGES;
-            mbar_wait(&full[s], (kb / TC_STAGES) & 1);
 #if MM_TC_A_TMEM
-            // thread = row (its TMEM lane): logical 16-byte chunk c of row r sits at physical chunk c ^ (r & 7) of the 128-byte swizzled row
+            // thread = row (its TMEM lane): logical 16-byte chunk c of row r sits at physical chunk c ^ (r & 7) of the 128-byte swizzled row.
+            // With 8 warps the two warps of a quarter take k-columns 0..15 and 16..31 of the row.
+            constexpr int kCh = TC_SPLIT_WARPS == 4 ? 8 : 4;          // 16-byte chunks per thread
             const int arow = (warp & 3) * 32 + lane;
-            const float4* rowp = reinterpret_cast<const float4*>(smem + s * TC_STAGE_BYTES + arow * 128);
-            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TC_TMEM_A_COL + (uint32_t)(s * 64);
-            if (TC_SPLIT_WARPS == 4) {
-                uint32_t hi[32], lo[32];
+            const float4* rowp = reinterpret_cast<const float4*>(smem + TC_A_SLOT_OFF + arow * 128);
+            mbar_wait(a_full, kb & 1);                                // this k-block's activation tile is in the slot
+            float4 av[kCh];
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const float4 v = rowp[c ^ (arow & 7)];
-                    const float e[4] = {v.x, v.y, v.z, v.w};
+            for (int c = 0; c < kCh; c++) av[c] = rowp[(c + (TC_SPLIT_WARPS == 8 ? 4 * whalf : 0)) ^ (arow & 7)];
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_free)) : "memory");  // slot read: the next tile may land
+            uint32_t hi[4 * kCh], lo[4 * kCh];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        hi[4 * c + j] = tf32_rn_bits(e[j]);
-                        lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
-                    }
+            for (int c = 0; c < kCh; c++) {
+                const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    hi[4 * c + j] = tf32_rn_bits(e[j]);
+                    lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
                 }
+            }
+            mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);         // TMEM A stage s is free: the MMAs of k-block kb - TC_STAGES have completed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TC_TMEM_A_COL + (uint32_t)(s * 64);
+            if constexpr (TC_SPLIT_WARPS == 4) {
                 tmem_st_32x32(ta, hi);
                 tmem_st_32x32(ta + 32, lo);
-            } else {  // the two warps of a quarter take k-columns 0..15 and 16..31 of the row
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const float4 v = rowp[(c + 4 * whalf) ^ (arow & 7)];
-                    const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        hi[4 * c + j] = tf32_rn_bits(e[j]);
-                        lo[4 * c + j] = tf32_rn_bits(e[j] - __uint_as_float(hi[4 * c + j]));
-                    }
-                }
+            } else {
                 tmem_st_32x16(ta + 16 * whalf, hi);
                 tmem_st_32x16(ta + 32 + 16 * whalf, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #else
+            mbar_wait(&full[s], (kb / TC_STAGES) & 1);
             float4* raw = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
             float4* lo_t = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_A_BYTES);
 #pragma unroll
