@@ -73,8 +73,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 struct TcMaps {
-    CUtensorMap a, w1_hi, w2_hi, w1_lo, w2_lo;
+    CUtensorMap a, w1_hi, w2_hi, w1_lo, w2_lo, y;
 };
+// MM_TC_TMA_STORE: the epilogue hands each 32 x 32 block of the result to the TMA (cp.async.bulk.tensor shared -> global) instead of
+// storing it with the LSU: the warp moves on to its next block at once, the tensor map clips rows >= M and columns >= n_valid, and the
+// burst of 148 CTAs x 135 KB leaves asynchronously.
+#ifndef MM_TC_TMA_STORE
+#define MM_TC_TMA_STORE 1
+#endif
 
 // Epilogue modes.  TC_EPI_RELU: y = relu(acc + bias).  TC_EPI_HEADS: this is the last trunk layer -- instead of storing y, the epilogue
 // contracts each row with the 6 head rows (5 move logits + 1 mark logit), masks, samples (or evaluates) the action and writes actions +
@@ -251,7 +257,13 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
         // half-written sectors per instruction (measured: half of the kernel's time).  Each warp therefore transposes 32x32 blocks
         // through shared memory -- the pipeline stages are free once tmem_full has fired -- and writes whole 128-byte row segments.
         constexpr int kTP = 36;  // padded row pitch (floats): 16-byte aligned, conflict-free for the quarter-warp float4 patterns below
+#if MM_TC_TMA_STORE
+        // two 4 KB blocks per warp in the TMA's 128-byte swizzle (row r, 16-byte chunk q at r*128 + ((q ^ (r&7)) << 4): conflict-free writes)
+        uint8_t* t_blk = smem + (size_t)(warp - 2) * 8192;
+        float* t_y = nullptr; (void)t_y;
+#else
         float* t_y = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * kTP;
+#endif
         const int row0 = m0 + quarter * 32;
         float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int c_lo = (TC_SPLIT_WARPS == 8 && whalf) ? 5 : 0, c_hi = (TC_SPLIT_WARPS == 8 && !whalf) ? 5 : 9;  // a quarter's two warps share the chunks
@@ -291,11 +303,26 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                         }
                     }
                 } else {
+#if MM_TC_TMA_STORE
+                    *reinterpret_cast<float4*>(t_blk + ((c - c_lo) & 1) * 4096 + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+#else
                     *reinterpret_cast<float4*>(&t_y[lane * kTP + 4 * q]) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+#endif
                 }
             }
             if (kHeads) continue;
             if (kMode == TC_EPI_RELU && gate_out && row0 + lane < M) gate_out[(size_t)(row0 + lane) * 9 + c] = word;
+#if MM_TC_TMA_STORE
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's block writes -> visible to the TMA
+            __syncwarp();
+            if (lane == 0) {
+                if (row0 < M && c * 32 < n_valid) tma_store_2d(&maps.y, t_blk + ((c - c_lo) & 1) * 4096, c * 32, row0);
+                tma_store_commit();
+                tma_store_wait_read<1>();  // the block written two iterations from now is the one whose store was committed before this one
+            }
+            __syncwarp();
+            continue;
+#endif
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; it++) {  // 4 rows x 128 contiguous bytes per instruction
@@ -308,8 +335,11 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
             }
             __syncwarp();
         }
+#if MM_TC_TMA_STORE
+        if (!kHeads && lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the TMA's reads
+#endif
         if (kHeads && TC_SPLIT_WARPS == 8) {  // add the partner warp's partial head dot products (same rows, the other column chunks)
-            float* xch = reinterpret_cast<float*>(smem) + (size_t)TC_SPLIT_WARPS * 32 * kTP + (size_t)(quarter * 32 + lane) * 6;
+            float* xch = reinterpret_cast<float*>(smem + (size_t)TC_SPLIT_WARPS * 8192) + (size_t)(quarter * 32 + lane) * 6;
             if (whalf) {
 #pragma unroll
                 for (int j = 0; j < 6; j++) xch[j] = hacc[j];
@@ -342,6 +372,17 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// fp32 row-major [rows][cols] with row pitch ld floats, {32 cols x 32 rows} box, 128-byte swizzle: the epilogue's store map
+static bool make_store_map(CUtensorMap* m, float* base, int rows, int cols, int ld) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // fp32 row-major [rows][cols] with a {32 cols x box_rows} box, 128-byte swizzle, zero fill out of bounds
 static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int box_rows) {
     PFN_encodeTiled enc = get_encode();
@@ -362,13 +403,13 @@ cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* 
                                 const uint32_t* gate, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream) {
     // The rollout calls this with the same scratch / weight pointers every step: keep the encoded maps (a tensor map depends only on
     // base pointer, extents and box) in a small per-thread cache instead of re-encoding 15 of them per policy step.
-    struct Entry { const float *x, *wh, *wl; int M, K, nw; TcMaps maps; };
+    struct Entry { const float *x, *wh, *wl, *y; int M, K, nw, ldy; TcMaps maps; };
     static thread_local Entry cache[8];
     static thread_local int next_slot = 0;
     if (n_rows_w <= 0 || n_rows_w > TC_N || (n_rows_w & 3) || (ldy & 3) || (K & 3)) return cudaErrorInvalidValue;
     const TcMaps* found = nullptr;
     for (int i = 0; i < 8; i++)
-        if (cache[i].x == x && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].M == M && cache[i].K == K && cache[i].nw == n_rows_w) { found = &cache[i].maps; break; }
+        if (cache[i].x == x && cache[i].wh == w_hi && cache[i].wl == w_lo && cache[i].y == y && cache[i].ldy == ldy && cache[i].M == M && cache[i].K == K && cache[i].nw == n_rows_w) { found = &cache[i].maps; break; }
     if (!found) {
         Entry& e = cache[next_slot];
         next_slot = (next_slot + 1) % 8;
@@ -376,7 +417,8 @@ cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* 
         if (!make_map(&e.maps.a, x, M, K, TC_BM) || !make_map(&e.maps.w1_hi, w_hi, n_rows_w, K, TC_N1) || !make_map(&e.maps.w2_hi, w_hi, n_rows_w, K, TC_N2) ||
             !make_map(&e.maps.w1_lo, w_lo, n_rows_w, K, TC_N1) || !make_map(&e.maps.w2_lo, w_lo, n_rows_w, K, TC_N2))
             return cudaErrorInvalidValue;
-        e.x = x; e.wh = w_hi; e.wl = w_lo; e.M = M; e.K = K; e.nw = n_rows_w;
+        if (y && !make_store_map(&e.maps.y, y, M, n_rows_w, ldy)) return cudaErrorInvalidValue;
+        e.x = x; e.wh = w_hi; e.wl = w_lo; e.y = y; e.ldy = ldy; e.M = M; e.K = K; e.nw = n_rows_w;
         found = &e.maps;
     }
     const TcMaps& maps = *found;
