@@ -15,10 +15,13 @@
 
 namespace mm {
 
+#ifndef MM_UL_MINBLOCKS
+#define MM_UL_MINBLOCKS 3
+#endif
 constexpr int UL_HID = 264, UL_CPL = 9 /* columns per lane, the 9th only for lanes 0-7 */, UL_WARPS = 4;
 constexpr int UL_PART_LD = 6 * UL_HID + 8;  // dWh [6][264], dbh [6], loss, unused
 
-__global__ void __launch_bounds__(UL_WARPS * 32, 3) k_ppo_heads_loss(const PpoLossArgs a) {
+__global__ void __launch_bounds__(UL_WARPS * 32, MM_UL_MINBLOCKS) k_ppo_heads_loss(const PpoLossArgs a) {
     __shared__ float s_w[6][UL_HID];
     __shared__ float s_acc[6 * UL_HID + 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(UL_WARPS * 32, 3) k_ppo_heads_loss(const PpoLo
     for (int i = threadIdx.x; i < UL_PART_LD; i += blockDim.x) a.part[(size_t)blockIdx.x * UL_PART_LD + i] = s_acc[i];
 }
 
-int ppo_loss_blocks() { return 3 * 148; }
+int ppo_loss_blocks() { return MM_UL_MINBLOCKS * 148; }
 int ppo_loss_part_ld() { return UL_PART_LD; }
 
 cudaError_t launch_ppo_heads_loss(const PpoLossArgs& a, cudaStream_t stream) {

@@ -63,6 +63,24 @@ class m_Attention(nn.Module):
         return (tok + torch.bmm(torch.softmax(scores, -1), self.values(tok))).reshape(-1, FEATURE_AMOUNT * EMBEDDING_DIM)
 
 
+def _few_distinct_rows(p, max_rows: int = 8):
+    """(rows [U, d], inverse [B]) with rows[inverse] == p, like torch.unique(p, dim=0, return_inverse=True) but without its
+    lexicographic sort when there are at most `max_rows` distinct rows (environment observations have 4 distinct facing prefixes):
+    `max_rows` rounds of "take the first row not yet matched, mark every row equal to it" -- 8 streaming passes over [B, d] and ONE
+    host synchronisation.  Unused slots repeat row 0 (harmless: nothing maps to them); more distinct rows fall back to torch.unique."""
+    p = p.contiguous()
+    inv = torch.full((p.shape[0],), -1, dtype=torch.int64, device=p.device)
+    reps = []
+    for u in range(max_rows):
+        rem = inv < 0
+        rep = p[torch.argmax(rem.to(torch.uint8))]          # first unmatched row (row 0 once everything is matched)
+        inv = torch.where(rem & (p == rep).all(1), u, inv)
+        reps.append(rep)
+    if bool((inv < 0).any()):
+        return torch.unique(p, dim=0, return_inverse=True)
+    return torch.stack(reps), inv
+
+
 class Actor(nn.Module):
     """obs [B,65] -> (move logits [B,5], mark logit [B,1]); hidden_sizes excludes the 460-wide input (networks.py:15)."""
 
@@ -82,7 +100,7 @@ class Actor(nn.Module):
         agree on those four columns have identical embeddings: large batches are evaluated once per DISTINCT prefix and gathered
         (same values, same gradients -- index_select's backward accumulates -- at a fraction of the batched-attention cost)."""
         if self.projection.faithful and x.shape[0] >= 4096:
-            uniq, inv = torch.unique(x[:, :max(FEATURE_DIMS)], dim=0, return_inverse=True)
+            uniq, inv = _few_distinct_rows(x[:, :max(FEATURE_DIMS)])
             if uniq.shape[0] * 8 <= x.shape[0]:
                 xin = x.new_zeros(uniq.shape[0], OBS_SPACE)
                 xin[:, :uniq.shape[1]] = uniq
