@@ -95,23 +95,30 @@ class Actor(nn.Module):
         self.mark_head = nn.Linear(widths[-1], 1)
         self.initialize_weights()
 
-    def embed(self, x):
-        """Projection + attention -> [B, 460].  With the faithful projection every token reads obs[:, 0:4] only, so rows that
-        agree on those four columns have identical embeddings: large batches are evaluated once per DISTINCT prefix and gathered
-        (same values, same gradients -- index_select's backward accumulates -- at a fraction of the batched-attention cost)."""
+    def embed_parts(self, x):
+        """Projection + attention as (rows [U, 460], inverse [B] or None): the embedding of observation b is rows[inverse[b]] (rows itself
+        when inverse is None).  With the faithful projection every token reads obs[:, 0:4] only, so rows that agree on those four columns
+        have identical embeddings: large batches are evaluated once per DISTINCT prefix (same values, same gradients, at a fraction of the
+        batched-attention cost)."""
         if self.projection.faithful and x.shape[0] >= 4096:
             uniq, inv = _few_distinct_rows(x[:, :max(FEATURE_DIMS)])
             if uniq.shape[0] * 8 <= x.shape[0]:
                 xin = x.new_zeros(uniq.shape[0], OBS_SPACE)
                 xin[:, :uniq.shape[1]] = uniq
-                emb = self.attention(self.projection(xin))
-                if uniq.shape[0] <= 8 and x.is_cuda and x.dtype == torch.float32:  # backward = one streaming segment-sum kernel (update.GatherRows)
-                    from .update import GatherRows
-                    return GatherRows.apply(emb, inv)
-                if uniq.shape[0] <= 64:  # gather as a one-hot matmul: its backward is a dense [U,B]x[B,460] GEMM instead of a scatter-add
-                    return torch.nn.functional.one_hot(inv, uniq.shape[0]).to(emb.dtype) @ emb  # into a handful of rows (atomics contention)
-                return emb.index_select(0, inv)
-        return self.attention(self.projection(x))
+                return self.attention(self.projection(xin)), inv
+        return self.attention(self.projection(x)), None
+
+    def embed(self, x):
+        """Projection + attention -> [B, 460] (embed_parts, gathered)."""
+        emb, inv = self.embed_parts(x)
+        if inv is None:
+            return emb
+        if emb.shape[0] <= 8 and x.is_cuda and x.dtype == torch.float32:  # backward = one streaming segment-sum kernel (update.GatherRows)
+            from .update import GatherRows
+            return GatherRows.apply(emb, inv)
+        if emb.shape[0] <= 64:  # gather as a one-hot matmul: its backward is a dense [U,B]x[B,460] GEMM instead of a scatter-add
+            return torch.nn.functional.one_hot(inv, emb.shape[0]).to(emb.dtype) @ emb  # into a handful of rows (atomics contention)
+        return emb.index_select(0, inv)
 
     def trunk(self, x):
         dev = self.move_head.weight.device

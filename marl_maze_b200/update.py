@@ -41,6 +41,15 @@ def wgrad(dz: torch.Tensor, h: torch.Tensor):
     return tot[:, :k_in], tot[:, k_in]
 
 
+def segment_sum(x: torch.Tensor, seg: torch.Tensor, n_seg: int) -> torch.Tensor:
+    """out[s] = sum of the rows r of x with seg[r] == s (n_seg <= 8; mm_segment_sum)."""
+    x = x.contiguous()
+    L = _abi.lib()
+    part = torch.empty(L.mm_segment_sum_blocks(x.shape[0]), n_seg, x.shape[1], device=x.device, dtype=torch.float32)
+    _abi.check(L.mm_segment_sum(_ptr(x), _ptr(seg), x.shape[0], x.shape[1], n_seg, _ptr(part), _stream(x)), "mm_segment_sum")
+    return part.sum(0)
+
+
 class GatherRows(torch.autograd.Function):
     """src[inv] for a handful (<= 8) of distinct source rows; the backward is mm_segment_sum instead of a scatter-add into those rows."""
 
@@ -53,11 +62,7 @@ class GatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (inv,) = ctx.saved_tensors
-        g = g.contiguous()
-        L = _abi.lib()
-        part = torch.empty(L.mm_segment_sum_blocks(g.shape[0]), ctx.n, g.shape[1], device=g.device, dtype=torch.float32)
-        _abi.check(L.mm_segment_sum(_ptr(g), _ptr(inv), g.shape[0], g.shape[1], ctx.n, _ptr(part), _stream(g)), "mm_segment_sum")
-        return part.sum(0), None
+        return segment_sum(g, inv, ctx.n), None
 
 
 MM_LINEAR_RELU, MM_LINEAR_GATE, MM_LINEAR_PLAIN = 0, 2, 3
@@ -131,8 +136,10 @@ class _ActorTrunkLoss(torch.autograd.Function):
     forward() (no activation outlives the call) and backward() only scales the stored gradients."""
 
     @staticmethod
-    def forward(ctx, x0, w0, b0, w1, b1, w2, b2, wh, bh, sp, masks, actions, old_logp, adv, clip, scale):
-        x0 = x0.detach().contiguous()
+    def forward(ctx, x0, inv, w0, b0, w1, b1, w2, b2, wh, bh, sp, masks, actions, old_logp, adv, clip, scale):
+        """x0 [2E,460], inv None -- or x0 = the few DISTINCT embedding rows [U<=8,460] and inv [2E] the row of each agent (Actor.embed_parts)."""
+        src = x0.detach().contiguous()
+        x0 = src if inv is None else src.index_select(0, inv)
         h0, bits0 = linear_tc(x0, sp["fwd"][0], MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
         h1, bits1 = linear_tc(h0, sp["fwd"][1], MM_LINEAR_RELU, bias=b1.detach().contiguous(), want_bits=True)
         h2 = linear_tc(h1, sp["fwd"][2], MM_LINEAR_RELU, bias=b2.detach().contiguous())
@@ -146,11 +153,17 @@ class _ActorTrunkLoss(torch.autograd.Function):
         del dz1, h0
         dw0, db0 = wgrad(dz0, x0)
         dx0 = None
-        if ctx.needs_input_grad[0]:  # the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
-            dx0 = torch.empty_like(x0)
-            for i, blk in enumerate(sp["t0"]):
-                linear_tc(dz0, blk, MM_LINEAR_PLAIN, out=dx0, col0=264 * i)
-        ctx.grads = (dx0, dw0, db0, dw1, db1, dw2, db2, dwh, dbh)
+        if ctx.needs_input_grad[0]:
+            if inv is not None:
+                # the gather's backward is a segment sum over agent rows, and a segment sum commutes with the right-multiplication by W0:
+                # d loss / d src = segsum(dZ0 W0) = segsum(dZ0) W0 -- one streaming pass over [2E,264] and a [U,264]x[264,460] product
+                # instead of the 460-wide data-gradient GEMM and a pass over its [2E,460] result
+                dx0 = segment_sum(dz0, inv, src.shape[0]) @ w0.detach()
+            else:  # the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
+                dx0 = torch.empty_like(x0)
+                for i, blk in enumerate(sp["t0"]):
+                    linear_tc(dz0, blk, MM_LINEAR_PLAIN, out=dx0, col0=264 * i)
+        ctx.grads = (dx0, None, dw0, db0, dw1, db1, dw2, db2, dwh, dbh)
         ctx.mark_non_differentiable(logp)
         return loss, logp
 
@@ -173,11 +186,13 @@ def fused_available(actor) -> bool:
 def actor_loss(actor, obs2, masks2, actions2, old_logp, adv, clip, scale):
     """scale * sum_e -min(ratio_e A_e, clip(ratio_e) A_e) over E envs, and the new joint log-probs [E] (no grad).
     obs2 [2E,65] f32 (agent rows 2e, 2e+1), masks2 [2E,6] bool/u8, actions2 [2E,2] (move, mark) any integer/float dtype."""
-    x0 = actor.embed(obs2)
+    x0, inv = actor.embed_parts(obs2)
+    if inv is not None and x0.shape[0] > 8:   # too many distinct rows for mm_segment_sum: materialise the gather in autograd
+        x0, inv = actor.embed(obs2), None
     ls = actor.layers
     wh = torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)
     bh = torch.cat([actor.move_head.bias, actor.mark_head.bias], 0)
     masks = masks2.contiguous().view(torch.uint8) if masks2.dtype == torch.bool else masks2.to(torch.uint8).contiguous()
     actions = actions2.to(torch.uint8).contiguous()
-    return _ActorTrunkLoss.apply(x0, ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, wh, bh, trunk_splits(actor), masks,
+    return _ActorTrunkLoss.apply(x0, inv, ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, wh, bh, trunk_splits(actor), masks,
                                  actions, old_logp, adv, float(clip), float(scale))

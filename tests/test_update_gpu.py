@@ -162,19 +162,24 @@ def test_fused_actor_loss_gradients_match_autograd(faithful):
         old = (loss_ref(ref_actor, torch.float64, None) + 0.3 * torch.randn(E, device="cuda", generator=g).double()).float()
     ref_loss = loss_ref(ref_actor, torch.float64, old); ref_loss.backward()
     loss_ref(a32, torch.float32, old).backward()
-    embed = actor.embed
+    parts = actor.embed_parts
 
-    def embed_kept(x):
-        out = embed(x)
-        out.retain_grad(); kept["fused"] = out
-        return out
+    def parts_kept(x):
+        emb, inv = parts(x)
+        emb.retain_grad(); kept["fused"] = (emb, inv)
+        return emb, inv
 
-    actor.embed = embed_kept
+    actor.embed_parts = parts_kept
     loss, logp = actor_loss(actor, obs, masks, actions, old, adv, 0.2, 1.0 / E)
     loss.backward()
     assert abs(float(loss.detach()) - float(ref_loss.detach())) < 2e-5 * max(1.0, abs(float(ref_loss.detach())))
-    # the gradient handed back to autograd at the embedding output (element-wise, against the largest element)
-    r_dx0, r32_dx0 = _rel(kept["fused"].grad, kept[torch.float64].grad), _rel(kept[torch.float32].grad, kept[torch.float64].grad)
+    # the gradient handed back to autograd at the embedding output (element-wise, against the largest element): per agent row, or -- when the
+    # embedding was evaluated once per distinct observation prefix -- summed over the rows that share an embedding row
+    emb, inv = kept["fused"]
+    assert (inv is not None) == faithful
+    want = {dt: kept[dt].grad if inv is None else torch.zeros(emb.shape[0], 460, device="cuda", dtype=dt).index_add_(0, inv, kept[dt].grad)
+            for dt in (torch.float64, torch.float32)}
+    r_dx0, r32_dx0 = _rel(emb.grad, want[torch.float64]), _rel(want[torch.float32], want[torch.float64])
     assert r_dx0 < max(2e-5, 4 * r32_dx0), (r_dx0, r32_dx0)
     worst = 0.0
     for (name, p), (_, q), (_, t) in zip(actor.named_parameters(), ref_actor.named_parameters(), a32.named_parameters()):
