@@ -235,42 +235,44 @@ class PPO:
         index_list = torch.randperm(N, device=self.device, generator=g)
         used = min(self.batch_size, N)
         mb = max(1, self.mbatch_size if self.batch_size <= N else N // 5)
+        # The reference shuffles ONCE per train iteration and walks the same minibatches in every update epoch (PPO.py:48-55): gather the
+        # used part of the rollout into that order once, and every minibatch / micro-batch below is a contiguous view.
+        sel = index_list[:used]
+        p_obs, p_act, p_masks, p_logp, p_adv, p_rtg = (t.index_select(0, sel) for t in (b_obs, b_actions, b_masks, b_log_probs, b_advs, b_rtgs))
         stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0)
+        a_sum = torch.zeros((), device=self.device); c_sum = torch.zeros((), device=self.device)   # summed on the device: no sync per micro-batch
         fused = self.fused_update and _upd.fused_available(self.actor)
         for _ in range(self.updates_per_batch):
             self.decay_lr()
             for start in range(0, used, mb):
-                idx = index_list[start:start + mb]
-                n = idx.numel()
+                n = min(mb, used - start)
                 self.actor_optim.zero_grad(set_to_none=True)
-                a_loss = 0.0
-                for s0 in range(0, n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
-                    j = idx[s0:s0 + self.micro_batch]
-                    m_obs, m_act, m_masks = b_obs[j], b_actions[j], b_masks[j]
-                    adv = b_advs[j]
+                for s0 in range(start, start + n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
+                    s1 = min(s0 + self.micro_batch, start + n)
+                    m_obs, m_act, m_masks, adv = p_obs[s0:s1], p_act[s0:s1], p_masks[s0:s1], p_adv[s0:s1]
                     if fused:  # K5: trunk + heads + clipped surrogate, forward and backward, in hand-written kernels (update.py)
                         loss, _ = _upd.actor_loss(self.actor, m_obs.reshape(-1, m_obs.shape[-1]), m_masks.reshape(-1, 6), m_act.reshape(-1, 2),
-                                                  b_log_probs[j], adv, self.clip, 1.0 / n)
+                                                  p_logp[s0:s1], adv, self.clip, 1.0 / n)
                     else:
                         cur = self.joint_log_probs(m_obs, m_act, m_masks)
-                        ratio = torch.exp(cur - b_log_probs[j])
+                        ratio = torch.exp(cur - p_logp[s0:s1])
                         loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
                     loss.backward()
-                    a_loss += float(loss.detach())
+                    a_sum += loss.detach()
                 self._allreduce_grads(self.actor)
                 torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
                 self.actor_optim.step()
                 self.critic_optim.zero_grad(set_to_none=True)
-                c_loss = 0.0
-                for s0 in range(0, n, self.micro_batch):
-                    j = idx[s0:s0 + self.micro_batch]
-                    loss = ((self.get_state_values(b_obs[j]) - b_rtgs[j]) ** 2).sum() / n
+                for s0 in range(start, start + n, self.micro_batch):
+                    s1 = min(s0 + self.micro_batch, start + n)
+                    loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
                     loss.backward()
-                    c_loss += float(loss.detach())
+                    c_sum += loss.detach()
                 self._allreduce_grads(self.critic)
                 torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad)
                 self.critic_optim.step()
-                stats["actor_loss"] += a_loss; stats["critic_loss"] += c_loss; stats["steps"] += 1
+                stats["steps"] += 1
+        stats["actor_loss"], stats["critic_loss"] = float(a_sum), float(c_sum)
         return stats
 
     def train(self):

@@ -170,8 +170,9 @@ class _ActorTrunkLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _g_logp):
         grads, ctx.grads = ctx.grads, None
-        if float(g) != 1.0:  # loss.backward() arrives with 1: do not spend a pass over the [2E,460] dX0 on multiplying by it
-            grads = tuple(None if t is None else g * t for t in grads)
+        # g is 1 for loss.backward(); reading it would cost a device synchronisation per micro-batch, so scale instead -- in place for a
+        # full [2E,460] dX0 (one pass, no second buffer), out of place for the small tensors
+        grads = tuple(None if t is None else (t.mul_(g) if t.numel() > (1 << 22) else g * t) for t in grads)
         return grads + (None,) * 7
 
 
