@@ -15,7 +15,8 @@ critic, grad-norm clip 0.5, two Adams, lr x0.997 per update -- with gradients av
 torch.distributed is initialised and advantage statistics taken over all ranks.  The actor's trunk, heads and loss run
 forward AND backward in hand-written kernels (K5, update.py: tcgen05 3xTF32 GEMMs for the forward, data-gradient and
 weight-gradient passes); the 23-token embedding in front of it and the small critic stay PyTorch autograd
-(`fused_update=False` puts the whole update back on autograd).
+(`fused_update=False` puts the whole update back on autograd).  The shuffled rollout is gathered once per update and
+the minibatches are views of it (the reference, too, shuffles once and reuses the order in every epoch).
 """
 from __future__ import annotations
 
