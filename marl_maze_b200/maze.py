@@ -55,14 +55,27 @@ class Maze:
             self.refill_pool()
         return self.engine
 
+    def _pool_args(self):
+        # maze ids are global and never reused: (generation, global env slot) -> results do not depend on how envs are sharded
+        id_base = (self._generation * (1 << 26) + self.env_offset * self.pool_episodes) & 0xFFFFFFFF
+        return dict(side_range=self.side_range, rand_start=self.rand_start, difficulty=self.difficulty, id_base=id_base, id_mod=self.num_envs,
+                    id_mul=self.pool_episodes)
+
+    def prefetch_pool(self):
+        """Start generating the NEXT pool (the one the next refill_pool() would build) on a side stream, into staging buffers."""
+        if self.engine is None or getattr(self, "_staged", None) == (id(self.engine), self._generation):
+            return
+        self.engine.generate_staged(self.seed, **self._pool_args())
+        self._staged = (id(self.engine), self._generation)
+
     def refill_pool(self):
         """Generate a fresh pool (K1).  Only between episodes of ALL envs: a live episode reads its maze's exit field from the pool."""
         eng = self.engine
-        total = eng.P
-        # maze ids are global and never reused: (generation, global env slot) -> results do not depend on how envs are sharded
-        id_base = (self._generation * (1 << 26) + self.env_offset * self.pool_episodes) & 0xFFFFFFFF
-        eng.generate(self.seed, side_range=self.side_range, rand_start=self.rand_start, difficulty=self.difficulty, id_base=id_base,
-                     id_mod=self.num_envs, id_mul=self.pool_episodes)
+        if getattr(self, "_staged", None) == (id(eng), self._generation):
+            eng.commit_staged()       # built ahead by prefetch_pool(): same ids, same mazes
+        else:
+            eng.generate(self.seed, **self._pool_args())
+        self._staged = None
         eng.env_episode.zero_()
         self._generation += 1
         self._resets_since_fill = 0

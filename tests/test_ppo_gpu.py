@@ -135,6 +135,24 @@ def test_cuda_graph_rollout_equals_eager_rollout(tmp_path):
     assert not torch.equal(outs[True][1][1], outs[True][2][1])  # different rollouts draw different actions
 
 
+def test_prefetched_pool_equals_inline_generation(tmp_path):
+    """get_batch starts carving the NEXT rollout's mazes on a side stream (Maze.prefetch_pool) and the next refill copies them in; the
+    rollouts must be exactly those of generating the pool inline."""
+    outs = {}
+    for mode in (False, True):
+        brain, agents, maze = _make(128, tmp_path / f"p{int(mode)}", batch_size=128 * 24 - 2, horizon=24, prefetch_pool=mode)
+        res = []
+        for _ in range(3):
+            b = brain.get_batch()
+            res.append([b[0].clone(), b[1].clone(), b[2].clone(), b[5].clone(), b[6].clone(), b[7].clone(), maze.engine.pool_hdr.clone()])
+        outs[mode] = res
+        assert (getattr(maze, "_staged", None) is not None) == mode
+    for r_a, r_b in zip(outs[False], outs[True]):
+        for x, y in zip(r_a, r_b):
+            assert torch.equal(x, y)
+    assert not torch.equal(outs[True][0][6], outs[True][1][6])  # every rollout runs on new mazes
+
+
 @pytest.mark.parametrize("faithful", [True, False], ids=["column0_projection", "indexed_projection"])
 def test_fused_update_tracks_autograd_update(tmp_path, faithful):
     """PPO.update with the K5 kernels (fused_update=True, default) against the same schedule on PyTorch autograd: same rollout, same
