@@ -11,6 +11,10 @@ cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, i
                             uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, cudaStream_t stream);
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
                           int, const uint64_t*, cudaStream_t);
+cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream);
+cudaError_t launch_tokens_bwd(const float* wts, const float* obs, const float* dout, int R, float* dy40, float* part, cudaStream_t stream);
+size_t tokens_bwd_scratch_floats(int R);
+int tokens_bwd_blocks();
 cudaError_t launch_add_u64(unsigned long long* p, unsigned long long v, cudaStream_t stream);
 int policy_offsets_host(int32_t* out);
 cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatches, cudaStream_t stream);
@@ -209,6 +213,17 @@ int mm_segment_sum_blocks(int rows) { return rows > 0 ? segment_sum_blocks(rows)
 int mm_segment_sum(const float* x, const int64_t* seg, int rows, int cols, int n_seg, float* part, void* stream) {
     if (!x || !seg || !part || rows <= 0 || cols <= 0 || (cols & 3) || n_seg < 1 || n_seg > 8 || ((uintptr_t)x & 15) || ((uintptr_t)part & 15)) return MM_ERR_BAD_ARG;
     return cuda_status(launch_segment_sum(x, (const long long*)seg, rows, cols, n_seg, part, (cudaStream_t)stream));
+}
+
+int mm_tokens_forward(const float* weights, const float* obs, int rows, float* x0, void* stream) {
+    if (!weights || !obs || !x0 || rows <= 0 || ((uintptr_t)x0 & 15)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_tokens_fwd(weights, obs, rows, x0, (cudaStream_t)stream));
+}
+int mm_tokens_backward_blocks(void) { return tokens_bwd_blocks(); }
+size_t mm_sizeof_tokens_backward_scratch(int rows) { return rows > 0 ? tokens_bwd_scratch_floats(rows) * sizeof(float) : 0; }
+int mm_tokens_backward(const float* weights, const float* obs, const float* d_x0, int rows, void* scratch, float* part, void* stream) {
+    if (!weights || !obs || !d_x0 || !scratch || !part || rows <= 0 || ((uintptr_t)d_x0 & 15) || ((uintptr_t)scratch & 15)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_tokens_bwd(weights, obs, d_x0, rows, (float*)scratch, part, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -138,6 +138,221 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_MINBLOCKS) k_tokens(con
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tokens + attention, backward
+// d loss / d (per-token affine maps) from d loss / d x0 (K5: the embedding's backward for the general -- indexed -- projection, where every
+// agent row has its own 23 tokens).  Same mapping as k_tokens: one warp per row, one lane per token, keys / queries / values of the row
+// exchanged through a per-warp shared tile.  With y_a = M_a x_a + b_a = (token, key, query, value) of token a (60 outputs of <= 4 inputs):
+//     out_a = token_a + sum_b P[a][b] value_b,  P = softmax_b(query_a . key_b / sqrt(10))            (networks.py:75-82)
+//     d token_a = dO_a;   dP[a][b] = dO_a . value_b;   d value_b = sum_a P[a][b] dO_a
+//     dS[a][b] = P[a][b] (dP[a][b] - sum_b' P[a][b'] dP[a][b']) / sqrt(10);   d query_a = sum_b dS[a][b] key_b;   d key_b = sum_a dS[a][b] query_a
+// Lane a owns row a of P / dS (as the query) and, after a transposing pass through shared memory, column a (as key / value).  The map
+// gradients dM_a[j][c] = sum_rows dy_a[j] x_a[c], db_a[j] = sum_rows dy_a[j] are a reduction over ALL rows of 300 values per token: the
+// row kernel writes dy (key, query, value parts: [R][23][40]; the token part is dO itself) and k_tokens_bwd_reduce sums the outer
+// products with one thread per (token, 4 outputs) and 20 register accumulators (shared-memory atomics in the row kernel -- a CAS loop
+// per float -- made it 11x the forward).  The host adds the block partials and back-propagates through the folding
+// [I; Wk; Wq; Wv] (P_a, b_a) with autograd.
+constexpr int kTbWarps = 4;
+constexpr int kTbTile = kTok * (12 + 12 + kEmb + kEmb + 24 + 24);                                  // per-warp floats: k, q, v, dO, P, dS
+constexpr int kTbSmem = (60 * kTok * 4 + 60 * kTok + kTbWarps * kTbTile) * (int)sizeof(float);
+__global__ void __launch_bounds__(kTbWarps * 32, 2) k_tokens_bwd(const float* __restrict__ obs, const float* __restrict__ wts, const float* __restrict__ dout,
+                                                                 float* __restrict__ dy40, int R) {
+    const PolicyOffsets o = policy_offsets();
+    extern __shared__ __align__(16) float tb_smem[];
+    float (*s_m)[kTok][4] = reinterpret_cast<float (*)[kTok][4]>(tb_smem);
+    float (*s_b)[kTok] = reinterpret_cast<float (*)[kTok]>(tb_smem + 60 * kTok * 4);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tb_smem + 60 * kTok * 5 + w * kTbTile;
+    float (*s_k)[12] = reinterpret_cast<float (*)[12]>(tile);
+    float (*s_q)[12] = reinterpret_cast<float (*)[12]>(tile + kTok * 12);
+    float (*s_v)[kEmb] = reinterpret_cast<float (*)[kEmb]>(tile + kTok * 24);
+    float (*s_do)[kEmb] = reinterpret_cast<float (*)[kEmb]>(tile + kTok * (24 + kEmb));
+    float (*s_p)[24] = reinterpret_cast<float (*)[24]>(tile + kTok * (24 + 2 * kEmb));
+    float (*s_ds)[24] = reinterpret_cast<float (*)[24]>(tile + kTok * (48 + 2 * kEmb));
+    for (int i = threadIdx.x; i < 60 * kTok * 4; i += blockDim.x) (&s_m[0][0][0])[i] = wts[o.tokm + i];
+    for (int i = threadIdx.x; i < 60 * kTok; i += blockDim.x) (&s_b[0][0])[i] = wts[o.tokb + i];
+    __syncthreads();
+    const bool on = lane < kTok;
+    const int a = on ? lane : 0;
+    const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
+#pragma unroll 1
+    for (int row = blockIdx.x * kTbWarps + w; row < R; row += gridDim.x * kTbWarps) {
+        float x[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) x[c] = (c < nd) ? obs[(size_t)row * kObs + c0 + c] : 0.f;
+        auto affine = [&](int j) {
+            const float4 m = *reinterpret_cast<const float4*>(&s_m[j][a][0]);
+            return fmaf(x[3], m.w, fmaf(x[2], m.z, fmaf(x[1], m.y, fmaf(x[0], m.x, s_b[j][a]))));
+        };
+        float q[kKQ], dO[kEmb];
+        {
+            const float4* gp = reinterpret_cast<const float4*>(dout + (size_t)row * kX0 + a * kEmb);
+#pragma unroll
+            for (int d4 = 0; d4 < kEmb / 4; d4++) {
+                const float4 g = on ? __ldg(gp + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dO[4 * d4] = g.x; dO[4 * d4 + 1] = g.y; dO[4 * d4 + 2] = g.z; dO[4 * d4 + 3] = g.w;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < kKQ; d++) q[d] = affine(30 + d);
+        if (on) {
+#pragma unroll
+            for (int d = 0; d < kKQ; d++) { s_k[a][d] = affine(20 + d); s_q[a][d] = q[d]; }
+#pragma unroll
+            for (int d4 = 0; d4 < kEmb / 4; d4++) {
+                *reinterpret_cast<float4*>(&s_v[a][4 * d4]) = make_float4(affine(40 + 4 * d4), affine(41 + 4 * d4), affine(42 + 4 * d4), affine(43 + 4 * d4));
+                *reinterpret_cast<float4*>(&s_do[a][4 * d4]) = make_float4(dO[4 * d4], dO[4 * d4 + 1], dO[4 * d4 + 2], dO[4 * d4 + 3]);
+            }
+        }
+        __syncwarp();
+        // ---- row a of P, dP, dS; d query_a
+        float p[kTok], m = -INFINITY;
+#pragma unroll
+        for (int b = 0; b < kTok; b++) {
+            const float4 k0 = *reinterpret_cast<const float4*>(&s_k[b][0]), k1 = *reinterpret_cast<const float4*>(&s_k[b][4]);
+            const float2 k2 = *reinterpret_cast<const float2*>(&s_k[b][8]);
+            float acc = q[0] * k0.x;
+            acc = fmaf(q[1], k0.y, acc); acc = fmaf(q[2], k0.z, acc); acc = fmaf(q[3], k0.w, acc);
+            acc = fmaf(q[4], k1.x, acc); acc = fmaf(q[5], k1.y, acc); acc = fmaf(q[6], k1.z, acc); acc = fmaf(q[7], k1.w, acc);
+            acc = fmaf(q[8], k2.x, acc); acc = fmaf(q[9], k2.y, acc);
+            p[b] = acc * 0.31622776601683794f;
+            m = fmaxf(m, p[b]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int b = 0; b < kTok; b++) { p[b] = expf(p[b] - m); sum += p[b]; }
+        const float inv = 1.f / sum;
+        float dot = 0.f, ds[kTok];
+#pragma unroll
+        for (int b = 0; b < kTok; b++) {
+            p[b] *= inv;
+            float dp = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < kEmb / 4; d4++) {
+                const float4 vv = *reinterpret_cast<const float4*>(&s_v[b][4 * d4]);
+                dp = fmaf(dO[4 * d4], vv.x, dp); dp = fmaf(dO[4 * d4 + 1], vv.y, dp); dp = fmaf(dO[4 * d4 + 2], vv.z, dp); dp = fmaf(dO[4 * d4 + 3], vv.w, dp);
+            }
+            ds[b] = dp;
+            dot = fmaf(p[b], dp, dot);
+        }
+        float* dyr = dy40 + ((size_t)row * kTok + a) * 40;  // this token's (d key 10 | d query 10 | d value 20)
+        float dy_q[kKQ];
+#pragma unroll
+        for (int d = 0; d < kKQ; d++) dy_q[d] = 0.f;
+#pragma unroll
+        for (int b = 0; b < kTok; b++) {
+            ds[b] = p[b] * (ds[b] - dot) * 0.31622776601683794f;
+            const float4 k0 = *reinterpret_cast<const float4*>(&s_k[b][0]), k1 = *reinterpret_cast<const float4*>(&s_k[b][4]);
+            const float2 k2 = *reinterpret_cast<const float2*>(&s_k[b][8]);
+            dy_q[0] = fmaf(ds[b], k0.x, dy_q[0]); dy_q[1] = fmaf(ds[b], k0.y, dy_q[1]); dy_q[2] = fmaf(ds[b], k0.z, dy_q[2]); dy_q[3] = fmaf(ds[b], k0.w, dy_q[3]);
+            dy_q[4] = fmaf(ds[b], k1.x, dy_q[4]); dy_q[5] = fmaf(ds[b], k1.y, dy_q[5]); dy_q[6] = fmaf(ds[b], k1.z, dy_q[6]); dy_q[7] = fmaf(ds[b], k1.w, dy_q[7]);
+            dy_q[8] = fmaf(ds[b], k2.x, dy_q[8]); dy_q[9] = fmaf(ds[b], k2.y, dy_q[9]);
+            if (on) { s_p[a][b] = p[b]; s_ds[a][b] = ds[b]; }
+        }
+        if (on) {
+#pragma unroll
+            for (int d = 0; d < kKQ; d += 2) *reinterpret_cast<float2*>(dyr + 10 + d) = make_float2(dy_q[d], dy_q[d + 1]);
+        }
+        __syncwarp();
+        // ---- column a of dS and P: d key_a, then d value_a
+        {
+            float dy_k[kKQ];
+#pragma unroll
+            for (int d = 0; d < kKQ; d++) dy_k[d] = 0.f;
+#pragma unroll 1
+            for (int t = 0; t < kTok; t++) {  // t = the query token
+                const float dst = s_ds[t][a];
+                const float4 q0 = *reinterpret_cast<const float4*>(&s_q[t][0]), q1 = *reinterpret_cast<const float4*>(&s_q[t][4]);
+                const float2 q2 = *reinterpret_cast<const float2*>(&s_q[t][8]);
+                dy_k[0] = fmaf(dst, q0.x, dy_k[0]); dy_k[1] = fmaf(dst, q0.y, dy_k[1]); dy_k[2] = fmaf(dst, q0.z, dy_k[2]); dy_k[3] = fmaf(dst, q0.w, dy_k[3]);
+                dy_k[4] = fmaf(dst, q1.x, dy_k[4]); dy_k[5] = fmaf(dst, q1.y, dy_k[5]); dy_k[6] = fmaf(dst, q1.z, dy_k[6]); dy_k[7] = fmaf(dst, q1.w, dy_k[7]);
+                dy_k[8] = fmaf(dst, q2.x, dy_k[8]); dy_k[9] = fmaf(dst, q2.y, dy_k[9]);
+            }
+            if (on) {
+#pragma unroll
+                for (int d = 0; d < kKQ; d += 2) *reinterpret_cast<float2*>(dyr + d) = make_float2(dy_k[d], dy_k[d + 1]);
+            }
+        }
+        {
+            float dy_v[kEmb];
+#pragma unroll
+            for (int d = 0; d < kEmb; d++) dy_v[d] = 0.f;
+#pragma unroll 1
+            for (int t = 0; t < kTok; t++) {
+                const float pt = s_p[t][a];
+#pragma unroll
+                for (int d4 = 0; d4 < kEmb / 4; d4++) {
+                    const float4 g = *reinterpret_cast<const float4*>(&s_do[t][4 * d4]);
+                    dy_v[4 * d4] = fmaf(pt, g.x, dy_v[4 * d4]); dy_v[4 * d4 + 1] = fmaf(pt, g.y, dy_v[4 * d4 + 1]);
+                    dy_v[4 * d4 + 2] = fmaf(pt, g.z, dy_v[4 * d4 + 2]); dy_v[4 * d4 + 3] = fmaf(pt, g.w, dy_v[4 * d4 + 3]);
+                }
+            }
+            if (on) {
+#pragma unroll
+                for (int d4 = 0; d4 < kEmb / 4; d4++) *reinterpret_cast<float4*>(dyr + 20 + 4 * d4) = make_float4(dy_v[4 * d4], dy_v[4 * d4 + 1], dy_v[4 * d4 + 2], dy_v[4 * d4 + 3]);
+            }
+        }
+        __syncwarp();  // the row's tiles are reused by the next row of this warp
+    }
+}
+
+// part[block][j][a][0..3] = sum over the block's rows of dy_a[j] x_a[c], part[block][j][a][4] = sum of dy_a[j]; thread = (token a, 4 outputs):
+// groups 0-4 are the token part (dy = dO, read from dout), groups 5-14 the key | query | value parts (dy40).
+constexpr int kTrThreads = kTok * 15;  // 345
+__global__ void __launch_bounds__(kTrThreads) k_tokens_bwd_reduce(const float* __restrict__ obs, const float* __restrict__ wts, const float* __restrict__ dout,
+                                                                  const float* __restrict__ dy40, float* __restrict__ part, int R, int rows_per_block) {
+    const PolicyOffsets o = policy_offsets();
+    const int a = threadIdx.x / 15, g4 = threadIdx.x % 15;
+    const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+    float acc[4][5];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[i][c] = 0.f;
+    const bool tok = g4 < 5;
+    const size_t off = tok ? (size_t)a * kEmb + 4 * g4 : (size_t)a * 40 + 4 * (g4 - 5);
+    const size_t pitch = tok ? (size_t)kX0 : (size_t)kTok * 40;
+    const float* src = tok ? dout : dy40;
+#pragma unroll 4
+    for (int r = r0; r < r1; r++) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * pitch + off));
+        float x[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) x[c] = (c < nd) ? __ldg(obs + (size_t)r * kObs + c0 + c) : 0.f;
+        const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][c] = fmaf(dv[i], x[c], acc[i][c]);
+            acc[i][4] += dv[i];
+        }
+    }
+    const int j0 = tok ? 4 * g4 : 20 + 4 * (g4 - 5);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) part[(((size_t)blockIdx.x * 60 + j0 + i) * kTok + a) * 5 + c] = acc[i][c];
+}
+
+int tokens_bwd_blocks() { return 148 * 4; }
+size_t tokens_bwd_scratch_floats(int R) { return (size_t)R * kTok * 40; }
+cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
+    k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
+    return cudaGetLastError();
+}
+cudaError_t launch_tokens_bwd(const float* wts, const float* obs, const float* dout, int R, float* dy40, float* part, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tokens_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_tokens_bwd<<<min((R + kTbWarps - 1) / kTbWarps, 148 * 6), kTbWarps * 32, kTbSmem, stream>>>(obs, wts, dout, dy40, R);
+    const int blocks = tokens_bwd_blocks();
+    k_tokens_bwd_reduce<<<blocks, kTrThreads, 0, stream>>>(obs, wts, dout, dy40, part, R, (R + blocks - 1) / blocks);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ Y = relu(X W^T + b)
 // 128x64 output tile per block, 256 threads, 8x4 outputs per thread, K in slabs of 16 through shared memory.
 constexpr int BM = 128, BN = 64, BK = 16;

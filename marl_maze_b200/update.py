@@ -65,6 +65,65 @@ class GatherRows(torch.autograd.Function):
         return segment_sum(g, inv, ctx.n), None
 
 
+def token_maps(actor):
+    """The per-token affine maps the token kernels evaluate, as a DIFFERENTIABLE function of the embedding parameters:
+    [token; key; query; value]_a = [I; Wk; Wq; Wv] (P_a x_a + b_a)  ->  tokm [60,23,4], tokb [60,23]   (policy.pack_weights, csrc/mm_policy.cu)."""
+    import torch.nn.functional as F
+    from .networks import EMBEDDING_DIM
+    layers = actor.projection.layers
+    pw = torch.stack([F.pad(l.weight, (0, 4 - l.weight.shape[1])) for l in layers], 0)                     # [23,20,4]
+    pb = torch.stack([l.bias for l in layers], 0)                                                          # [23,20]
+    att = actor.attention
+    stack = torch.cat([torch.eye(EMBEDDING_DIM, device=pw.device, dtype=pw.dtype), att.keys.weight, att.querys.weight, att.values.weight], 0)  # [60,20]
+    return torch.einsum("jd,adc->jac", stack, pw).contiguous(), (stack @ pb.t()).contiguous()
+
+
+class TokenEmbed(torch.autograd.Function):
+    """Projection + attention of every row by the token kernels: forward = K4's k_tokens, backward = k_tokens_bwd (gradients at the
+    per-token maps; autograd carries them on to the parameters through token_maps)."""
+
+    @staticmethod
+    def forward(ctx, obs, tokm, tokb, faithful):
+        from .networks import FEATURE_DIMS
+        from .policy import offsets
+        o = offsets()
+        obs = obs.contiguous()
+        buf = torch.zeros(o["total"], dtype=torch.float32, device=obs.device)   # K4 buffer layout; the token kernels read these four blocks only
+        buf[o["tokm"]:o["tokm"] + tokm.numel()] = tokm.detach().reshape(-1)
+        buf[o["tokb"]:o["tokb"] + tokb.numel()] = tokb.detach().reshape(-1)
+        cols = [0 if faithful else sum(FEATURE_DIMS[:i]) for i in range(len(FEATURE_DIMS))]
+        buf[o["proj_col"]:o["proj_col"] + len(cols)] = torch.tensor(cols, dtype=torch.float32, device=obs.device)
+        buf[o["proj_dim"]:o["proj_dim"] + len(cols)] = torch.tensor(FEATURE_DIMS, dtype=torch.float32, device=obs.device)
+        x0 = torch.empty(obs.shape[0], 460, device=obs.device, dtype=torch.float32)
+        _abi.check(_abi.lib().mm_tokens_forward(_ptr(buf), _ptr(obs), obs.shape[0], _ptr(x0), _stream(obs)), "mm_tokens_forward")
+        ctx.save_for_backward(obs, buf)
+        return x0
+
+    @staticmethod
+    def backward(ctx, g):
+        obs, buf = ctx.saved_tensors
+        L = _abi.lib()
+        g = g.contiguous()
+        tot = None
+        for r0 in range(0, obs.shape[0], TOKENS_BWD_MAX_ROWS):   # bounds the per-row scratch (3680 B per row)
+            r = min(TOKENS_BWD_MAX_ROWS, obs.shape[0] - r0)
+            scratch = torch.empty(int(L.mm_sizeof_tokens_backward_scratch(r)), dtype=torch.uint8, device=g.device)
+            part = torch.empty(L.mm_tokens_backward_blocks(), 60, 23, 5, device=g.device, dtype=torch.float32)
+            _abi.check(L.mm_tokens_backward(_ptr(buf), _ptr(obs[r0:r0 + r]), _ptr(g[r0:r0 + r]), r, _ptr(scratch), _ptr(part), _stream(g)), "mm_tokens_backward")
+            t = part.sum(0)
+            tot = t if tot is None else tot + t
+        return None, tot[..., :4].contiguous(), tot[..., 4].contiguous(), None
+
+
+TOKENS_BWD_MAX_ROWS = 1 << 20
+
+
+def token_embed(actor, obs2):
+    """[B,460] embedding of obs2 [B,65] through the token kernels (any projection mode, no de-duplication)."""
+    tokm, tokb = token_maps(actor)
+    return TokenEmbed.apply(obs2, tokm, tokb, bool(actor.projection.faithful))
+
+
 MM_LINEAR_RELU, MM_LINEAR_GATE, MM_LINEAR_PLAIN = 0, 2, 3
 
 
@@ -187,9 +246,9 @@ def fused_available(actor) -> bool:
 def actor_loss(actor, obs2, masks2, actions2, old_logp, adv, clip, scale):
     """scale * sum_e -min(ratio_e A_e, clip(ratio_e) A_e) over E envs, and the new joint log-probs [E] (no grad).
     obs2 [2E,65] f32 (agent rows 2e, 2e+1), masks2 [2E,6] bool/u8, actions2 [2E,2] (move, mark) any integer/float dtype."""
-    x0, inv = actor.embed_parts(obs2)
-    if inv is not None and x0.shape[0] > 8:   # too many distinct rows for mm_segment_sum: materialise the gather in autograd
-        x0, inv = actor.embed(obs2), None
+    x0, inv = (actor.embed_parts(obs2) if actor.projection.faithful and obs2.shape[0] >= 4096 else (None, None))
+    if inv is None or x0.shape[0] > 8:   # no (or too little) duplication among the rows: every row through the token kernels
+        x0, inv = token_embed(actor, obs2), None
     ls = actor.layers
     wh = torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)
     bh = torch.cat([actor.move_head.bias, actor.mark_head.bias], 0)

@@ -138,7 +138,8 @@ def test_fused_actor_loss_gradients_match_autograd(faithful):
     # large as the gradient element itself.  Take it out of the comparison: every reference below uses the fused forward's own gates.
     from marl_maze_b200.update import linear_tc, tf32_split, MM_LINEAR_RELU
     with torch.no_grad():
-        hf, gates = actor.embed(obs).contiguous(), []
+        from marl_maze_b200.update import token_embed
+        hf, gates = (actor.embed(obs) if faithful else token_embed(actor, obs)).contiguous(), []   # the embedding path actor_loss takes
         for lin in actor.layers:
             hf = linear_tc(hf, tf32_split(lin.weight), MM_LINEAR_RELU, bias=lin.bias.detach().contiguous())
             gates.append(hf > 0)
@@ -175,12 +176,15 @@ def test_fused_actor_loss_gradients_match_autograd(faithful):
     assert abs(float(loss.detach()) - float(ref_loss.detach())) < 2e-5 * max(1.0, abs(float(ref_loss.detach())))
     # the gradient handed back to autograd at the embedding output (element-wise, against the largest element): per agent row, or -- when the
     # embedding was evaluated once per distinct observation prefix -- summed over the rows that share an embedding row
-    emb, inv = kept["fused"]
-    assert (inv is not None) == faithful
-    want = {dt: kept[dt].grad if inv is None else torch.zeros(emb.shape[0], 460, device="cuda", dtype=dt).index_add_(0, inv, kept[dt].grad)
-            for dt in (torch.float64, torch.float32)}
-    r_dx0, r32_dx0 = _rel(emb.grad, want[torch.float64]), _rel(want[torch.float32], want[torch.float64])
-    assert r_dx0 < max(2e-5, 4 * r32_dx0), (r_dx0, r32_dx0)
+    r_dx0 = r32_dx0 = float("nan")
+    if faithful:   # (the indexed mode embeds every row with the token kernels: their gradients are checked below, parameter by parameter)
+        emb, inv = kept["fused"]
+        assert inv is not None
+        want = {dt: torch.zeros(emb.shape[0], 460, device="cuda", dtype=dt).index_add_(0, inv, kept[dt].grad) for dt in (torch.float64, torch.float32)}
+        r_dx0, r32_dx0 = _rel(emb.grad, want[torch.float64]), _rel(want[torch.float32], want[torch.float64])
+        assert r_dx0 < max(2e-5, 4 * r32_dx0), (r_dx0, r32_dx0)
+    else:
+        assert "fused" not in kept
     worst = 0.0
     for (name, p), (_, q), (_, t) in zip(actor.named_parameters(), ref_actor.named_parameters(), a32.named_parameters()):
         if q.grad is None or float(q.grad.abs().max()) == 0.0:
@@ -239,3 +243,32 @@ def test_gather_rows_backward_is_segment_sum(rows, n_seg):
     out.backward(up)
     ref = torch.zeros(n_seg, 460, device="cuda", dtype=torch.float64).index_add_(0, inv, up.double())
     assert _rel(src.grad, ref) < 2e-6
+
+
+@pytest.mark.parametrize("faithful", [True, False], ids=["column0_projection", "indexed_projection"])
+def test_token_embed_forward_and_backward_match_autograd(faithful):
+    """update.token_embed (k_tokens / k_tokens_bwd + the differentiable folding of the parameters into per-token maps) against
+    Projection + m_Attention under torch autograd in fp64: values and every embedding parameter gradient."""
+    import copy
+    from marl_maze_b200.networks import Actor
+    from marl_maze_b200.update import token_embed
+    torch.manual_seed(31)
+    actor = Actor([264, 264, 264], faithful_projection=faithful).cuda()
+    ref = copy.deepcopy(actor).double()
+    g = torch.Generator(device="cuda"); g.manual_seed(32)
+    B = 3001
+    obs = torch.rand(B, 65, device="cuda", generator=g) * 2 - 0.5
+    up = torch.randn(B, 460, device="cuda", generator=g)
+    x0 = token_embed(actor, obs)
+    want = ref.attention(ref.projection(obs.double()))
+    assert _rel(x0, want) < 2e-6
+    x0.backward(up); want.backward(up.double())
+    worst = 0.0
+    for (name, p), (_, q) in zip(actor.named_parameters(), ref.named_parameters()):
+        if not name.startswith(("projection", "attention")):
+            assert p.grad is None, name
+            continue
+        r = _rel(p.grad, q.grad)
+        worst = max(worst, r)
+        assert r < 2e-5, (name, r)
+    print("worst embedding gradient error", worst)
