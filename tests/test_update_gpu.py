@@ -7,7 +7,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _rel(a, b):
-    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
 @pytest.mark.parametrize("R,k_in", [(32, 264), (1000, 264), (4096 + 17, 460), (70000, 264), (70000, 460)])
