@@ -182,8 +182,8 @@ int mm_wgrad_tf32x3(const float *dz, const float *h, int rows, int n_out, int k_
 /*
  * mm_linear_tf32x3: the trunk GEMM of K4 as a stand-alone call, y = epi(x W^T) with x [rows][k] f32 and W [n_rows_w <= 264][k] given as
  * its TF32 split (w_hi = tf32(W), w_lo = tf32(W - w_hi), both round-to-nearest).  Forward of a layer: mode MM_LINEAR_RELU, W = the
- * layer's weight, y = relu(. + bias) (Actor.forward, networks.py:36-38); gate_bits_out (may be NULL; needs n_rows_w == 264) receives the
- * ReLU pattern as [rows][9] u32, bit b of word c = y[row][32c+b] > 0.  Data gradient of a layer: W = the layer's weight TRANSPOSED,
+ * layer's weight, y = relu(. + bias) (Actor.forward, networks.py:36-38; Critic.forward, networks.py:96-102); gate_bits_out (may be NULL)
+ * receives the ReLU pattern as [rows][9] u32, bit b of word c = y[row][32c+b] > 0 (zero beyond column n_rows_w).  Data gradient of a layer: W = the layer's weight TRANSPOSED,
  * x = dZ, mode MM_LINEAR_GATE (y = acc where the bit of gate_bits -- the pattern of the ReLU below -- is set, else 0) or MM_LINEAR_PLAIN
  * (y = acc).  n_rows_w columns are written with row pitch ldy (floats), so a wider result (the 460-wide dX of layer 0) is made of column
  * blocks.

@@ -14,8 +14,8 @@ The update (PPO.py:46-85) keeps the reference's schedule -- clipped surrogate on
 critic, grad-norm clip 0.5, two Adams, lr x0.997 per update -- with gradients averaged over ranks (NCCL) when
 torch.distributed is initialised and advantage statistics taken over all ranks.  The actor's trunk, heads and loss run
 forward AND backward in hand-written kernels (K5, update.py: tcgen05 3xTF32 GEMMs for the forward, data-gradient and
-weight-gradient passes); the 23-token embedding in front of it and the small critic stay PyTorch autograd
-(`fused_update=False` puts the whole update back on autograd).  The shuffled rollout is gathered once per update and
+weight-gradient passes), so do the critic's hidden layers and -- when rows do not share their embedding -- the 23-token
+embedding (`fused_update=False` puts the whole update back on autograd).  The shuffled rollout is gathered once per update and
 the minibatches are views of it (the reference, too, shuffles once and reuses the order in every epoch).
 """
 from __future__ import annotations
@@ -246,6 +246,8 @@ class PPO:
         stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0)
         a_sum = torch.zeros((), device=self.device); c_sum = torch.zeros((), device=self.device)   # summed on the device: no sync per micro-batch
         fused = self.fused_update and _upd.fused_available(self.actor)
+        fused_critic = self.fused_update and _upd.critic_fused_available(self.critic)
+        p_xpad = _upd.pad_critic_obs(p_obs) if fused_critic else None
         for _ in range(self.updates_per_batch):
             self.decay_lr()
             for start in range(0, used, mb):
@@ -269,7 +271,10 @@ class PPO:
                 self.critic_optim.zero_grad(set_to_none=True)
                 for s0 in range(start, start + n, self.micro_batch):
                     s1 = min(s0 + self.micro_batch, start + n)
-                    loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
+                    if fused_critic:  # K5 GEMM kernels for the two hidden layers, forward and backward (update._CriticLoss)
+                        loss = _upd.critic_loss(self.critic, p_xpad[s0:s1], p_rtg[s0:s1], 1.0 / n)
+                    else:
+                        loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
                     loss.backward()
                     c_sum += loss.detach()
                 self._allreduce_grads(self.critic)

@@ -190,7 +190,7 @@ int mm_linear_tf32x3(const float* x, int rows, int k, const float* w_hi, const f
                      float* y, int ldy, int mode, uint32_t* gate_bits_out, void* stream) {
     if (!x || !w_hi || !w_lo || !y || rows <= 0 || k <= 0 || n_rows_w <= 0 || n_rows_w > 264 || ldy < n_rows_w) return MM_ERR_BAD_ARG;
     if (mode != MM_LINEAR_RELU && mode != MM_LINEAR_GATE && mode != MM_LINEAR_PLAIN) return MM_ERR_BAD_ARG;
-    if ((mode == MM_LINEAR_RELU && !bias) || (mode == MM_LINEAR_GATE && (!gate_bits || n_rows_w != 264)) || (gate_bits_out && (mode != MM_LINEAR_RELU || n_rows_w != 264)))
+    if ((mode == MM_LINEAR_RELU && !bias) || (mode == MM_LINEAR_GATE && !gate_bits) || (gate_bits_out && mode != MM_LINEAR_RELU))
         return MM_ERR_BAD_ARG;
     if (((uintptr_t)x & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15) || ((uintptr_t)y & 15) || ((uintptr_t)gate_bits & 3) || ((uintptr_t)gate_bits_out & 3) ||
         (k & 3) || (ldy & 3) || (n_rows_w & 3))

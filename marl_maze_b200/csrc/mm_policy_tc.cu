@@ -289,7 +289,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int col = c * 32 + 4 * q + j;
-                    if (kMode == TC_EPI_RELU || kMode == TC_EPI_HEADS) yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < TC_N ? __ldg(&bias[col]) : 0.f), 0.f);
+                    if (kMode == TC_EPI_RELU || kMode == TC_EPI_HEADS) yv[j] = fmaxf(__uint_as_float(v[4 * q + j]) + (col < n_valid ? __ldg(&bias[col]) : 0.f), 0.f);
                     else if (kMode == TC_EPI_GATE) yv[j] = ((gword >> (4 * q + j)) & 1u) ? __uint_as_float(v[4 * q + j]) : 0.f;
                     else yv[j] = __uint_as_float(v[4 * q + j]);
                     if (kMode == TC_EPI_RELU) word |= (yv[j] > 0.f ? 1u : 0u) << (4 * q + j);
@@ -441,7 +441,7 @@ cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* 
         k_linear_tf32x3<TC_EPI_RELU><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, bias, y, M, K, nullptr, nullptr, HeadArgs{}, nullptr, gate_out, n_rows_w, ldy);
         break;
     case TC_EPI_GATE:
-        if (!gate || n_rows_w != TC_N) return cudaErrorInvalidValue;
+        if (!gate) return cudaErrorInvalidValue;
         k_linear_tf32x3<TC_EPI_GATE><<<blocks, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, nullptr, y, M, K, nullptr, nullptr, HeadArgs{}, gate, nullptr, n_rows_w, ldy);
         break;
     case TC_EPI_PLAIN:

@@ -256,3 +256,54 @@ def actor_loss(actor, obs2, masks2, actions2, old_logp, adv, clip, scale):
     actions = actions2.to(torch.uint8).contiguous()
     return _ActorTrunkLoss.apply(x0, inv, ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, wh, bh, trunk_splits(actor), masks,
                                  actions, old_logp, adv, float(clip), float(scale))
+
+
+# ------------------------------------------------------------------------------------------------ critic (PPO.py:79-84)
+CRITIC_IN = 130   # both agents' observations (networks.py:96-102); padded to 132 columns: TMA rows must be multiples of 16 bytes
+
+
+def pad_critic_obs(obs: torch.Tensor) -> torch.Tensor:
+    """[n,2,65] -> [n,132] (two zero columns), the input layout critic_loss takes; PPO.update pads the whole shuffled rollout once."""
+    return torch.nn.functional.pad(obs.reshape(obs.shape[0], CRITIC_IN), (0, 2))
+
+
+class _CriticLoss(torch.autograd.Function):
+    """scale * sum_e (V(s_e) - rtg_e)^2 through the centralised critic 130 -> 64 -> 64 -> 1 (Critic.forward networks.py:96-102, the MSE of
+    PPO.py:79) as one autograd node evaluated forward AND backward in forward(), like _ActorTrunkLoss: the two hidden layers, their data
+    gradient and their weight gradients are the K5 GEMM kernels (64 of the 272-column tile used); the 64 -> 1 output layer and the
+    element-wise steps around it are torch."""
+
+    @staticmethod
+    def forward(ctx, xpad, w0, b0, w1, b1, w2, b2, rtg, scale):
+        w0p = torch.nn.functional.pad(w0.detach(), (0, xpad.shape[1] - w0.shape[1]))
+        h0, bits0 = linear_tc(xpad, tf32_split(w0p), MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
+        h1 = linear_tc(h0, tf32_split(w1), MM_LINEAR_RELU, bias=b1.detach().contiguous())
+        v = torch.addmv(b2.detach(), h1, w2.detach()[0])
+        diff = v - rtg
+        loss = (diff * diff).sum() * scale
+        dv = diff * (2.0 * scale)
+        dw2, db2 = (dv @ h1).unsqueeze(0), dv.sum().reshape(1)
+        dz1 = (dv.unsqueeze(1) * w2.detach()) * (h1 > 0)
+        dw1, db1 = wgrad(dz1, h0)
+        dz0 = linear_tc(dz1, tf32_split(w1.detach().t()), MM_LINEAR_GATE, gate_bits=bits0)
+        dw0p, db0 = wgrad(dz0, xpad)
+        ctx.grads = (dw0p[:, :w0.shape[1]].contiguous(), db0, dw1, db1, dw2, db2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grads, ctx.grads = ctx.grads, None
+        return (None,) + tuple(g * t for t in grads) + (None, None)
+
+
+def critic_fused_available(critic) -> bool:
+    ls = critic.layers
+    import torch.nn as nn
+    return (len(ls) == 3 and ls[0].in_features == CRITIC_IN and ls[0].out_features == 64 and ls[1].out_features == 64 and ls[2].out_features == 1
+            and critic.activation is nn.ReLU and ls[0].weight.is_cuda)
+
+
+def critic_loss(critic, xpad, rtg, scale):
+    """scale * sum (critic(obs) - rtg)^2 for xpad = pad_critic_obs(obs) [n,132], rtg [n]."""
+    ls = critic.layers
+    return _CriticLoss.apply(xpad.contiguous(), ls[0].weight, ls[0].bias, ls[1].weight, ls[1].bias, ls[2].weight, ls[2].bias, rtg.contiguous(), float(scale))

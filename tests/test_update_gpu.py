@@ -273,3 +273,34 @@ def test_token_embed_forward_and_backward_match_autograd(faithful):
         worst = max(worst, r)
         assert r < 2e-5, (name, r)
     print("worst embedding gradient error", worst)
+
+
+def test_fused_critic_loss_matches_autograd():
+    """update.critic_loss (K5 GEMM kernels for the critic's hidden layers) against Critic + MSE under torch autograd in fp64."""
+    import copy
+    from marl_maze_b200.networks import Critic
+    from marl_maze_b200.update import critic_loss, critic_fused_available, pad_critic_obs, linear_tc, tf32_split, MM_LINEAR_RELU
+    torch.manual_seed(41)
+    critic = Critic(2, hidden_sizes=[64, 64]).cuda()
+    assert critic_fused_available(critic)
+    ref = copy.deepcopy(critic).double()
+    g = torch.Generator(device="cuda"); g.manual_seed(42)
+    n = 5003
+    obs = torch.rand(n, 2, 65, device="cuda", generator=g)
+    rtg = torch.randn(n, device="cuda", generator=g)
+    xpad = pad_critic_obs(obs)
+    loss = critic_loss(critic, xpad, rtg, 1.0 / n)
+    loss.backward()
+    # same ReLU gates in the reference as in the fused forward (see test_fused_actor_loss_gradients_match_autograd)
+    with torch.no_grad():
+        w0p = torch.nn.functional.pad(critic.layers[0].weight, (0, 2))
+        h0 = linear_tc(xpad, tf32_split(w0p), MM_LINEAR_RELU, bias=critic.layers[0].bias.detach().contiguous())
+        h1 = linear_tc(h0, tf32_split(critic.layers[1].weight), MM_LINEAR_RELU, bias=critic.layers[1].bias.detach().contiguous())
+    x = obs.double().reshape(n, 130)
+    r0 = ref.layers[0](x) * (h0 > 0)
+    r1 = ref.layers[1](r0) * (h1 > 0)
+    ref_loss = ((ref.layers[2](r1).squeeze(-1) - rtg.double()) ** 2).sum() / n
+    ref_loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) < 1e-5 * float(ref_loss.detach())
+    for (name, p), (_, q) in zip(critic.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad, q.grad) < 2e-5, (name, _rel(p.grad, q.grad))
