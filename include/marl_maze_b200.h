@@ -95,6 +95,10 @@ int mm_load_layouts(const mm_state *st, int first, int n, const uint8_t *layouts
  */
 int mm_generate(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
                 uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, void *stream);
+/* as mm_generate with at most max_blocks thread blocks of 64 mazes in flight (0 = no cap): a background build on a side stream that leaves
+ * most of every SM to the kernels it runs beside */
+int mm_generate_ex(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
+                uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, int max_blocks, void *stream);
 
 /*
  * Maze.reset() (maze.py:55-72) + Agent.reset() (maze_agent.py:59-79) for every env with reset_mask[e] != 0

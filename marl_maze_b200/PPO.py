@@ -129,18 +129,21 @@ class PPO:
         if self.prefetch_pool:  # the next rollout's mazes are carved on a side stream while the statistics and the update run
             maze.prefetch_pool()
 
-        # episode statistics for the progress prints (PPO.py:36-43): lengths of finished episodes and their shortest paths
-        t_idx = torch.arange(1, T + 1, device=dev, dtype=torch.int32).view(T, 1).expand(T, E)
-        d = done.bool()
-        last = torch.where(d, t_idx, torch.zeros_like(t_idx))
-        prev_end = torch.cat([torch.zeros(1, E, dtype=torch.int32, device=dev), torch.cummax(last, 0).values[:-1]], 0)
-        episode_lens = (t_idx - prev_end)[d]
-        k_idx = (torch.cumsum(d.int(), 0) - 1)[d]                       # episode index within the rollout, per finished episode
-        e_idx = torch.arange(E, device=dev).view(1, E).expand(T, E)[d]
+        # episode statistics for the progress prints (PPO.py:36-43): lengths of finished episodes and their shortest paths.  Finished episodes
+        # are sparse in [T,E]: one nonzero() (sorted by env, then time), then everything on the short list
+        e_s, t_s = done.t().nonzero(as_tuple=True)
+        n_ep = e_s.numel()
+        pos = torch.arange(n_ep, device=dev)
+        same = torch.zeros(n_ep, dtype=torch.bool, device=dev)
+        same[1:] = e_s[1:] == e_s[:-1]                                    # the previous entry is an earlier episode of the same env
+        lens_s = t_s + 1 - torch.where(same, torch.roll(t_s, 1) + 1, torch.zeros_like(t_s))
+        k_s = pos - torch.cummax(torch.where(same, torch.zeros_like(pos), pos), 0).values if n_ep else pos   # episode index within the rollout
         spl_all = (eng.pool_hdr.view(torch.int32).view(-1, 4)[:, 2] >> 16) & 0xFFFF
-        b_shortest = spl_all[(e_idx + k_idx * E) % eng.P]
-        self.last_stats = dict(env_steps=T * E, episodes=int(d.sum()), solved=int((reward == 1).sum()), keys=int((reward == 0.5).sum()),
-                               mean_reward_per_step=float(reward.mean()), horizon=T, num_envs=E)
+        order = torch.argsort(t_s * E + e_s)                              # report in (time, env) order
+        episode_lens = lens_s[order].to(torch.int32)
+        b_shortest = spl_all[(e_s + k_s * E) % eng.P][order]
+        solved, keys, rsum = torch.stack([(reward == 1).sum(), (reward == 0.5).sum(), reward.sum()]).tolist()
+        self.last_stats = dict(env_steps=T * E, episodes=n_ep, solved=int(solved), keys=int(keys), mean_reward_per_step=rsum / (T * E), horizon=T, num_envs=E)
         N = T * E
         return (obs[:T].reshape(N, 2, 65), actions.reshape(N, 2, 2).float(), logp.reshape(N), b_shortest.cpu().numpy(), episode_lens.cpu().numpy(),
                 masks[:T].reshape(N, 2, 6).bool(), adv.reshape(N), values[:T].reshape(N))

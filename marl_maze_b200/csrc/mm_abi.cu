@@ -8,7 +8,7 @@ namespace mm {
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream);
 cudaError_t launch_gae(const float*, const float*, const uint8_t*, const float*, float*, float*, int, int, double, double, cudaStream_t);
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
-                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, cudaStream_t stream);
+                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, cudaStream_t stream);
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
                           int, const uint64_t*, cudaStream_t);
 cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream);
@@ -90,13 +90,18 @@ int mm_load_layouts(const mm_state* st, int first, int n, const uint8_t* layouts
     return cuda_status(cudaGetLastError());
 }
 
-int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
-                int id_mod, int id_mul, void* scratch, void* stream) {
+int mm_generate_ex(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
+                   int id_mod, int id_mul, void* scratch, int max_blocks, void* stream) {
     if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 4 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
-        id_mod < 0 || (n && !scratch))
+        id_mod < 0 || (n && !scratch) || max_blocks < 0)
         return MM_ERR_BAD_ARG;
     if (n == 0) return MM_OK;
-    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, (cudaStream_t)stream));
+    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks,
+                                       (cudaStream_t)stream));
+}
+int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
+                int id_mod, int id_mul, void* scratch, void* stream) {
+    return mm_generate_ex(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, 0, stream);
 }
 
 int mm_reset(const mm_state* st, const uint8_t* reset_mask, float* obs, uint8_t* masks, void* stream) {

@@ -33,8 +33,9 @@ struct PhiloxStream {
 __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglong2* pool_d2e, uint4* pool_hdr, int first, int n, int rows, int smax,
                                                 int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base, int id_mod, int id_mul,
                                                 uint16_t* scratch) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // grid-stride over mazes: a full grid for an inline build, a few blocks per SM for a background build that trickles along beside
+    // other kernels (each thread's serial carve holds its residency slot for milliseconds)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int p = first + i;
     uint16_t* q = scratch + (size_t)i * smax * smax;  // DFS stack, then BFS queue
     const uint32_t maze_id = id_mod ? id_base + (uint32_t)(i % id_mod) * (uint32_t)id_mul + (uint32_t)(i / id_mod) : id_base + (uint32_t)i;
@@ -181,11 +182,14 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
     pool_hdr[p] = make_uint4((uint32_t)W | ((uint32_t)Hh << 8) | ((uint32_t)sx << 16) | ((uint32_t)sy << 24),
                              (uint32_t)p1x | ((uint32_t)p1y << 8) | ((uint32_t)ex << 16) | ((uint32_t)ey << 24),
                              (uint32_t)kx | ((uint32_t)ky << 8) | ((uint32_t)spl << 16), maze_id);
+    }
 }
 
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed,
-                            uint32_t id_base, int id_mod, int id_mul, void* scratch, cudaStream_t stream) {
-    k_generate<<<(n + 63) / 64, 64, 0, stream>>>((ulonglong2*)st->pool_grid, (ulonglong2*)st->pool_d2e, (uint4*)st->pool_hdr, first, n,
+                            uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, cudaStream_t stream) {
+    int blocks = (n + 63) / 64;
+    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
+    k_generate<<<blocks, 64, 0, stream>>>((ulonglong2*)st->pool_grid, (ulonglong2*)st->pool_d2e, (uint4*)st->pool_hdr, first, n,
                                                  st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, (uint16_t*)scratch);
     return cudaGetLastError();
 }

@@ -130,9 +130,11 @@ class MazeEngine:
         sg = self._stage
         sg["stream"].wait_stream(torch.cuda.current_stream(self.device))  # a previous commit may still be reading the staging buffers
         with torch.cuda.stream(sg["stream"]):
-            _abi.check(self.lib.mm_generate(C.byref(sg["st"]), 0, self.P, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
-                                            C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(sg["scratch"]),
-                                            C.c_void_p(sg["stream"].cuda_stream)), "mm_generate")
+            # at most 3 blocks of 64 carving threads per SM: each holds its residency slot for milliseconds, and a full grid would keep the
+            # kernels of the main stream waiting for slots (measured: a concurrent GEMM was delayed by the whole 13 ms)
+            _abi.check(self.lib.mm_generate_ex(C.byref(sg["st"]), 0, self.P, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
+                                               C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(sg["scratch"]),
+                                               148 * 3, C.c_void_p(sg["stream"].cuda_stream)), "mm_generate_ex")
             sg["event"].record(sg["stream"])
         self.launches += 1
 
