@@ -97,3 +97,27 @@ def test_actor_embedding_dedup_matches_per_row_evaluation():
     g2 = torch.autograd.grad(mv.sum() + mk.sum(), list(actor.parameters()), allow_unused=True)
     for a, b in zip(g1, g2):
         assert (a is None and b is None) or torch.allclose(a, b, rtol=1e-4, atol=1e-4)
+
+
+def test_token_maps_match_the_packed_policy_weights_and_the_oracle_embedding():
+    """update.token_maps (the differentiable folding [I; Wk; Wq; Wv](P_a, b_a) the K5 token kernels are driven with) equals the maps
+    policy.pack_weights builds for K4, and evaluating them reproduces the oracle's Projection + attention inputs (tokens, keys,
+    queries, values) for both projection modes."""
+    import torch
+    from marl_maze_b200.networks import Actor, FEATURE_DIMS
+    from marl_maze_b200.update import token_maps
+    torch.manual_seed(5)
+    for faithful in (True, False):
+        actor = Actor([264, 264, 264], faithful_projection=faithful)
+        tokm, tokb = token_maps(actor)
+        assert tokm.shape == (60, 23, 4) and tokb.shape == (60, 23) and tokm.requires_grad
+        x = torch.rand(7, 65)
+        tok = actor.projection(x)                                   # [7,23,20]
+        k, q, v = actor.attention.keys(tok), actor.attention.querys(tok), actor.attention.values(tok)
+        want = torch.cat([tok, k, q, v], -1)                        # [7,23,60]
+        cols = [0 if faithful else sum(FEATURE_DIMS[:i]) for i in range(23)]
+        xin = torch.stack([torch.nn.functional.pad(x[:, c:c + d], (0, 4 - d)) for c, d in zip(cols, FEATURE_DIMS)], 1)   # [7,23,4]
+        got = torch.einsum("jac,rac->raj", tokm, xin) + tokb.t().unsqueeze(0)
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+        tokm.sum().backward()
+        assert all(l.weight.grad is not None for l in actor.projection.layers) and actor.attention.keys.weight.grad is not None
