@@ -44,7 +44,7 @@ class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
                  verbose: bool = True, micro_batch: int = 1 << 20, update_tf32: bool = False, use_cuda_graph: bool = True,
-                 fused_update: bool = True, prefetch_pool: bool = True):
+                 fused_update: bool = True, prefetch_pool: bool = False):
         if agent_amount != 2:
             raise NotImplementedError("two agents (README.md:34)")
         self.maze = None  # injected by Maze.__init__ (maze.py:40-42)
@@ -59,7 +59,8 @@ class PPO:
         self.horizon, self.seed, self.model_path, self.verbose, self.micro_batch = horizon, seed, model_path, verbose, micro_batch
         self.update_tf32 = update_tf32  # let cuBLAS use TF32 tensor cores in the autograd update (the reference is fp32; off by default)
         self.fused_update = fused_update  # actor trunk + heads + clipped surrogate, fwd and bwd, as hand-written tcgen05 3xTF32 kernels (update.py)
-        self.prefetch_pool = prefetch_pool
+        self.prefetch_pool = prefetch_pool  # build the next rollout's maze pool in the background during the update (off by default: it only moves
+                                            # the ~13 ms carve from the rollout to the update, and hurts when rollouts follow each other directly)
         self.use_cuda_graph = use_cuda_graph  # replay the T-step rollout (6 launches per step) as one captured CUDA graph from the 2nd rollout on
         self._buf = None
         self._graph = None
