@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=65536); ap.add_argument("--horizon", type=int, default=128); ap.add_argument("--side-half", type=int, default=13)
-ap.add_argument("--epochs", type=int, default=2); ap.add_argument("--max-t", type=int, default=1200); ap.add_argument("--no-update", action="store_true"); ap.add_argument("--update-tf32", action="store_true"); ap.add_argument("--simt", action="store_true"); ap.add_argument("--autograd-update", action="store_true", help="PyTorch autograd actor update instead of the K5 kernels"); ap.add_argument("--no-prefetch", action="store_true")
+ap.add_argument("--epochs", type=int, default=2); ap.add_argument("--max-t", type=int, default=1200); ap.add_argument("--no-update", action="store_true"); ap.add_argument("--update-tf32", action="store_true"); ap.add_argument("--simt", action="store_true"); ap.add_argument("--autograd-update", action="store_true", help="PyTorch autograd actor update instead of the K5 kernels"); ap.add_argument("--prefetch", action="store_true", help="PPO(prefetch_pool=True): build the next pool in the background")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -20,7 +20,7 @@ from marl_maze_b200.maze import Maze
 from marl_maze_b200.maze_agent import Agent
 
 E, T = a.envs, a.horizon
-brain = PPO(agent_amount=2, batch_size=E * T - 1 if (E * T) % 5 else E * T - 5, lr=0.00014, epochs=1, verbose=False, model_path=None, horizon=T, device=f"cuda:{local}", update_tf32=a.update_tf32, fused_update=not a.autograd_update, prefetch_pool=not a.no_prefetch)
+brain = PPO(agent_amount=2, batch_size=E * T - 1 if (E * T) % 5 else E * T - 5, lr=0.00014, epochs=1, verbose=False, model_path=None, horizon=T, device=f"cuda:{local}", update_tf32=a.update_tf32, fused_update=not a.autograd_update, prefetch_pool=a.prefetch)
 agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
 maze = Maze(agents=agents, max_timestep=a.max_t, rand_sizes=True, rand_range=[a.side_half, a.side_half], rand_start=True, num_envs=E, device=f"cuda:{local}",
             seed=1, env_offset=rank * E)
