@@ -1,5 +1,11 @@
-"""Host side of the PPO actor update kernels (K5; PPO.py:58-85 of the reference = loss.backward() through the actor + the clipped
-surrogate).  Thin wrappers over the C ABI: torch owns every buffer, the library borrows pointers for the duration of a call."""
+"""Host side of the PPO update kernels (K5; PPO.py:58-85 of the reference: the clipped-surrogate actor loss and the critic's MSE, each
+with its loss.backward()).  Thin wrappers over the C ABI -- torch owns every buffer, the library borrows pointers for the duration of a
+call -- and the autograd nodes built from them:
+    _ActorTrunkLoss  trunk + heads + masked log-probs + ratio + clipped surrogate, forward and backward (actor_loss)
+    TokenEmbed       the 23-token projection + attention in front of the trunk, forward (K4's kernel) and backward (token_embed)
+    GatherRows       embedding rows shared by many agents: gather forward, segment sum backward
+    _CriticLoss      the centralised critic + MSE, forward and backward (critic_loss)
+There is no CPU path: every entry point raises _abi.MMError when the library or a GPU is missing."""
 from __future__ import annotations
 
 import ctypes as C
