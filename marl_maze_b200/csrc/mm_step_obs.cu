@@ -86,6 +86,7 @@ struct LaneCtx {
     bool mk;          // this agent marked its (pre-move) cell this step
     int px, py;       // pre-move cell
     bool want_reset;
+    bool have_d2e;    // phase 1 put this agent's dir-to-exit row in flight (only agents that already know the exit need it for certain)
     float* stage;     // this warp's 32 x 65-float staging area in shared memory (doubles as the landing zone of the window rows)
 };
 
@@ -179,10 +180,14 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
             const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(wbase_s + lane * 176), s1 = (uint32_t)__cvta_generic_to_shared(wbase_s + 32 * 176 + lane * 16);
 #pragma unroll
             for (int r = 0; r < 11; r++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16 * r), "l"(grid + me.y + r) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + me.y) : "memory");
+            // the dir-to-exit row is consumed only by an agent that knows the exit at the END of this step; one that does not know it yet
+            // and learns it during the observation (a sighting, a shared route) fetches the row then -- rare -- instead of every
+            // agent fetching a 32-byte sector every step
+            if (me.ke) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + me.y) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    c.have_d2e = !kResetOnly && valid && me.ke;
     c.me = me; c.t = t; c.keyp = keyp; c.err = err; c.pidx = pidx; c.W = W; c.Hh = Hh; c.ex = ex; c.ey = ey; c.kx = kx; c.ky = ky;
     c.reward = reward; c.done = done; c.mk = mk; c.px = px; c.py = py; c.want_reset = want_reset;
 }
@@ -262,7 +267,7 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
                 if (m0 && r0 >= 0 && r0 <= 10) { ulonglong2 v = slot[r0]; const unsigned long long bit = 1ull << (m0x + kPad); v.y |= bit; v.x &= ~bit; slot[r0] = v; }  // tag 2
                 if (m1 && r1 >= 0 && r1 <= 10) { ulonglong2 v = slot[r1]; const unsigned long long bit = 1ull << (m1x + kPad); v.y |= bit; v.x |= bit; slot[r1] = v; }   // tag 3
                 if (mk) p.env_grid[(size_t)e * p.rows + py + kPad] = slot[py - y + kPad];  // the marked row goes back to HBM with both marks applied
-                dd = *dslot;
+                if (c.have_d2e) dd = *dslot;
             }
 #pragma unroll
             for (int r = 0; r < 11; r++) {
@@ -277,9 +282,7 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
                 const ulonglong2 v = act ? __ldcg(&grid[y + r]) : make_ulonglong2(~0ull, 0ull);
                 l[r] = (uint32_t)(v.x >> x); h[r] = (uint32_t)(v.y >> x);
             }
-            if (act) dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
         }
-        const int d2e_here = (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
 
         // ------------------------------------------------------------ per-direction bit masks (abs 0 N, 1 E, 2 S, 3 W)
         uint32_t l5, h5, wl4, wl5, wl6;
@@ -325,7 +328,6 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
         if (act) {
             me.miny = min(me.miny, y - n[0]); me.maxx = max(me.maxx, x + n[1]);
             me.maxy = max(me.maxy, y + n[2]); me.minx = min(me.minx, x - n[3]);
-            me.d2e = d2e_here;
         }
 
         // ------------------------------------------------------------ sightings: exit, key, other agent
@@ -372,6 +374,10 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
             if (!mine && sh && act) { me.ke = 1; me.oke = 1; }  // route shared with me: agent.knows_end = agent.other_knows_end = True
         }
 
+        // dir-to-exit of the current cell, for whoever knows the exit now (own sighting, or a route shared by the other agent)
+        if (act && me.ke && !(pass == 0 && !kResetOnly && c.have_d2e)) dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
+        const int d2e_here = (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
+        if (act) me.d2e = d2e_here;
         // next_move_to_exit (maze_agent.py:113-118): exit_route[-1] == dir-to-exit of the current cell
         const uint32_t nm = (s_ke && !at_end) ? (1u << ((d2e_here - f) & 3)) : 0xfu;
         // exit_ready (maze.py:100-106): each term sampled right after that agent's own observation
