@@ -7,11 +7,13 @@
 //
 // Activations travel through HBM ONCE, as plain fp32: the split of the A operand happens inside the kernel.  One CTA = one 128-row
 // tile of X through one layer (N = 264 outputs, padded to 272 = 144 + 128 so that each half is a legal UMMA N for M = 128).
-// Warp roles: warp 0 = TMA producer (one lane); warp 1 = TMEM allocator + MMA issuer (one lane); warps 2-5 = SPLITTER during the
-// main loop (turn the TMA-landed fp32 A tile into its hi tile in place and its lo tile next to it, both in the TMA's own
-// 128-byte-swizzled layout, so the transform is position-preserving) and EPILOGUE afterwards (TMEM -> registers -> bias + ReLU ->
-// shared-memory transpose -> whole 128-byte row segments to global).  Weights are pre-split on the host.  Operands are staged
-// through a 2-stage mbarrier ring; out-of-bounds rows / columns (M tail, K = 460 -> 480, N = 264 -> 272) are zero-filled by TMA.
+// Warp roles (default build): warp 0 = TMA producer (one lane): pre-split hi/lo weight tiles through a 3-stage mbarrier ring, the fp32
+// activation tile through a slot of its own; warp 1 = TMEM allocator + MMA issuer (one lane), TS-form MMAs: A from tensor memory, B from
+// shared memory; warps 2-9 = SPLITTER during the main loop (thread = row: read the landed fp32 row, write its hi and lo halves into a
+// 3-stage [hi 32 | lo 32]-column TMEM ring with tcgen05.st) and EPILOGUE afterwards (TMEM -> registers -> bias + ReLU / gate / heads ->
+// 32 x 32 blocks in the TMA's swizzle -> cp.async.bulk.tensor stores).  Out-of-bounds rows / columns (M tail, K = 460 -> 480,
+// N = 264 -> 272) are zero-filled by TMA loads and clipped by TMA stores.  -DMM_TC_A_TMEM=0 builds the first version (A split in shared
+// memory, SS-form MMAs, 2-stage ring), -DMM_TC_SPLIT_WARPS=4 / -DMM_TC_TMA_STORE=0 the intermediate ones, for A/B measurements.
 #include <cuda.h>
 #include <stdio.h>
 #include "mm_env.cuh"
