@@ -216,15 +216,20 @@ class _ActorTrunkLoss(torch.autograd.Function):
         dw1, db1 = wgrad(dz1, h0)
         dz0 = linear_tc(dz1, sp["t1"], MM_LINEAR_GATE, gate_bits=bits0)
         del dz1, h0
-        dw0, db0 = wgrad(dz0, x0)
         dx0 = None
-        if ctx.needs_input_grad[0]:
-            if inv is not None:
-                # the gather's backward is a segment sum over agent rows, and a segment sum commutes with the right-multiplication by W0:
-                # d loss / d src = segsum(dZ0 W0) = segsum(dZ0) W0 -- one streaming pass over [2E,264] and a [U,264]x[264,460] product
-                # instead of the 460-wide data-gradient GEMM and a pass over its [2E,460] result
-                dx0 = segment_sum(dz0, inv, src.shape[0]) @ w0.detach()
-            else:  # the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
+        if inv is not None:
+            # Layer 0's input is a GATHER of a few source rows, X0 = G src.  Both gradients that involve X0 are adjoints of that gather,
+            # and the gather's adjoint is a segment sum over agent rows that commutes with the products by W0 / src:
+            #     d loss / d src = G^T (dZ0 W0) = (G^T dZ0) W0,      dW0 = dZ0^T (G src) = (G^T dZ0)^T src,      db0 = sum_u (G^T dZ0)_u
+            # -- one streaming pass over [2E,264] (mm_segment_sum) and two [U x 264 x 460] products instead of the 460-wide data-gradient
+            # GEMM, a pass over its [2E,460] result, and the 460-wide weight-gradient GEMM
+            seg = segment_sum(dz0, inv, src.shape[0])                     # [U,264] = G^T dZ0
+            dw0, db0 = seg.t() @ src, seg.sum(0)
+            if ctx.needs_input_grad[0]:
+                dx0 = seg @ w0.detach()
+        else:
+            dw0, db0 = wgrad(dz0, x0)
+            if ctx.needs_input_grad[0]:  # the 460 output columns of dX0 = dZ0 W0 are produced as two blocks of <= 264
                 dx0 = torch.empty_like(x0)
                 for i, blk in enumerate(sp["t0"]):
                     linear_tc(dz0, blk, MM_LINEAR_PLAIN, out=dx0, col0=264 * i)
