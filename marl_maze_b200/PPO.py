@@ -52,6 +52,8 @@ class PPO:
         torch.manual_seed(seed)  # PPO.py:7
         self.actor = Actor([264, 264, 264], faithful_projection=faithful_projection).to(self.device)
         self.critic = Critic(agent_amount, hidden_sizes=[64, 64]).to(self.device)
+        # torch.optim.Adam exactly as in the reference (PPO.py:20-21).  (fused=True was tried for its launch count and changed the training
+        # trajectory from the first update on -- the plain implementation is the one that tracks the autograd reference path.)
         self.actor_optim = torch.optim.Adam(self.actor.parameters(), lr=lr)
         self.critic_optim = torch.optim.Adam(self.critic.parameters(), lr=lr)
         self.epochs, self.batch_size, self.lr, self.discount_rate, self.lam = epochs, batch_size, lr, discount_rate, lam

@@ -66,8 +66,8 @@ class m_Attention(nn.Module):
 def _few_distinct_rows(p, max_rows: int = 8):
     """(rows [U, d], inverse [B]) with rows[inverse] == p, like torch.unique(p, dim=0, return_inverse=True) but without its
     lexicographic sort when there are at most `max_rows` distinct rows (environment observations have 4 distinct facing prefixes):
-    `max_rows` rounds of "take the first row not yet matched, mark every row equal to it" -- 8 streaming passes over [B, d] and ONE
-    host synchronisation.  Unused slots repeat row 0 (harmless: nothing maps to them); more distinct rows fall back to torch.unique."""
+    rounds of "take the first row not yet matched, mark every row equal to it" -- 4 (or 8) streaming passes over [B, d] and one (or two)
+    host synchronisations.  Unused slots repeat row 0 (harmless: nothing maps to them); more distinct rows fall back to torch.unique."""
     p = p.contiguous()
     inv = torch.full((p.shape[0],), -1, dtype=torch.int64, device=p.device)
     reps = []
@@ -76,9 +76,9 @@ def _few_distinct_rows(p, max_rows: int = 8):
         rep = p[torch.argmax(rem.to(torch.uint8))]          # first unmatched row (row 0 once everything is matched)
         inv = torch.where(rem & (p == rep).all(1), u, inv)
         reps.append(rep)
-    if bool((inv < 0).any()):
-        return torch.unique(p, dim=0, return_inverse=True)
-    return torch.stack(reps), inv
+        if u % 4 == 3 and not bool((inv < 0).any()):        # the one host synchronisation, after 4 (the facings) or 8 rounds
+            return torch.stack(reps), inv
+    return torch.unique(p, dim=0, return_inverse=True)
 
 
 class Actor(nn.Module):
