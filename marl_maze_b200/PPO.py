@@ -40,6 +40,22 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
+def finished_episodes(done: torch.Tensor):
+    """From done [T,E] (uint8 / bool): (length, index of the episode within its env, env) of every finished episode, in (time, env)
+    order.  Finished episodes are sparse in [T,E]: one nonzero() (sorted by env, then time), then everything on the short list."""
+    T, E = done.shape
+    dev = done.device
+    e_s, t_s = done.t().nonzero(as_tuple=True)
+    n_ep = e_s.numel()
+    pos = torch.arange(n_ep, device=dev)
+    same = torch.zeros(n_ep, dtype=torch.bool, device=dev)
+    same[1:] = e_s[1:] == e_s[:-1]                                    # the previous entry is an earlier episode of the same env
+    lens_s = t_s + 1 - torch.where(same, torch.roll(t_s, 1) + 1, torch.zeros_like(t_s))
+    k_s = pos - torch.cummax(torch.where(same, torch.zeros_like(pos), pos), 0).values if n_ep else pos
+    order = torch.argsort(t_s * E + e_s)                              # report in (time, env) order
+    return lens_s[order].to(torch.int32), k_s[order], e_s[order]
+
+
 class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
@@ -132,19 +148,11 @@ class PPO:
         if self.prefetch_pool:  # the next rollout's mazes are carved on a side stream while the statistics and the update run
             maze.prefetch_pool()
 
-        # episode statistics for the progress prints (PPO.py:36-43): lengths of finished episodes and their shortest paths.  Finished episodes
-        # are sparse in [T,E]: one nonzero() (sorted by env, then time), then everything on the short list
-        e_s, t_s = done.t().nonzero(as_tuple=True)
-        n_ep = e_s.numel()
-        pos = torch.arange(n_ep, device=dev)
-        same = torch.zeros(n_ep, dtype=torch.bool, device=dev)
-        same[1:] = e_s[1:] == e_s[:-1]                                    # the previous entry is an earlier episode of the same env
-        lens_s = t_s + 1 - torch.where(same, torch.roll(t_s, 1) + 1, torch.zeros_like(t_s))
-        k_s = pos - torch.cummax(torch.where(same, torch.zeros_like(pos), pos), 0).values if n_ep else pos   # episode index within the rollout
+        # episode statistics for the progress prints (PPO.py:36-43): lengths of finished episodes and their shortest paths
+        episode_lens, k_ep, e_ep = finished_episodes(done)
+        n_ep = episode_lens.numel()
         spl_all = (eng.pool_hdr.view(torch.int32).view(-1, 4)[:, 2] >> 16) & 0xFFFF
-        order = torch.argsort(t_s * E + e_s)                              # report in (time, env) order
-        episode_lens = lens_s[order].to(torch.int32)
-        b_shortest = spl_all[(e_s + k_s * E) % eng.P][order]
+        b_shortest = spl_all[(e_ep + k_ep * E) % eng.P]
         solved, keys, rsum = torch.stack([(reward == 1).sum(), (reward == 0.5).sum(), reward.sum()]).tolist()
         self.last_stats = dict(env_steps=T * E, episodes=n_ep, solved=int(solved), keys=int(keys), mean_reward_per_step=rsum / (T * E), horizon=T, num_envs=E)
         N = T * E

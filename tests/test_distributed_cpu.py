@@ -61,3 +61,28 @@ def test_global_maze_ids_do_not_depend_on_sharding():
     one = ids(0, 8)
     two = {**ids(0, 4), **ids(4, 4)}
     assert one == two and len(set(one.values())) == 32
+
+
+def test_finished_episode_statistics_and_row_grouping_cpu():
+    """Host logic of the rollout / update that needs no GPU: PPO.finished_episodes against the dense [T,E] formulation, and
+    networks._few_distinct_rows against torch.unique."""
+    import torch
+    from marl_maze_b200.PPO import finished_episodes
+    from marl_maze_b200.networks import _few_distinct_rows
+    torch.manual_seed(0)
+    T, E = 37, 53
+    for trial in range(10):
+        done = (torch.rand(T, E) < (0.0 if trial == 0 else 0.07)).to(torch.uint8)
+        t_idx = torch.arange(1, T + 1, dtype=torch.int32).view(T, 1).expand(T, E)
+        d = done.bool()
+        last = torch.where(d, t_idx, torch.zeros_like(t_idx))
+        prev_end = torch.cat([torch.zeros(1, E, dtype=torch.int32), torch.cummax(last, 0).values[:-1]], 0)
+        lens, k, e = finished_episodes(done)
+        assert torch.equal(lens, (t_idx - prev_end)[d])
+        assert torch.equal(k, (torch.cumsum(d.int(), 0) - 1)[d].long())
+        assert torch.equal(e, torch.arange(E).view(1, E).expand(T, E)[d])
+    for p in (torch.nn.functional.one_hot(torch.randint(0, 4, (5000,)), 4).float(),        # 4 facings: one round of four
+              torch.randint(0, 7, (5000, 1)).float().repeat(1, 4),                          # 7 distinct rows: two rounds
+              torch.randn(300, 4)):                                                         # all distinct: torch.unique fallback
+        rows, inv = _few_distinct_rows(p)
+        assert torch.equal(rows[inv], p) and rows.shape[0] <= max(8, torch.unique(p, dim=0).shape[0])
