@@ -16,6 +16,22 @@
 
 namespace mm {
 
+// Per-device one-time launch configuration (cudaFuncSetAttribute applies to the CURRENT device's context, so a process-wide flag would
+// leave a second GPU unconfigured).  `true` the first time it is asked for the current device.
+constexpr int kMaxDevices = 64;
+struct PerDeviceFlag {
+    bool done[kMaxDevices] = {};
+    bool first_time() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+    void retract() { int d = 0; if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDevices) done[d] = false; }
+};
+inline int current_device_slot() { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDevices) ? d : 0; }
+
 constexpr int kPad = MM_PAD;
 constexpr int kObs = MM_OBS_DIM;
 constexpr unsigned kFull = 0xffffffffu;

@@ -341,11 +341,10 @@ cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* 
     return cudaGetLastError();
 }
 cudaError_t launch_tokens_bwd(const float* wts, const float* obs, const float* dout, int R, float* dy40, float* part, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (configured.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(k_tokens_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem);
-        if (e != cudaSuccess) return e;
-        configured = true;
+        if (e != cudaSuccess) { configured.retract(); return e; }
     }
     k_tokens_bwd<<<min((R + kTbWarps - 1) / kTbWarps, 148 * 6), kTbWarps * 32, kTbSmem, stream>>>(obs, wts, dout, dy40, R);
     const int blocks = tokens_bwd_blocks();
@@ -506,8 +505,11 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
     // flags bit 1: the critic only reads obs, so it runs on a side stream forked from / joined to `stream` by events (legal inside a
     // stream capture, where it becomes a parallel branch of the graph) and overlaps the actor's token + trunk kernels.  The stream and
     // the two events are created once per host thread, on the first (eager) call.
-    static thread_local cudaStream_t side = nullptr;
-    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    static thread_local cudaStream_t side_d[kMaxDevices] = {};
+    static thread_local cudaEvent_t ev_fork_d[kMaxDevices] = {}, ev_join_d[kMaxDevices] = {};
+    const int dslot = current_device_slot();   // streams and events belong to the device they were created on
+    cudaStream_t& side = side_d[dslot];
+    cudaEvent_t &ev_fork = ev_fork_d[dslot], &ev_join = ev_join_d[dslot];
     const bool overlap = value && (flags & 2);
     if (overlap) {
         if (!side) {

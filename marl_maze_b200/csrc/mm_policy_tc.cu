@@ -424,14 +424,13 @@ cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* 
         found = &e.maps;
     }
     const TcMaps& maps = *found;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (configured.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tf32x3<TC_EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
+        if (e != cudaSuccess) { configured.retract(); return e; }
     }
     const int blocks = (M + TC_BM - 1) / TC_BM;
     switch (mode) {

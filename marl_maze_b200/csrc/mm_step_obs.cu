@@ -22,7 +22,7 @@ namespace mm {
 #endif
 constexpr int kThreads = MM_K2_THREADS;
 #ifndef MM_K2_MINBLOCKS
-#define MM_K2_MINBLOCKS 4
+#define MM_K2_MINBLOCKS 5
 #endif
 #ifndef MM_K2_MINBLOCKS2
 #define MM_K2_MINBLOCKS2 3
@@ -32,6 +32,13 @@ constexpr int kThreads = MM_K2_THREADS;
 // DRAM traffic per launch the memory system, not exposed latency, is the limiter, and the pipelined form costs a block of occupancy.
 #ifndef MM_K2_GROUPS
 #define MM_K2_GROUPS 1
+#endif
+// Window transport.  1 = each lane's 11 window rows (176 contiguous bytes) travel global -> shared as ONE cp.async.bulk (TMA bulk copy,
+// completion on the warp's mbarrier) instead of 11 cp.async.cg of 16 bytes: a 16-byte request still moves a whole 32-byte sector over the
+// L1 <-> L2 crossbar, so the per-row form sent 23 M sector requests per launch (1 Mi mazes) for 6.5 M distinct sectors -- the request
+// path (l1tex2xbar 56 % busy in profiles/r01h) was the most loaded unit after DRAM.
+#ifndef MM_K2_BULK
+#define MM_K2_BULK 1
 #endif
 
 // One axis ray seen from the agent.  cw: bit j-1 = wall (or out of bounds) at distance j, j = 1..5.
@@ -88,7 +95,10 @@ struct LaneCtx {
     bool want_reset;
     bool have_d2e;    // phase 1 put this agent's dir-to-exit row in flight (only agents that already know the exit need it for certain)
     float* stage;     // this warp's 32 x 65-float staging area in shared memory (doubles as the landing zone of the window rows)
+    uint64_t* bar;    // this warp's mbarrier (MM_K2_BULK: completion of the window bulk copies)
 };
+
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Phase 1: load state, S1 (Maze.step / single_agent_step), reward/done, and put the window rows of the NEW position in flight.
 template <bool kResetOnly>
@@ -175,11 +185,22 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
         // capacity otherwise caps the number of outstanding window loads per SM (profiles/r01_notes.md).  Landing zone = the warp's
         // own observation staging area: [lane][11 rows] then [lane] field row.
         char* wbase_s = reinterpret_cast<char*>(c.stage);
+#if MM_K2_BULK
+        {   // one arrival carrying the byte count of every bulk copy this warp is about to issue
+            const uint32_t vmask = __ballot_sync(kFull, valid);
+            if (lane == 0 && vmask)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(c.bar)), "r"(176u * (uint32_t)__popc(vmask)) : "memory");
+        }
+#endif
         if (valid) {
             const ulonglong2* grid = (const ulonglong2*)(p.env_grid + (size_t)e * p.rows);
             const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(wbase_s + lane * 176), s1 = (uint32_t)__cvta_generic_to_shared(wbase_s + 32 * 176 + lane * 16);
+#if MM_K2_BULK
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], 176, [%2];" ::"r"(s0), "l"(grid + me.y), "r"(k2_smem_u32(c.bar)) : "memory");
+#else
 #pragma unroll
             for (int r = 0; r < 11; r++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16 * r), "l"(grid + me.y + r) : "memory");
+#endif
             // the dir-to-exit row is consumed only by an agent that knows the exit at the END of this step; one that does not know it yet
             // and learns it during the observation (a sighting, a shared route) fetches the row then -- rare -- instead of every
             // agent fetching a 32-byte sector every step
@@ -262,6 +283,17 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
             const bool m0 = a ? (omk != 0) : mk, m1 = a ? mk : (omk != 0);
             const int m0x = a ? opx : px, m0y = a ? opy : py, m1x = a ? px : opx, m1y = a ? py : opy;
             asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+#if MM_K2_BULK
+            if (__ballot_sync(kFull, valid)) {  // bounded spin: a protocol bug must surface as a launch failure, never as a hung GPU
+                const uint32_t b = k2_smem_u32(c.bar);
+                uint32_t ok = 0;
+                const long long t0 = clock64();
+                while (!ok) {
+                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(b) : "memory");
+                    if (!ok && clock64() - t0 > 2000000000ll) __trap();
+                }
+            }
+#endif
             if (act) {  // apply both marks to this lane's private copy of its window rows (dynamic row index = plain smem addressing)
                 const int r0 = m0y - y + kPad, r1 = m1y - y + kPad;
                 if (m0 && r0 >= 0 && r0 <= 10) { ulonglong2 v = slot[r0]; const unsigned long long bit = 1ull << (m0x + kPad); v.y |= bit; v.x &= ~bit; slot[r0] = v; }  // tag 2
@@ -513,6 +545,16 @@ __global__ void __launch_bounds__(kThreads, kGroups == 2 ? MM_K2_MINBLOCKS2 : MM
         c[gi].g = ((long long)blockIdx.x * kGroups + gi) * kThreads + tid;
         c[gi].e = (int)(c[gi].g >> 1); c[gi].a = (int)(c[gi].g & 1); c[gi].valid = c[gi].e < p.E;
         c[gi].stage = s_obs + (gi * kThreads + (tid & ~31)) * kObs;
+        c[gi].bar = reinterpret_cast<uint64_t*>(s_obs + kGroups * kThreads * kObs) + gi * (kThreads / 32) + (tid >> 5);
+#if MM_K2_BULK
+        if (!kResetOnly) {
+            if (lane == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2_smem_u32(c[gi].bar)) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+        }
+#endif
         k2_phase1<kResetOnly>(p, c[gi], lane);
     }
     if (kGroups == 2) { k2_phase2<kResetOnly, 1>(p, c[0], lane); k2_phase2<kResetOnly, 0>(p, c[kGroups - 1], lane); }
@@ -538,15 +580,14 @@ cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t s
     // NOTE (measured, profiles/r01_notes.md): forcing the maximum shared-memory carveout halves throughput, so the driver's default is kept.
     if (reset_only) {
         const int blocks = (int)((agents + kThreads - 1) / kThreads);
-        k_step_obs<true, 1><<<blocks, kThreads, (size_t)kThreads * kObs * sizeof(float), stream>>>(p);
+        k_step_obs<true, 1><<<blocks, kThreads, (size_t)kThreads * kObs * sizeof(float) + (kThreads / 32) * sizeof(uint64_t), stream>>>(p);
     } else {
         constexpr int G = MM_K2_GROUPS;
-        const size_t smem = (size_t)G * kThreads * kObs * sizeof(float);
-        static bool configured = false;
-        if (!configured) {
+        const size_t smem = (size_t)G * kThreads * kObs * sizeof(float) + (size_t)G * (kThreads / 32) * sizeof(uint64_t);
+        static PerDeviceFlag configured;
+        if (configured.first_time()) {
             cudaError_t e = cudaFuncSetAttribute(k_step_obs<false, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = true;
+            if (e != cudaSuccess) { configured.retract(); return e; }
         }
         const int blocks = (int)((agents + (long long)G * kThreads - 1) / ((long long)G * kThreads));
         k_step_obs<false, G><<<blocks, kThreads, smem, stream>>>(p);

@@ -252,11 +252,10 @@ cudaError_t launch_wgrad_tc(const float* dz, const float* h, int R, int n_out, i
     const int n_mt = (out_rows + WG_M - 1) / WG_M, n_nt = ld / WG_N;
     WgMaps maps;
     if (!make_map_mn(&maps.a, tr ? h : dz, R, a_cols) || !make_map_mn(&maps.b, tr ? dz : h, R, b_cols)) return cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (configured.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
+        if (e != cudaSuccess) { configured.retract(); return e; }
     }
     k_wgrad_tf32x3<<<slabs * n_mt * n_nt, WG_THREADS, WG_SMEM_BYTES, stream>>>(maps, part, R, a_cols, b_cols, tr, n_mt, n_nt, kb_per, ld);
     return cudaGetLastError();
