@@ -5,22 +5,34 @@
     python bench.py --impl reference [--gpus N] [--steps K] ...    # reference arm: the CPU path on the host cores
 
 Workload (config.workload): BASELINE config[3] -- 1,048,576 mazes x 2 agents PER GPU at 4x the default maze area
-(side 49), max_timestep 1200, uniform mask-legal random actions, auto-reset on.  Weak scaling: envs are independent,
-each rank owns its own shard (no data-path collective).
+(side 49), max_timestep 1200, uniform mask-legal random actions, auto-reset on, episode phases spread uniformly over
+[0, max_timestep) before timing (steady-state rate of truncations / resets).  Weak scaling: envs are independent, each
+rank owns its own shard (no data-path collective).
 
 One "step" = one pass of the hot path over all envs of the rank (one K2 launch).
-  value  : whole-job agent-steps/s with everything resident in HBM (actions are sampled inside the kernel).
-  e2e    : the same through the host-buffer API: every step copies the step's actions from pinned host memory
-           to the device and the step's full result (obs, masks, reward, done) back to pinned host memory.
-  roofline: algorithmic bytes per launch (685 + ceil(S^2/4) B per env-step) / mean launch duration
-           measured with CUDA events on the launching stream, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline: the CPU oracle (a C port of the reference loop, oracle/) on the box's host cores, bounded sample.
+  value   : whole-job agent-steps/s with everything resident in HBM (actions are sampled inside the kernel).  The timed
+            region is `reps` back-to-back blocks of exactly K steps (reps chosen so that it lasts >= 60 ms: the clock sampler
+            needs more than a 4 ms window); ms_per_step is the mean over all of them.
+  e2e     : the same through the host-buffer API: every step copies the step's actions from pinned host memory to the device
+            and the step's full result (obs, masks, reward, done) back to pinned host memory.
+  roofline: algorithmic bytes per launch (685 + ceil(S^2/4) B per env-step) / mean launch duration measured with
+            CUDA events on the launching stream, against MEASURED_PEAKS.json hbm_gbs (`frac`); `frac_dram` is the same with the
+            DRAM bytes ncu measured for that launch (profiles/k2_traffic.json, `traffic_source`).
+  cpu_baseline: the CPU oracle (a C port of the reference loop, oracle/) on the box's host cores, bounded sample -- and,
+            under `python_reference`, the UNMODIFIED Python reference (staged under baseline/_ref/) timed on the same host.
+Extra legs of our arm (extra keys; they do not change `value`):
+  rollout   : BASELINE config[2] (65,536 mazes, T = 128, side 25): full PPO rollout (K4 policy + K2 step per step, K3 GAE) and the
+              5 x 5 update, N = 1 only.
+  train_iter: the same iteration per rank at N > 1 -- the one place a collective (NCCL gradient all-reduce) is on the path.
+  strong    : K2 with 1,048,576 mazes in TOTAL (1 Mi / N per GPU): the strong-scaling point of config[3].
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -34,6 +46,8 @@ MAX_T = 1200            # main.py:20
 ENVS_PER_GPU = 1 << 20
 BYTES_PER_ENV_STEP = 685 + (SIDE * SIDE + 3) // 4   # SURVEY 8d -> 1286 B at S=49 (643 B per agent-step)
 FALLBACK_HBM_GBS = 6650.0
+MIN_TIMED_MS = 60.0
+STAGGER_HASH = 2654435761
 
 
 def _peaks():
@@ -42,6 +56,14 @@ def _peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(envs_per_gpu: int, world: int) -> dict:
+    """The SAME dict in both arms: the driver compares the arms' configs."""
+    return {"workload": f"config[3]: {envs_per_gpu} mazes x 2 agents per GPU, side {SIDE} (4x default area), max_timestep {MAX_T}, uniform mask-legal "
+                        "random actions, auto-reset on, episode phases spread uniformly before timing",
+            "envs_per_gpu": envs_per_gpu, "side": SIDE, "max_timestep": MAX_T, "parallelism": f"env-shard x{world}",
+            "l2": f"per-step traffic ({BYTES_PER_ENV_STEP * envs_per_gpu / 1e6:.0f} MB algorithmic) exceeds the 126 MB L2; no flush needed"}
 
 
 class ClockSampler:
@@ -94,54 +116,122 @@ class ClockSampler:
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_leg(n_envs: int, steps: int, warmup: int, threads: int):
-    """The reference's CPU loop (C port in oracle/) on `threads` host threads; returns agent-steps/s and a description."""
-    from oracle import OracleBatch
-    b = OracleBatch(n_envs, n_envs, max_timestep=MAX_T, threads=threads)
-    for p in range(n_envs):
-        b.generate_pool_maze(p, SIDE, True, 1, 12345, p)
-    b.reset_all()
-    if warmup:
-        b.run_random(warmup, seed=1)
-    t0 = time.perf_counter()
-    n = b.run_random(steps, seed=2)
-    dt = time.perf_counter() - t0
-    return 2.0 * n / dt, dt, f"{n_envs} mazes of side {SIDE} x {steps} steps, uniform legal random actions, auto-reset, env-major OpenMP"
+# ------------------------------------------------------------------------------------------------ CPU arms
+class CpuPort:
+    """The reference's CPU loop as its C restatement (oracle/), on `threads` host threads.  ONE code path for both CPU numbers the bench
+    prints (the `cpu_baseline` leg of our arm and the whole `--impl reference` arm): env-major OpenMP over a bounded sample of the
+    workload's mazes, every call one parallel region of `inner` consecutive steps per env, phases spread before timing."""
+
+    def __init__(self, n_envs: int, threads: int):
+        from oracle import OracleBatch
+        self.n_envs, self.threads = n_envs, threads
+        self.b = OracleBatch(n_envs, n_envs, max_timestep=MAX_T, threads=threads)
+        for p in range(n_envs):
+            self.b.generate_pool_maze(p, SIDE, True, 1, 12345, p)
+        self.b.reset_all()
+        self.b.run_random(0, seed=1, stagger=MAX_T)   # env e advances (e * 2654435761 mod 2^32) mod 1200 steps
+        self.calls = 0
+
+    def step(self, inner: int) -> int:
+        self.calls += 1
+        return self.b.run_random(inner, seed=100 + self.calls)
+
+    def describe(self, inner: int) -> str:
+        return (f"{self.n_envs} mazes of side {SIDE} (bounded sample of the workload), {inner} consecutive steps per env per call, uniform mask-legal "
+                "random actions, auto-reset, phases spread, env-major OpenMP")
+
+
+def python_reference_legs(seconds: float, threads: int) -> dict:
+    """The UNMODIFIED Python reference on this host, staged under baseline/_ref/ by baseline/stage_reference.py."""
+    script = os.path.join(ROOT, "baseline", "ref_python_bench.py")
+    out = {"source": "baseline/_ref (unmodified rhuangr/MARL-Maze, staged by baseline/stage_reference.py)", "host_threads": threads}
+
+    def run(*extra, timeout=600):
+        try:
+            r = subprocess.run([sys.executable, script, *extra], capture_output=True, text=True, timeout=timeout,
+                               env=dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1"))
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001
+            return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+    first = run("--mode", "env", "--seconds", str(seconds), "--side-half", str(SIDE_HALF))
+    if "unavailable" in first:
+        out["unavailable"] = first["unavailable"]
+        return out
+    allp = run("--mode", "env", "--seconds", str(seconds), "--side-half", str(SIDE_HALF), "--procs", str(threads))
+    out["env_step_obs"] = {"what": f"Maze.step + observations (maze.py:74-163), side {SIDE}, mask-legal uniform random actions, resets included",
+                           "one_process_agent_steps_per_s": first.get("agent_steps_per_s"),
+                           "all_cores_agent_steps_per_s": allp.get("agent_steps_per_s"), "processes": threads, "unit": "agent-steps/s"}
+    pol = run("--mode", "policy", "--seconds", str(min(seconds, 5.0)))
+    out["config1_policy_rollout"] = {"what": "display_policy.update_env loop with PPO.pth, 1 maze, main.py settings (maze.py:477-493), 1 torch thread",
+                                     "agent_steps_per_s": pol.get("agent_steps_per_s"), "unit": "agent-steps/s"}
+    bat = run("--mode", "batch", "--batch", "300")
+    out["get_batch"] = {"what": "PPO.get_batch (PPO.py:89-152), batch_size 300, 1 torch thread", "env_steps_per_s": bat.get("env_steps_per_s"), "unit": "env-steps/s"}
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    n_envs = args.ref_envs
-    from oracle import OracleBatch
-    b = OracleBatch(n_envs, n_envs, max_timestep=MAX_T, threads=threads)
-    for p in range(n_envs):
-        b.generate_pool_maze(p, SIDE, True, 1, 12345, p)
-    b.reset_all()
-    for _ in range(args.warmup):
-        b.run_random(1, seed=1)
+    inner = args.ref_inner
+    cpu = CpuPort(args.ref_envs, threads)
+    for _ in range(max(args.warmup, 1)):
+        cpu.step(inner)
     t0 = time.perf_counter()
     n = 0
-    for k in range(args.steps):  # one step = one pass of the path over the bounded sample
-        n += b.run_random(1, seed=2 + k)
+    for _ in range(args.steps):  # one step = one call = one pass of the path over the bounded sample (inner consecutive steps per env)
+        n += cpu.step(inner)
     dt = time.perf_counter() - t0
     val = 2.0 * n / dt
-    sample = f"{n_envs} mazes of side {SIDE} per step (bounded sample of the {ENVS_PER_GPU}-maze workload), uniform legal random actions, auto-reset"
+    sample = cpu.describe(inner)
+    py = None if args.no_python_reference else python_reference_legs(args.py_seconds, threads)
     line = {
         "impl": "reference", "metric": "agent_steps_per_sec", "value": val, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32/f64->f32", "data": "synthetic",
-        "config": {"workload": f"config[3] sample: {sample}", "side": SIDE, "max_timestep": MAX_T, "envs_per_step": n_envs},
-        "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.envs, world),
+        "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample, "seconds": round(dt, 2),
+                         "env_steps_per_step": args.ref_envs * inner, "python_reference": py},
         "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference is pure Python and cannot travel to the GPU box; this arm times oracle/ (its C restatement, pinned bit-exactly to the "
-                "reference by tests/golden) on all host threads",
+        "note": "value = the reference's CPU loop as its C restatement (oracle/, pinned bit-exactly to the reference by tests/golden) on all host threads -- "
+                "about 1000x the Python reference per core, i.e. a deliberately stringent CPU arm; the unmodified Python reference timed on this host is under "
+                "cpu_baseline.python_reference",
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def _bind_to_gpu_numa_node(local: int):
+    """CPU affinity of this rank = the cores NVML reports as local to its GPU (no-op on single-node hosts / VMs that expose one domain):
+    the rank's pinned host buffers are then first-touched on the GPU's own NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus and len(cpus) < (os.cpu_count() or 1):
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to GPU {local}"
+        return "single affinity domain (nothing to bind)"
+    except Exception as e:  # noqa: BLE001
+        return f"unavailable ({type(e).__name__})"
+
+
+def spread_phases(eng, torch, steps: int = MAX_T):
+    """Bring the envs to uniformly spread episode times: `steps` K2 steps during which env e is reset once, at step
+    (e * 2654435761 mod 2^32) mod steps -- afterwards about E / max_timestep envs hit the time limit (and reset in-launch) every step."""
+    E = eng.E
+    phase = ((torch.arange(E, device=eng.device, dtype=torch.int64) * STAGGER_HASH) % (1 << 32)) % steps
+    for k in range(steps):
+        eng.step(None, auto_reset=True, action_seed=3)
+        eng.reset((phase == k).to(torch.uint8))
 
 
 def run_ours(args):
@@ -154,6 +244,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    affinity = _bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -171,32 +262,43 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    E, K, Wm = args.envs, args.steps, args.warmup
+    def timed_k2(eng, K, reps, sampler=None):
+        """`reps` back-to-back blocks of exactly K device-resident steps; returns total ms (max over ranks)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(K * reps):
+            eng.step(None, auto_reset=True, action_seed=1)
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
+    E, K, Wm = args.envs, args.steps, max(args.warmup, 3)
     eng = MazeEngine(E, smax=SIDE, max_timestep=MAX_T, pool_size=E, env_offset=rank * E)
     eng.generate(seed=2026, side_range=(SIDE_HALF, SIDE_HALF), rand_start=True, difficulty=1, id_base=rank * E)
     eng.reset()
     torch.cuda.synchronize()
-    actions_out = torch.zeros(E, 2, 2, dtype=torch.uint8, device=dev)
 
     # ---------------------------------------------------------------- leg 1: device-resident (value)
-    # spread episode phases before timing so that resets are in steady state (about E/episode_len per step)
-    for _ in range(max(Wm, 3)):
-        eng.step(None, auto_reset=True, action_seed=1, actions_out=actions_out)
+    if not args.no_spread:
+        spread_phases(eng, torch)
+    for _ in range(Wm):
+        eng.step(None, auto_reset=True, action_seed=1)
     barrier()
+    # calibrate the number of K-step blocks so that the timed region lasts >= MIN_TIMED_MS on every rank
+    probe = timed_k2(eng, K, 1)
+    reps = max(1, int(math.ceil(MIN_TIMED_MS / max(probe, 1e-3))))
     l0 = eng.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        barrier()
-        ev0.record()
-        for _ in range(K):
-            eng.step(None, auto_reset=True, action_seed=1, actions_out=actions_out)
-        ev1.record()
-        barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+        ms_total = timed_k2(eng, K, reps)
     launches = eng.launches - l0
-    ms_per_step = ms_total / K
-    value = 2.0 * E * world * K / (ms_total * 1e-3)
-    errs = int(eng.envs()[:, 6].sum())
+    ms_per_step = ms_total / (K * reps)
+    value = 2.0 * E * world * K * reps / (ms_total * 1e-3)
+    envs_now = eng.envs()
+    errs = int(envs_now[:, 6].sum())
+    resets_per_step = None
+    if not args.no_spread:  # evidence that the timed window sat in reset steady state: episodes started during it
+        resets_per_step = float((envs_now[:, 0] < K * reps).sum()) / (K * reps) if K * reps < MAX_T else None
 
     # ---------------------------------------------------------------- leg 2: host buffers (e2e)
     Ke = max(8, min(K, args.e2e_steps))
@@ -240,47 +342,137 @@ def run_ours(args):
     e2e_value = 2.0 * E * world * Ke / (ms_e2e * 1e-3)
     h2d = d_act.numel()
     d2h = h_obs.numel() * 4 + h_masks.numel() + h_rew.numel() * 4 + h_done.numel()
+    del h_act, h_obs, h_masks, h_rew, h_done, d_act
 
     # ---------------------------------------------------------------- roofline of K2 (dominant and only kernel of the step)
     peak, peak_src = _peaks()
     achieved = BYTES_PER_ENV_STEP * E / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU; every rank runs the same launch
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "cited, not measured by this run: " + tj.get("source", "profiles/k2_traffic.json")
     except Exception:
         pass
+    frac_dram = (traffic * E / ENVS_PER_GPU / (ms_per_step * 1e-3) / 1e9 / peak) if traffic else None
+
+    # ---------------------------------------------------------------- strong-scaling point: 1 Mi mazes in TOTAL
+    strong = None
+    if not args.no_extra_legs and world > 1 and ENVS_PER_GPU % world == 0:
+        del eng
+        torch.cuda.empty_cache()
+        Es = ENVS_PER_GPU // world
+        eng_s = MazeEngine(Es, smax=SIDE, max_timestep=MAX_T, pool_size=Es, env_offset=rank * Es)
+        eng_s.generate(seed=2026, side_range=(SIDE_HALF, SIDE_HALF), rand_start=True, difficulty=1, id_base=rank * Es)
+        eng_s.reset()
+        if not args.no_spread:
+            spread_phases(eng_s, torch)
+        for _ in range(Wm):
+            eng_s.step(None, auto_reset=True, action_seed=1)
+        p_s = timed_k2(eng_s, K, 1)
+        reps_s = max(1, int(math.ceil(MIN_TIMED_MS / max(p_s, 1e-3))))
+        ms_s = timed_k2(eng_s, K, reps_s)
+        strong = {"what": f"config[3] strong scaling: {ENVS_PER_GPU} mazes in total, {Es} per GPU", "n_gpus": world, "value": 2.0 * Es * world * K * reps_s / (ms_s * 1e-3),
+                  "unit": "agent-steps/s", "ms_per_step": ms_s / (K * reps_s)}
+        del eng_s
+    else:
+        del eng
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- PPO legs: config[2] rollout + update (N = 1), train iteration (N > 1)
+    ppo_leg = None
+    if not args.no_extra_legs:
+        ppo_leg = ppo_iteration_leg(torch, dist, world, rank, local, args)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt, sample = cpu_leg(args.cpu_envs, args.cpu_steps, 2, threads)
-        cpu = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample, "seconds": round(dt, 2)}
+        port = CpuPort(args.cpu_envs, threads)
+        port.step(args.ref_inner)  # warm-up call
+        t0 = time.perf_counter()
+        n = 0
+        calls = max(1, args.cpu_steps // args.ref_inner)
+        for _ in range(calls):
+            n += port.step(args.ref_inner)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 2.0 * n / dt, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": port.describe(args.ref_inner) + f", {calls} calls",
+               "seconds": round(dt, 2), "python_reference": None if args.no_python_reference else python_reference_legs(args.py_seconds, threads)}
 
     if rank == 0:
         line = {
-            "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 bit-planes/int32 -> f32 obs",
+            "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bit-planes / int32 -> f32 obs (bit-exact); policy legs: fp32-grade 3-term split on tcgen05, 1e-5 rel on log-probs / values",
             "data": "synthetic",
-            "config": {"workload": f"config[3]: {E} mazes x 2 agents per GPU, side {SIDE} (4x default area), max_timestep {MAX_T}, uniform mask-legal "
-                                   "random actions sampled in-kernel, auto-reset on, mazes from the K1 generator",
-                       "envs_per_gpu": E, "side": SIDE, "max_timestep": MAX_T, "parallelism": f"env-shard x{world}",
-                       "l2": f"per-step traffic ({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB algorithmic) exceeds the 126 MB L2; no flush needed"},
+            "config": workload_config(E, world),
+            "timed_region": {"reps": reps, "steps_total": K * reps, "ms_total": ms_total, "resets_per_step": resets_per_step,
+                             "actions": "sampled in-kernel (Philox)", "mazes": "K1 generator"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "ms_per_step": ms_e2e / Ke,
+                    "ms_per_step": ms_e2e / Ke, "d2h_GBs_aggregate": d2h * world / (ms_e2e / Ke * 1e-3) / 1e9, "cpu_affinity": affinity,
                     "what": "pinned host actions -> device, mm_step_obs, full result (obs, masks, reward, done) -> pinned host, every step"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "mm::k_step_obs<false>", "bytes_per_launch": BYTES_PER_ENV_STEP * E, "launch_ms": ms_per_step,
-                         "peak_source": peak_src, "bytes_per_agent_step": BYTES_PER_ENV_STEP / 2},
+                         "traffic_source": traffic_src, "frac_dram": frac_dram,
+                         "kernel": "mm::k_step_obs<false, 1> (ncu: void mm::k_step_obs<0, 1>(mm::StepParams))", "bytes_per_launch": BYTES_PER_ENV_STEP * E,
+                         "launch_ms": ms_per_step, "peak_source": peak_src, "bytes_per_agent_step": BYTES_PER_ENV_STEP / 2},
             "cpu_baseline": cpu,
             "env_error_flags": errs,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if ppo_leg is not None:
+            line["rollout" if world == 1 else "train_iter"] = ppo_leg
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ppo_iteration_leg(torch, dist, world, rank, local, args):
+    """BASELINE config[2] per rank: 65,536 mazes x 128 steps of side 25 -- rollout (K4 + K2 per step, K3 at the end) and the 5 x 5 update.
+    Device-timed, max over ranks.  At N > 1 the update's gradient all-reduce (NCCL) is on the path and is timed separately."""
+    from marl_maze_b200.PPO import PPO
+    from marl_maze_b200.maze import Maze
+    from marl_maze_b200.maze_agent import Agent
+
+    E, T = args.ppo_envs, args.ppo_horizon
+    dev = f"cuda:{local}"
+    brain = PPO(agent_amount=2, batch_size=E * T - 5, lr=0.00014, epochs=1, verbose=False, model_path=None, horizon=T, device=dev)
+    agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
+    Maze(agents=agents, max_timestep=MAX_T, rand_sizes=True, rand_range=[13, 13], rand_start=True, num_envs=E, device=dev, seed=1, env_offset=rank * E)
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return out, float(ms.item())
+
+    roll_ms = upd_ms = None
+    stats = {}
+    for it in range(3):  # iteration 0 runs eagerly and warms up, 1 captures the rollout graph, 2 is the one reported
+        batch, roll_ms = timed(brain.get_batch)
+        stats = dict(brain.last_stats)
+        upd, upd_ms = timed(lambda: brain.update(batch))
+        del batch
+    steps = E * T * world
+    out = {"what": f"config[2]: {E} mazes x 2 agents per GPU, T = {T}, side 25: PPO rollout (K4 policy forward + fused sampling, K2 step + obs, per step; K3 GAE) "
+                   "then the 5 x 5 minibatch update (K5)",
+           "n_gpus": world, "envs_per_gpu": E, "horizon": T, "rollout_ms": roll_ms, "update_ms": upd_ms,
+           "rollout_agent_steps_per_s": 2.0 * steps / (roll_ms * 1e-3), "iteration_env_steps_per_s": steps / ((roll_ms + upd_ms) * 1e-3),
+           "allreduce_ms": getattr(brain, "last_allreduce_ms", None), "optimizer_steps": upd.get("steps") if isinstance(upd, dict) else None,
+           "episodes": stats.get("episodes"), "mem_GB": torch.cuda.max_memory_allocated() / 1e9}
+    try:
+        with open(os.path.join(ROOT, "profiles", "k4_tensor_pipe.json")) as f:
+            out["policy_gemm_tensor_pipe"] = json.load(f)
+    except Exception:
+        pass
+    return out
 
 
 def main():
@@ -292,9 +484,16 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="mazes per GPU")
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-envs", type=int, default=65536)
-    ap.add_argument("--cpu-steps", type=int, default=1200)  # ~10 s of CPU work on a 16-thread host
+    ap.add_argument("--cpu-steps", type=int, default=1280)  # ~10 s of CPU work on a 16-thread host
     ap.add_argument("--ref-envs", type=int, default=65536)
+    ap.add_argument("--ref-inner", type=int, default=64, help="consecutive steps per env inside one CPU call (one OpenMP region)")
+    ap.add_argument("--py-seconds", type=float, default=6.0, help="seconds per timed leg of the unmodified Python reference")
+    ap.add_argument("--ppo-envs", type=int, default=65536)
+    ap.add_argument("--ppo-horizon", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the rollout / train_iter / strong legs")
+    ap.add_argument("--no-spread", action="store_true", help="skip the phase spreader (all envs start at t = 0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -55,6 +55,9 @@ typedef struct mm_state {
 } mm_state;
 
 int mm_abi_version(void);
+/* SHA-256 (hex) of the sources this library was compiled from, as computed by marl_maze_b200/build.py; the Python loader compares it
+ * with the sources it finds next to the library and refuses (rebuilds) a stale build.  "unknown" when built by hand. */
+const char *mm_source_hash(void);
 const char *mm_error_string(int code);
 /* last CUDA error text seen by this library on the calling thread ("" if none) */
 const char *mm_last_cuda_error(void);

@@ -318,10 +318,21 @@ class PPO:
 
     # ------------------------------------------------------------------ checkpoint I/O (PPO.py:222-238, same format)
     def save_parameters(self):
+        """Same four keys as the reference (PPO.py:222-227).  Every tensor is saved as a CPU tensor: the reference loads with a bare
+        torch.load(MODEL_PATH) (PPO.py:231), which on the CPU-only machine it normally runs on cannot deserialise CUDA storages."""
         if not self.model_path:
             return
-        torch.save({"actor": self.actor.state_dict(), "critic": self.critic.state_dict(),
-                    "actor_optim": self.actor_optim.state_dict(), "critic_optim": self.critic_optim.state_dict()}, self.model_path)
+
+        def cpu(o):
+            if torch.is_tensor(o):
+                return o.detach().cpu()
+            if isinstance(o, dict):
+                return {k: cpu(v) for k, v in o.items()}
+            if isinstance(o, (list, tuple)):
+                return type(o)(cpu(v) for v in o)
+            return o
+        torch.save({"actor": cpu(self.actor.state_dict()), "critic": cpu(self.critic.state_dict()),
+                    "actor_optim": cpu(self.actor_optim.state_dict()), "critic_optim": cpu(self.critic_optim.state_dict())}, self.model_path)
 
     def load_parameters(self):
         if self.model_path and os.path.exists(self.model_path):

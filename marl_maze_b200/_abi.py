@@ -7,7 +7,7 @@ import os
 from . import build as _build
 
 EXPORTS = [
-    "mm_abi_version", "mm_error_string", "mm_last_cuda_error",
+    "mm_abi_version", "mm_source_hash", "mm_error_string", "mm_last_cuda_error",
     "mm_sizeof_pool_grid", "mm_sizeof_pool_d2e", "mm_sizeof_pool_hdr", "mm_sizeof_env_grid", "mm_sizeof_env_hdr",
     "mm_sizeof_env_episode", "mm_sizeof_agent_a", "mm_sizeof_agent_b", "mm_sizeof_finalize_scratch", "mm_sizeof_generate_scratch",
     "mm_init_state", "mm_load_layouts", "mm_generate", "mm_generate_ex", "mm_reset", "mm_step_obs",
@@ -38,19 +38,28 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("MARL_MAZE_LIB", _build.LIB)  # override: A/B-testing kernel variants
-    if not os.path.exists(path):
-        # sources present (a checkout): build in-tree; otherwise fail loudly -- there is no other code path
-        try:
-            path = _build.build()
-        except Exception as e:  # noqa: BLE001
-            raise MMError(f"libmarl_maze_b200.so is missing and could not be built ({e}); "
-                          "run `python -m marl_maze_b200.build` (needs nvcc). There is no CPU fallback.") from e
+    path = os.environ.get("MARL_MAZE_LIB")  # override: A/B-testing kernel variants (used as it is)
+    if path is None:
+        path = _build.LIB
+        # A checkout: (re)build in-tree when the library is missing OR older than any source / header -- a stale .so that still exports
+        # every symbol would otherwise silently run the old kernels.  build() is a no-op when the library is up to date.
+        if not os.path.exists(path) or _build.needs_build():
+            try:
+                path = _build.build()
+            except Exception as e:  # noqa: BLE001
+                if not os.path.exists(path):
+                    raise MMError(f"libmarl_maze_b200.so is missing and could not be built ({e}); "
+                                  "run `python -m marl_maze_b200.build` (needs nvcc). There is no CPU fallback.") from e
+                raise MMError(f"libmarl_maze_b200.so is older than its sources and could not be rebuilt ({e}); rebuild it with "
+                              "`python -m marl_maze_b200.build`, or point MARL_MAZE_LIB at the library you mean to run.") from e
+    elif not os.path.exists(path):
+        raise MMError(f"MARL_MAZE_LIB={path} does not exist")
     L = C.CDLL(path)
     vp, i32, u64, u32, sz = C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_size_t
     st = C.POINTER(MMState)
     sig = {
         "mm_abi_version": (i32, []),
+        "mm_source_hash": (C.c_char_p, []),
         "mm_error_string": (C.c_char_p, [i32]),
         "mm_last_cuda_error": (C.c_char_p, []),
         "mm_sizeof_pool_grid": (sz, [i32, i32]), "mm_sizeof_pool_d2e": (sz, [i32, i32]), "mm_sizeof_pool_hdr": (sz, [i32]),

@@ -30,12 +30,39 @@ def sources():
     return srcs, hdrs
 
 
+def source_hash() -> str:
+    """SHA-256 over the names and contents of every source and header the library is built from (compiled in as MM_SRC_HASH)."""
+    import hashlib
+    h = hashlib.sha256()
+    srcs, hdrs = sources()
+    for f in sorted(srcs + hdrs):
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def built_hash(path: str | None = None) -> str | None:
+    """The hash a built library reports (mm_source_hash), or None when it cannot be loaded / predates the export."""
+    import ctypes
+    try:
+        lib = ctypes.CDLL(path or LIB)
+        fn = lib.mm_source_hash
+        fn.restype = ctypes.c_char_p
+        return fn().decode()
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def needs_build() -> bool:
+    """True when the library is missing or was compiled from other sources than the ones present (content hash, not mtime: the
+    snapshot that travels to the GPU box does not keep modification times)."""
     if not os.path.exists(LIB):
         return True
-    srcs, hdrs = sources()
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in srcs + hdrs)
+    srcs, _ = sources()
+    if not srcs:
+        return False   # a binary-only install: nothing to compare against
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
@@ -45,7 +72,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
         return LIB
     srcs, _ = sources()
     tmp = LIB + f".tmp{os.getpid()}"
-    cmd = [_nvcc()] + FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+    cmd = [_nvcc()] + FLAGS + [f'-DMM_SRC_HASH="{source_hash()}"'] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -53,6 +53,10 @@ static StepParams make_params(const mm_state* st) {
 extern "C" {
 
 int mm_abi_version(void) { return 1; }
+#ifndef MM_SRC_HASH
+#define MM_SRC_HASH "unknown"
+#endif
+const char* mm_source_hash(void) { return MM_SRC_HASH; }
 const char* mm_error_string(int code) {
     switch (code) {
         case MM_OK: return "ok";

@@ -17,12 +17,14 @@
 
 namespace mm {
 
+// Block = 2 warps, 10 blocks per SM (96 registers): measured on B200 against 128-thread blocks x 5 (same 20 warps per SM): 0.1948 vs
+// 0.1970 ms per 1 Mi-maze launch (profiles/r02b_k2_variants.jsonl) -- finer-grained block turnover.
 #ifndef MM_K2_THREADS
-#define MM_K2_THREADS 128
+#define MM_K2_THREADS 64
 #endif
 constexpr int kThreads = MM_K2_THREADS;
 #ifndef MM_K2_MINBLOCKS
-#define MM_K2_MINBLOCKS 5
+#define MM_K2_MINBLOCKS (640 / MM_K2_THREADS)
 #endif
 #ifndef MM_K2_MINBLOCKS2
 #define MM_K2_MINBLOCKS2 3

@@ -19,6 +19,14 @@ import torch
 from .engine import MazeEngine
 
 DELTAS = [(0, -1), (1, 0), (0, 1), (-1, 0)]  # N, E, S, W
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
 
 
 class Maze:
@@ -55,17 +63,21 @@ class Maze:
             self.refill_pool()
         return self.engine
 
-    def _pool_args(self):
-        # maze ids are global and never reused: (generation, global env slot) -> results do not depend on how envs are sharded
-        id_base = (self._generation * (1 << 26) + self.env_offset * self.pool_episodes) & 0xFFFFFFFF
-        return dict(side_range=self.side_range, rand_start=self.rand_start, difficulty=self.difficulty, id_base=id_base, id_mod=self.num_envs,
-                    id_mul=self.pool_episodes)
+    def _pool_args(self, generation: Optional[int] = None):
+        """K1 arguments of pool refill number `generation`.  A maze is keyed by (64-bit seed, 32-bit id): the id is the maze's GLOBAL slot
+        (global env, episode within the pool) -- so results do not depend on how envs are sharded over ranks -- and the refill counter is
+        folded into the SEED (splitmix64), so no (seed, id) pair ever repeats across refills: a 32-bit id alone wrapped after 64 refills."""
+        g = self._generation if generation is None else generation
+        if (self.env_offset + self.num_envs) * self.pool_episodes > 1 << 32:
+            raise ValueError("(env_offset + num_envs) * pool_episodes must fit the 32-bit maze id")
+        return dict(seed=(self.seed + _splitmix64(g)) & _M64 if g else self.seed & _M64, side_range=self.side_range, rand_start=self.rand_start,
+                    difficulty=self.difficulty, id_base=self.env_offset * self.pool_episodes, id_mod=self.num_envs, id_mul=self.pool_episodes)
 
     def prefetch_pool(self):
         """Start generating the NEXT pool (the one the next refill_pool() would build) on a side stream, into staging buffers."""
         if self.engine is None or getattr(self, "_staged", None) == (id(self.engine), self._generation):
             return
-        self.engine.generate_staged(self.seed, **self._pool_args())
+        self.engine.generate_staged(**self._pool_args())
         self._staged = (id(self.engine), self._generation)
 
     def refill_pool(self):
@@ -74,7 +86,7 @@ class Maze:
         if getattr(self, "_staged", None) == (id(eng), self._generation):
             eng.commit_staged()       # built ahead by prefetch_pool(): same ids, same mazes
         else:
-            eng.generate(self.seed, **self._pool_args())
+            eng.generate(**self._pool_args())
         self._staged = None
         eng.env_episode.zero_()
         self._generation += 1

@@ -63,6 +63,7 @@ def load_lib():
         "obatch_errors": (i32, [vp]),
         "obatch_random_actions": (None, [vp, pu8, pu8, C.POINTER(C.c_uint64)]),
         "obatch_run_random": (C.c_long, [vp, i32, i32, u64, pf, pu8, C.POINTER(C.c_double)]),
+        "obatch_run_random_ex": (C.c_long, [vp, i32, i32, i32, u64, pf, pu8, C.POINTER(C.c_double)]),
         "obatch_guided_actions": (None, [vp, pu8, pu8, C.POINTER(C.c_uint64), i32, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -215,7 +216,8 @@ class OracleBatch:
                                        int(p_follow * 1024), int(p_mark * 1024), self.threads)
         return act
 
-    def run_random(self, steps: int, seed: int = 0) -> int:
-        """CPU-baseline driver: `steps` uniform-legal-random steps per env with auto-reset, env-major, OpenMP over envs."""
+    def run_random(self, steps: int, seed: int = 0, stagger: int = 0) -> int:
+        """CPU-baseline driver: `steps` uniform-legal-random steps per env with auto-reset, env-major, OpenMP over envs.
+        stagger > 0: env e runs (e * 2654435761 mod 2^32) mod stagger steps instead (spreads episode phases).  Returns env-steps run."""
         rs = C.c_double()
-        return int(self.lib.obatch_run_random(self.h, int(steps), self.threads, seed, _p(self.obs, C.c_float), _p(self.masks, C.c_uint8), C.byref(rs)))
+        return int(self.lib.obatch_run_random_ex(self.h, int(steps), int(stagger), self.threads, seed, _p(self.obs, C.c_float), _p(self.masks, C.c_uint8), C.byref(rs)))

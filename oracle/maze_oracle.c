@@ -752,13 +752,19 @@ void obatch_guided_actions(OBatch *b, const uint8_t *masks, uint8_t *actions, ui
  * case for the CPU), OpenMP over envs.  Observations are produced every step exactly as the reference does and
  * left in the per-env slot of `obs`.  Returns the number of env-steps executed.
  * ------------------------------------------------------------------------------------------------ */
-long obatch_run_random(OBatch *b, int steps, int threads, uint64_t seed, float *obs, uint8_t *masks, double *reward_sum) {
+/* stagger > 0: env e runs (e * 2654435761 mod 2^32) mod stagger steps instead of `steps` -- the benchmark's phase spreader: after it the
+ * envs sit at uniformly spread episode times, so a timed window sees the steady-state rate of truncations and resets (bench.py does the
+ * same on the GPU with masked resets). */
+long obatch_run_random_ex(OBatch *b, int steps, int stagger, int threads, uint64_t seed, float *obs, uint8_t *masks, double *reward_sum) {
     double rs = 0.0;
-#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 8) reduction(+ : rs)
+    long total = 0;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 8) reduction(+ : rs, total)
     for (int e = 0; e < b->E; e++) {
         uint64_t s = (seed + (uint64_t)e + 1) * 0x9E3779B97F4A7C15ull;
         float *o = obs + (size_t)e * 2 * OBS_DIM; uint8_t *mk = masks + (size_t)e * 12;
-        for (int t = 0; t < steps; t++) {
+        const int n_steps = stagger > 0 ? (int)(((uint32_t)e * 2654435761u) % (uint32_t)stagger) : steps;
+        total += n_steps;
+        for (int t = 0; t < n_steps; t++) {
             int act[4];
             for (int a = 0; a < 2; a++) {
                 int legal[5], n = 0; for (int k = 0; k < 5; k++) if (mk[a * 6 + k]) legal[n++] = k;
@@ -773,5 +779,8 @@ long obatch_run_random(OBatch *b, int steps, int threads, uint64_t seed, float *
         }
     }
     if (reward_sum) *reward_sum = rs;
-    return (long)b->E * steps;
+    return total;
+}
+long obatch_run_random(OBatch *b, int steps, int threads, uint64_t seed, float *obs, uint8_t *masks, double *reward_sum) {
+    return obatch_run_random_ex(b, steps, 0, threads, seed, obs, masks, reward_sum);
 }

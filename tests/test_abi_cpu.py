@@ -38,6 +38,21 @@ def test_size_helpers_and_error_strings():
     assert L.mm_gae(None, None, None, None, None, None, 1, 1, 0.99, 0.95, None) == 1
 
 
+def test_loader_detects_a_stale_library():
+    """a library compiled from other sources than the ones present must not be used silently -- the compiled-in content hash
+    (mm_source_hash) is compared with the sources' hash on load."""
+    from marl_maze_b200 import _abi, build
+    build.build()
+    assert build.built_hash() == build.source_hash() and not build.needs_build()
+    assert _abi.lib().mm_source_hash().decode() == build.source_hash()
+    real = build.source_hash
+    try:
+        build.source_hash = lambda: "0" * 64          # pretend a source changed
+        assert build.needs_build()
+    finally:
+        build.source_hash = real
+
+
 def test_product_path_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "marl_maze_b200")
     for dp, _, fs in os.walk(pkg):
