@@ -344,6 +344,10 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
         cw[1] = (wl5 >> 6) & 0x1fu; lat[1] = (lat5 >> 6) & 0xfu; ownm[1] = (own5 >> 6) & 0xfu; othm[1] = (oth5 >> 6) & 0xfu;
         cw[3] = rev5(wl5); lat[3] = rev5(lat5) & 0xfu; ownm[3] = rev5(own5) & 0xfu; othm[3] = rev5(oth5) & 0xfu;
         const uint32_t own_open = ((wl5 >> 5) & 1u) ^ 1u;
+        // An agent standing INSIDE a wall got there through an illegal (masked-off) move: the reference has no wall check
+        // (maze.py:137-155) and neither has this kernel -- positions, marks and observations keep following the reference -- but the
+        // env's error flag is raised: the exit-route bookkeeping (R2 in DESIGN.md) is only defined on open cells.
+        if (pass == 0 && !kResetOnly && act && !own_open) err = 1;
         const uint32_t cell_is_own = ((h5 >> 5) & 1u) & ((((l5 >> 5) & 1u) ^ ua) ^ 1u);  // layout[y][x] == tag
 
         int n[4], de[4];
@@ -491,6 +495,7 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
     }
 
     // ---------------------------------------------------------------- state write-back
+    if (!kResetOnly) err |= __shfl_xor_sync(kFull, err, 1);   // either agent's illegal move flags the env (agent 0's lane writes the header)
     if (valid && (!kResetOnly || want_reset)) {
         p.agent_a[g] = pack_agent(me);
         p.agent_b[g] = me.time;

@@ -533,6 +533,9 @@ static int single_agent_step(OMaze *m, OAgent *a, int move, int mark) { /* maze.
     int got_key = 0;
     a->current_t = m->current_t;
     if (mark == 1) { LAY(m, a->x, a->y) = (uint8_t)a->tag; a->has_last_mark = 1; a->lm_x = a->x; a->lm_y = a->y; }
+    /* moves outside 0..4 are outside the reference's domain (it would walk like move % 4 and then raise IndexError in get_memory,
+     * maze_agent.py:289-294): treated as `stop` + error flag, the same convention as the out-of-bounds move below */
+    if (move < 0 || move > 4) { m->error |= 1; return 0; }
     if (move != 4) {
         int direction = (move + a->direction) % 4;
         int nx = a->x + DELTAS[direction][0], ny = a->y + DELTAS[direction][1];

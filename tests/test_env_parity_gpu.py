@@ -215,3 +215,75 @@ def test_rectangular_mazes_injected():
     for ds in [(4, 9), (12, 5)]:
         cfg = dict(rand_sizes=False, rand_start=True, difficulty=2, default_size=ds)
         _run_vs_oracle(E=96, K=10, T=260, max_t=90, cfg=cfg, p_follow=0.8, p_mark=0.4)
+
+
+def test_illegal_actions_follow_the_stated_convention():
+    """SURVEY H3 / VERDICT r1 weak #1a: what happens on input the reference's masks forbid, through the C ABI, against the oracle.
+      * a move that would leave the grid (maze.py:141-145 prints, then indexes out of range): `stop` + the env's error flag;
+      * a move code above 4 (the reference would IndexError in get_memory): `stop` + error flag;
+      * an in-bounds move INTO A WALL: reproduced like the reference, which has no wall check (the agent stands in the wall, marks
+        overwrite wall cells, observations follow) -- bit-exact against the oracle -- and the error flag is raised.
+    Marks ordered with an illegal move are still applied (maze.py:132-134 runs before the move).  Envs fed legal actions keep err = 0."""
+    E, max_t = 512, 400
+    cfg = dict(difficulty=1, rand_start=True, rand_sizes=True, rand_range=(12, 13), default_size=(4, 4))
+    mazes = _oracle_pool(E, 1, cfg, seed0=4000)
+    S = max(max(m["width"], m["height"]) for m in mazes)
+    ob = OracleBatch(E, E, max_timestep=max_t, threads=8)
+    for p, m in enumerate(mazes):
+        ob.set_pool_maze(p, m)
+    eng = _engine(E, smax=S, max_timestep=max_t, pool_size=E)
+    eng.load_layouts(0, mazes)
+    g_obs, g_masks = eng.reset(); o_obs, o_masks = ob.reset_all()
+    _assert_obs_equal(g_obs.cpu().numpy(), o_obs, "reset")
+    rng = np.random.default_rng(17)
+    rs = np.arange(1, E + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    DX, DY = [0, 1, 0, -1], [-1, 0, 1, 0]
+    kind = np.zeros(E, np.int32)            # 0 legal, 1 out of bounds, 2 code > 4, 3 into a wall
+    for t in range(6):                      # a few legal steps first so that agents have left their start cells
+        act = ob.random_actions(rs)
+        eng.step(torch.from_numpy(act).cuda(), auto_reset=False); ob.step(act, auto_reset=False)
+    ag = ob.agents(); act = ob.random_actions(rs)
+    for e in range(E):
+        m = mazes[e]; lay = ob.layout(e); W, H = m["width"], m["height"]
+        if ag[e, :, 3].any():               # somebody already knows the exit: keep this env legal (route bookkeeping is defined on open cells only)
+            continue
+        x, y, d = int(ag[e, 0, 0]), int(ag[e, 0, 1]), int(ag[e, 0, 2])
+        choice = e % 4
+        if choice == 1:                     # out of bounds, if agent 0 stands on the border
+            for mv in range(4):
+                nd = (mv + d) % 4; nx, ny = x + DX[nd], y + DY[nd]
+                if not (0 <= nx < W and 0 <= ny < H):
+                    act[e, 0] = [mv, 1]; kind[e] = 1; break
+        elif choice == 2:
+            act[e, 0] = [5 + int(rng.integers(0, 200)), int(rng.integers(0, 2))]; kind[e] = 2
+        elif choice == 3:                   # in-bounds wall
+            for mv in range(4):
+                nd = (mv + d) % 4; nx, ny = x + DX[nd], y + DY[nd]
+                if 0 <= nx < W and 0 <= ny < H and lay[ny, nx] == 1:
+                    act[e, 0] = [mv, int(rng.integers(0, 2))]; kind[e] = 3; break
+    assert (kind == 1).sum() > 5 and (kind == 2).sum() > 50 and (kind == 3).sum() > 50, np.bincount(kind)
+    g = eng.step(torch.from_numpy(act).cuda(), auto_reset=False)
+    o = ob.step(act, auto_reset=False)
+    ga, oa = eng.agents(), ob.agents()
+    # an agent may SIGHT the exit from inside a wall; from then on its route bookkeeping is outside R2's domain: compare the others
+    keep = ~(oa[:, :, 3].any(1) & (kind == 3))
+    assert keep.sum() > E - 40
+    _assert_obs_equal(g[0].cpu().numpy()[keep], o[0][keep], "illegal step")
+    assert np.array_equal(g[1].cpu().numpy()[keep], o[1][keep]) and np.array_equal(g[2].cpu().numpy(), o[2]) and np.array_equal(g[3].cpu().numpy(), o[3])
+    assert np.array_equal(ga[keep], oa[keep]), np.argwhere(ga != oa)[:5]
+    err = eng.envs()[:, 6]
+    assert np.array_equal(err != 0, kind != 0), (np.bincount(kind), np.bincount(kind[err != 0], minlength=4))
+    # stop semantics: position, facing and move memory of agent 0 unchanged by kinds 1 and 2; kind 3 really stands in the wall
+    for e in np.flatnonzero((kind == 1) | (kind == 2)):
+        assert tuple(ga[e, 0, :3]) == tuple(ag[e, 0, :3])
+    for e in np.flatnonzero(kind == 3)[:50]:
+        lay = mazes[e]["layout"]
+        assert lay[ga[e, 0, 1], ga[e, 0, 0]] == 1
+    # the wall-walkers keep following the reference afterwards (three more steps of whatever the masks now allow), flags stay raised
+    for t in range(3):
+        act = ob.random_actions(rs)
+        g = eng.step(torch.from_numpy(act).cuda(), auto_reset=False); o = ob.step(act, auto_reset=False)
+        keep = ~ob.agents()[:, :, 3].any(1)      # compare where nobody has learnt the exit meanwhile
+        _assert_obs_equal(g[0].cpu().numpy()[keep], o[0][keep], f"after illegal step +{t}")
+        assert np.array_equal(g[1].cpu().numpy()[keep], o[1][keep])
+    assert np.array_equal(eng.envs()[:, 6] != 0, kind != 0)

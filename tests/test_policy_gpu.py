@@ -93,3 +93,46 @@ def test_sampling_distribution_chi_square():
     pm = 1 / (1 + np.exp(-float(mk[0, 0])))
     z = (act[:, 1].mean() - pm) / np.sqrt(pm * (1 - pm) / n)
     assert abs(z) < 4.5, (z, pm)
+
+
+def _ppo_pth_nets():
+    """The reference's shipped checkpoint (tests/golden/kat5_ppo_pth.npz, recorded by tools/make_golden.py --kat5)."""
+    from marl_maze_b200.networks import Actor, Critic
+    Z = np.load(os.path.join(GOLDEN, "kat5_ppo_pth.npz"))
+    actor = Actor([264, 264, 264]).cuda(); critic = Critic(2, hidden_sizes=[64, 64]).cuda()
+    actor.load_state_dict({k[6:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("actor/")})
+    critic.load_state_dict({k[7:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("critic/")})
+    return Z, actor, critic
+
+
+@pytest.mark.parametrize("tc", [False, True], ids=["simt_fp32", "tcgen05"])
+def test_kat5_reference_checkpoint_through_mm_policy_forward(tc):
+    """SURVEY 8c KAT(5) through the C ABI: the reference's own PPO.pth, packed by policy.pack_weights, evaluated by mm_policy_forward on
+    the four facing one-hots -- against the logits the REFERENCE's networks.py computes from the same file (and the survey's printed
+    values) -- and on 192 recorded observations with the recorded actions: logits, values and joint log-probs (PPO.get_log_probs)."""
+    from marl_maze_b200.policy import PolicyRunner
+    Z, actor, critic = _ppo_pth_nets()
+    # --- the four facings.  Rows are agents; the kernel takes [E,2,65], so the 4 probes are laid out as 2 envs x 2 agents
+    x = torch.from_numpy(Z["kat5/obs"]).cuda().view(2, 2, 65).contiguous()
+    masks = torch.ones(2, 2, 6, dtype=torch.uint8, device="cuda")
+    run = PolicyRunner(actor, critic, 2, "cuda", tensor_cores=tc)
+    logits = torch.zeros(2, 2, 6, device="cuda")
+    run.forward(x, masks, logits=logits)
+    lg = logits.cpu().numpy().reshape(4, 6)
+    assert np.allclose(lg[:, :5], Z["kat5/move_logits"], **TOL_LOGITS[tc]) and np.allclose(lg[:, 5], Z["kat5/mark_logits"], **TOL_LOGITS[tc])
+    assert np.allclose(lg[0, :5], [5.7483, -0.3037, -7.4898, 10.1972, -9.9180], atol=2e-4)                 # SURVEY 8c KAT(5), as printed there
+    assert np.allclose(1 / (1 + np.exp(-lg[:, 5])), [.5609, .5664, .5459, .5300], atol=2e-4)
+    # --- recorded observations / actions
+    obs, mk, acts = Z["trace/obs"], Z["trace/masks"], Z["trace/actions"]
+    E = obs.shape[0]
+    run = PolicyRunner(actor, critic, E, "cuda", tensor_cores=tc)
+    logits = torch.zeros(E, 2, 6, device="cuda")
+    _, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(mk).cuda(), actions_in=torch.from_numpy(acts).cuda(), logits=logits)
+    lg = logits.cpu().numpy()
+    assert np.allclose(lg[:, :, :5].reshape(-1, 5), Z["trace/move_logits"], **TOL_LOGITS[tc])
+    assert np.allclose(lg[:, :, 5].reshape(-1), Z["trace/mark_logits"], **TOL_LOGITS[tc])
+    assert np.allclose(val.cpu().numpy(), Z["trace/values"], **TOL)
+    want = Z["trace/log_probs"].sum(1)
+    fin = np.isfinite(want)
+    got = logp.cpu().numpy()
+    assert np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], want[fin], **TOL)

@@ -88,19 +88,40 @@ def test_train_epoch_and_checkpoint_round_trip(tmp_path):
 
 
 def test_reference_checkpoint_drives_the_kernel_policy(tmp_path):
-    """Config 1 flavour: the shipped PPO.pth (when present) through the fused policy kernel on one maze."""
-    src = "/root/reference/PPO.pth"
-    if not os.path.exists(src):
-        pytest.skip("reference checkpoint not on this box")
-    import shutil
-    shutil.copy(src, tmp_path / "PPO.pth")
-    brain, agents, maze = _make(1, tmp_path)
+    """Config 1 flavour: the reference's shipped PPO.pth (its tensors travel as tests/golden/kat5_ppo_pth.npz) written as a checkpoint in
+    the reference's format, picked up by PPO.__init__ (PPO.py:31), and driven through Agent.get_action + Maze.step on ONE maze -- and
+    through the batched kernel policy (PolicyRunner) on the same observations: the kernel's logits are the checkpoint's."""
+    from golden_util import GOLDEN
+    from marl_maze_b200.PPO import PPO
+    from marl_maze_b200.policy import PolicyRunner
+    Z = np.load(os.path.join(GOLDEN, "kat5_ppo_pth.npz"))
+    seed_brain = PPO(agent_amount=2, lr=0.00014, verbose=False, model_path=str(tmp_path / "PPO.pth"))
+    seed_brain.actor.load_state_dict({k[6:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("actor/")})
+    seed_brain.critic.load_state_dict({k[7:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("critic/")})
+    seed_brain.save_parameters()
+    brain, agents, maze = _make(1, tmp_path)           # loads tmp_path/PPO.pth
+    assert torch.equal(brain.actor.move_head.weight.cpu(), torch.from_numpy(Z["actor/move_head.weight"]))
     obs, masks = maze.reset()
-    for _ in range(50):
+    run = PolicyRunner(brain.actor, brain.critic, 1, "cuda")
+    seen = 0
+    for _ in range(60):
+        o_t = torch.tensor(obs, dtype=torch.float32, device="cuda").view(1, 2, 65)
+        m_t = torch.tensor(masks, dtype=torch.uint8, device="cuda").view(1, 2, 6)
+        logits = torch.zeros(1, 2, 6, device="cuda")
+        k_act, _, k_val = run.forward(o_t, m_t, logits=logits)
+        with torch.no_grad():
+            mv, mk = brain.actor(o_t.view(2, 65))
+            v = brain.critic(o_t)
+        assert torch.allclose(logits[0, :, :5], mv, rtol=1e-5, atol=8e-6) and torch.allclose(logits[0, :, 5], mk.view(-1), rtol=1e-5, atol=8e-6)
+        assert torch.allclose(k_val, v.view(-1), rtol=1e-5, atol=2e-6)
+        assert all(masks[i][int(k_act[0, i, 0])] for i in range(2))      # the kernel's sampled moves are legal
         acts = [agents[i].get_action(obs[i], masks[i])[0] for i in range(2)]
+        assert all(masks[i][acts[i][0]] for i in range(2))
         obs, masks, r, d = maze.step(acts)
+        seen += 1
         if d:
             obs, masks = maze.reset()
+    assert seen == 60
 
 
 def test_reference_main_py_flow_single_env_train(tmp_path):

@@ -82,6 +82,28 @@ def test_reference_checkpoint_loads_and_matches_kat5():
     assert np.allclose(torch.sigmoid(mk).reshape(-1).numpy(), [.5609, .5664, .5459, .5300], atol=2e-4)
 
 
+def test_kat5_fixture_matches_reference_outputs_on_cpu():
+    """tests/golden/kat5_ppo_pth.npz (the reference's PPO.pth and what the reference's networks.py computes from it, recorded by
+    tools/make_golden.py --kat5) through this repo's torch modules and the numpy oracle: the fixture the GPU test drives the kernels with."""
+    from marl_maze_b200.networks import Actor, Critic
+    Z = np.load(os.path.join(GOLDEN, "kat5_ppo_pth.npz"))
+    asd = {k[6:]: Z[k] for k in Z.files if k.startswith("actor/")}; csd = {k[7:]: Z[k] for k in Z.files if k.startswith("critic/")}
+    actor = Actor([264, 264, 264]); critic = Critic(2, hidden_sizes=[64, 64])
+    actor.load_state_dict({k: torch.from_numpy(v) for k, v in asd.items()}); critic.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+    with torch.no_grad():
+        mv4, mk4 = actor(torch.from_numpy(Z["kat5/obs"]))
+        mv, mk = actor(torch.from_numpy(Z["trace/obs"].reshape(-1, 65)))
+        val = critic(torch.from_numpy(Z["trace/obs"]))
+    assert np.allclose(mv4.numpy(), Z["kat5/move_logits"], rtol=1e-6, atol=1e-6) and np.allclose(mk4.numpy().reshape(-1), Z["kat5/mark_logits"], rtol=1e-6, atol=1e-6)
+    assert np.allclose(mv4[0].numpy(), [5.7483, -0.3037, -7.4898, 10.1972, -9.9180], atol=2e-4)
+    assert np.allclose(mv.numpy(), Z["trace/move_logits"], rtol=1e-6, atol=2e-6) and np.allclose(val.numpy().reshape(-1), Z["trace/values"], rtol=1e-6, atol=1e-6)
+    omv, omk = po.actor_forward(asd, Z["trace/obs"].reshape(-1, 65))
+    assert np.allclose(omv, Z["trace/move_logits"], rtol=1e-5, atol=2e-6) and np.allclose(omk.reshape(-1), Z["trace/mark_logits"], rtol=1e-5, atol=2e-6)
+    if os.path.exists("/root/reference/PPO.pth"):   # the fixture IS the checkpoint
+        sd = torch.load("/root/reference/PPO.pth", map_location="cpu")
+        assert all(np.array_equal(sd["actor"][k].numpy(), v) for k, v in asd.items()) and all(np.array_equal(sd["critic"][k].numpy(), v) for k, v in csd.items())
+
+
 def test_actor_embedding_dedup_matches_per_row_evaluation():
     """Large faithful batches evaluate projection+attention once per distinct obs[:, 0:4] prefix; values and gradients must equal
     the plain per-row evaluation."""

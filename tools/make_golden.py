@@ -142,7 +142,7 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__" and "--ppo" not in sys.argv and "--upd" not in sys.argv:
+if __name__ == "__main__" and "--ppo" not in sys.argv and "--upd" not in sys.argv and "--kat5" not in sys.argv:
     main()
 
 
@@ -263,3 +263,47 @@ if __name__ == "__main__" and "--ppo" in sys.argv:
     make_ppo_kats()
 if __name__ == "__main__" and "--upd" in sys.argv:
     make_upd_kats()
+
+
+def make_kat5():
+    """SURVEY 8c KAT(5) as a fixture that travels: the reference's shipped checkpoint (PPO.pth: actor + critic tensors, fp32) and what the
+    REFERENCE's own networks.py computes from it -- on the four facing one-hots (the survey's KAT) and on 192 recorded observations --
+    plus the log-probs of the recorded actions through the reference's PPO.get_log_probs.  Lets the `-m gpu` tests push the real
+    checkpoint through mm_policy_forward on a box that has neither /root/reference nor PPO.pth."""
+    import contextlib, io
+    import torch
+    rh.load_reference()
+    sys.path.insert(0, rh.REFERENCE_DIR)
+    cwd = os.getcwd(); os.chdir("/tmp")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import PPO as ref_ppo, networks as ref_net
+    finally:
+        os.chdir(cwd); sys.path.remove(rh.REFERENCE_DIR)
+    sd = torch.load(os.path.join(rh.REFERENCE_DIR, "PPO.pth"), map_location="cpu")
+    actor = ref_net.Actor([264, 264, 264]); critic = ref_net.Critic(2, hidden_sizes=[64, 64])
+    actor.load_state_dict(sd["actor"]); critic.load_state_dict(sd["critic"])
+    out = {f"actor/{k}": v.numpy().astype(np.float32) for k, v in sd["actor"].items()}
+    out.update({f"critic/{k}": v.numpy().astype(np.float32) for k, v in sd["critic"].items()})
+    x = torch.zeros(4, 65); x[torch.arange(4), torch.arange(4)] = 1
+    z = np.load(os.path.join(OUT, "env_traces.npz"))
+    obs = z["guided_a/step_obs"][:192]; masks = z["guided_a/step_masks"][:192].astype(bool); acts = z["guided_a/actions"][1:193]
+
+    class Holder:
+        pass
+    h = Holder(); h.actor = actor
+    with torch.no_grad():
+        mv4, mk4 = actor(x)
+        mv, mk = actor(torch.from_numpy(obs.reshape(-1, 65)))
+        val = critic(torch.from_numpy(obs))
+        lps = [ref_ppo.PPO.get_log_probs(h, i, torch.from_numpy(obs), torch.from_numpy(acts.astype(np.float32)), torch.from_numpy(masks)).numpy() for i in range(2)]
+    out["kat5/obs"] = x.numpy(); out["kat5/move_logits"] = mv4.numpy(); out["kat5/mark_logits"] = mk4.numpy().reshape(-1)
+    out["trace/obs"] = obs; out["trace/masks"] = masks.astype(np.uint8); out["trace/actions"] = acts
+    out["trace/move_logits"] = mv.numpy(); out["trace/mark_logits"] = mk.numpy().reshape(-1); out["trace/values"] = val.numpy().reshape(-1)
+    out["trace/log_probs"] = np.stack(lps, 1)
+    np.savez_compressed(os.path.join(OUT, "kat5_ppo_pth.npz"), **out)
+    print("kat5_ppo_pth.npz", os.path.getsize(os.path.join(OUT, "kat5_ppo_pth.npz")), mv4.numpy()[0], torch.sigmoid(mk4).reshape(-1).numpy())
+
+
+if __name__ == "__main__" and "--kat5" in sys.argv:
+    make_kat5()
