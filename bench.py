@@ -11,8 +11,8 @@ rank owns its own shard (no data-path collective).
 
 One "step" = one pass of the hot path over all envs of the rank (one K2 launch).
   value   : whole-job agent-steps/s with everything resident in HBM (actions are sampled inside the kernel).  The timed
-            region is `reps` back-to-back blocks of exactly K steps (reps chosen so that it lasts >= 60 ms: the clock sampler
-            needs more than a 4 ms window); ms_per_step is the mean over all of them.
+            region is `reps` back-to-back blocks of exactly K steps (reps chosen so that it lasts >= 400 ms: the clock sampler
+            needs many NVML round trips); ms_per_step is the mean over all of them.
   e2e     : the same through the host-buffer API: every step copies the step's actions from pinned host memory to the device
             and the step's full result (obs, masks, reward, done) back to pinned host memory.
   roofline: algorithmic bytes per launch (685 + ceil(S^2/4) B per env-step) / mean launch duration measured with
@@ -46,7 +46,7 @@ MAX_T = 1200            # main.py:20
 ENVS_PER_GPU = 1 << 20
 BYTES_PER_ENV_STEP = 685 + (SIDE * SIDE + 3) // 4   # SURVEY 8d -> 1286 B at S=49 (643 B per agent-step)
 FALLBACK_HBM_GBS = 6650.0
-MIN_TIMED_MS = 60.0
+MIN_TIMED_MS = 400.0   # NVML clock queries take tens of ms each while the GPU is busy: a 60 ms region got ONE sample
 STAGGER_HASH = 2654435761
 
 
@@ -69,7 +69,7 @@ def workload_config(envs_per_gpu: int, world: int) -> dict:
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index: int, period=0.004):
+    def __init__(self, index: int, period=0.002):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()

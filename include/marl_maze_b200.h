@@ -160,7 +160,10 @@ int mm_gae(const float *reward, const float *value, const uint8_t *done, const f
  *   logp [E] f32 = joint log-prob of both agents' actions (PPO.py:118,121); value [E] f32 (may be NULL); logits_out [E][2][6]
  *   f32 (may be NULL; 5 move logits + mark logit, unmasked).
  */
-int mm_policy_offsets(int32_t *out /* [32] */);
+#define MM_POLICY_N_OFFSETS 41
+int mm_policy_offsets(int32_t *out /* [MM_POLICY_N_OFFSETS]: the blocks listed above, then c0_wt, c1_wt (critic weights transposed), tokm, tokb
+                                      (per-token affine maps), l{0,1,2}_{h16,l16} (FP16 hi / lo split of 2^e W, fp16 [264][kpad] with kpad = 480,
+                                      288, 288, two halves per float slot) and l{0,1,2}_asc (the scalar 2^-e) -- read by MM_POLICY_FP16_SPLIT */);
 /* critic only: value [E] = Critic(obs [E][2][65]) (networks.py:96-102); used for the bootstrap value V(s_T) */
 int mm_critic_forward(const float *weights, const float *obs, int n_envs, float *value, void *stream);
 size_t mm_sizeof_policy_scratch(int n_envs);
@@ -172,6 +175,8 @@ int mm_policy_forward(const float *weights, const float *obs, const uint8_t *mas
 int mm_counter_add(uint64_t *counter_dev, uint64_t v, void *stream);
 #define MM_POLICY_TCGEN05 1 /* flags: trunk GEMMs as error-compensated 3xTF32 tcgen05.mma (TMA + TMEM); 0 = fp32 SIMT tiles */
 #define MM_POLICY_OVERLAP_CRITIC 2 /* flags: run the critic on an internal side stream forked from / joined to `stream` (capturable) */
+#define MM_POLICY_FP16_SPLIT 4 /* flags (with MM_POLICY_TCGEN05): the 3xFP16 kernel -- kind::f16 MMAs on the fp16 hi/lo split of the operands, 128 x 128|144
+                                  tiles, two CTAs per SM (csrc/mm_linear16.cu) -- instead of the 3xTF32 one */
 
 /*
  * K5 -- building blocks of the PPO actor update (PPO.py:58-85: loss.backward() through Actor.layers), SURVEY 8(f).1.
@@ -200,6 +205,16 @@ int mm_wgrad_tf32x3(const float *dz, const float *h, int rows, int n_out, int k_
 #define MM_LINEAR_PLAIN 3
 int mm_linear_tf32x3(const float *x, int rows, int k, const float *w_hi, const float *w_lo, int n_rows_w, const float *bias,
                      const uint32_t *gate_bits, float *y, int ldy, int mode, uint32_t *gate_bits_out, void *stream);
+
+/*
+ * mm_linear_f16x3: the forward GEMM as 3xFP16 (csrc/mm_linear16.cu): y[:, 0:n_rows_w] = relu(acc_scale * x W16^T + bias), x [rows][k] f32,
+ * W16 = fp16 hi / lo split of 2^e W, each fp16 [n_rows_w <= 264][kpad] with kpad = k rounded up to a multiple of 32 (zero padded), and
+ * *acc_scale (a DEVICE scalar) = 2^-e.  gate_bits_out (may be NULL) as in mm_linear_tf32x3.  Same result as MM_LINEAR_RELU of
+ * mm_linear_tf32x3 to ~1e-6 relative, at twice the tensor-core rate and half the weight traffic.  Forward only: gradients do not fit
+ * FP16's exponent range.
+ */
+int mm_linear_f16x3(const float *x, int rows, int k, const void *w_hi16, const void *w_lo16, int n_rows_w, int kpad, const float *acc_scale,
+                    const float *bias, float *y, int ldy, uint32_t *gate_bits_out, void *stream);
 
 /*
  * mm_ppo_heads_loss: heads + clipped surrogate, forward and backward (PPO.get_log_probs PPO.py:154-168 for both agents; ratio, clip,

@@ -17,6 +17,9 @@ size_t tokens_bwd_scratch_floats(int R);
 int tokens_bwd_blocks();
 cudaError_t launch_add_u64(unsigned long long* p, unsigned long long v, cudaStream_t stream);
 int policy_offsets_host(int32_t* out);
+cudaError_t launch_linear_f16x3(const float* x, const void* w_hi, const void* w_lo, int n_rows_w, int kpad, const float* acc_scale, const float* bias, float* y, int ldy,
+                                int M, int K, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, float* heads_part,
+                                cudaStream_t stream);
 cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatches, cudaStream_t stream);
 cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream);
 __global__ void k_load_layouts(ulonglong2*, ulonglong2*, uint4*, int, int, int, int, const uint8_t*, const int32_t*, uint16_t*);
@@ -168,7 +171,7 @@ int mm_critic_forward(const float* weights, const float* obs, int n_envs, float*
     if (!weights || !obs || !value || n_envs <= 0) return MM_ERR_BAD_ARG;
     return cuda_status(launch_critic(weights, obs, n_envs, value, (cudaStream_t)stream));
 }
-size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (460 + 2 * 264) * sizeof(float); }
+size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (460 + 2 * 264 + 16) * sizeof(float); }
 int mm_policy_forward(const float* weights, const float* obs, const uint8_t* masks, int n_envs, void* scratch, const uint8_t* actions_in,
                       uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter, int flags,
                       const uint64_t* counter_dev, void* stream) {
@@ -205,6 +208,16 @@ int mm_linear_tf32x3(const float* x, int rows, int k, const float* w_hi, const f
         (k & 3) || (ldy & 3) || (n_rows_w & 3))
         return MM_ERR_BAD_ARG;
     return cuda_status(launch_linear_tc_ex(x, w_hi, w_lo, n_rows_w, bias, y, ldy, rows, k, mode, gate_bits, gate_bits_out, nullptr, nullptr, nullptr, (cudaStream_t)stream));
+}
+int mm_linear_f16x3(const float* x, int rows, int k, const void* w_hi16, const void* w_lo16, int n_rows_w, int kpad, const float* acc_scale, const float* bias,
+                    float* y, int ldy, uint32_t* gate_bits_out, void* stream) {
+    if (!x || !w_hi16 || !w_lo16 || !acc_scale || !bias || !y || rows <= 0 || k <= 0 || n_rows_w <= 0 || n_rows_w > 264 || ldy < n_rows_w || kpad < k || (kpad & 31))
+        return MM_ERR_BAD_ARG;
+    if (((uintptr_t)x & 15) || ((uintptr_t)w_hi16 & 15) || ((uintptr_t)w_lo16 & 15) || ((uintptr_t)y & 15) || ((uintptr_t)gate_bits_out & 3) || (k & 3) || (ldy & 3) ||
+        (n_rows_w & 3))
+        return MM_ERR_BAD_ARG;
+    return cuda_status(launch_linear_f16x3(x, w_hi16, w_lo16, n_rows_w, kpad, acc_scale, bias, y, ldy, rows, k, gate_bits_out, nullptr, nullptr, nullptr, nullptr,
+                                           (cudaStream_t)stream));
 }
 int mm_ppo_loss_geometry(int32_t* blocks, int32_t* ld) {
     if (!blocks || !ld) return MM_ERR_BAD_ARG;

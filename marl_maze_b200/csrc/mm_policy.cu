@@ -28,8 +28,12 @@ struct PolicyOffsets {
     int l0_whi, l0_wlo, l1_whi, l1_wlo, l2_whi, l2_wlo;  // TF32 hi/lo splits of the three trunk weights (tensor-core path)
     int c0_wt, c1_wt;                                    // critic weights transposed: [130][64], [64][64] (coalesced lane = neuron reads)
     int tokm, tokb;                                      // per-token affine maps [60][23][4], [60][23]: rows 0-19 token, 20-29 key, 30-39 query, 40-59 value
+    // FP16 hi/lo splits of 2^e * W for the three trunk layers (mm_linear16.cu): fp16 [264][kpad] each, kpad = K rounded up to 32 (480, 288,
+    // 288; zero padded), stored in this fp32 buffer (two halves per float slot); l*_asc = the device scalar 2^-e
+    int l0_h16, l0_l16, l1_h16, l1_l16, l2_h16, l2_l16, l0_asc, l1_asc, l2_asc;
     int total;
 };
+constexpr int kPad0 = 480, kPad1 = 288;   // K = 460 / 264 rounded up to the 32-element k-block
 __host__ __device__ inline PolicyOffsets policy_offsets() {
     PolicyOffsets o; int p = 0;
     auto take = [&](int n) { int r = p; p += (n + 3) & ~3; return r; };  // keep every block 16-byte aligned
@@ -42,6 +46,8 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
     o.l2_whi = take(kHid * kHid); o.l2_wlo = take(kHid * kHid);
     o.c0_wt = take(130 * kCH); o.c1_wt = take(kCH * kCH);
     o.tokm = take(60 * kTok * 4); o.tokb = take(60 * kTok);
+    o.l0_h16 = take(kHid * kPad0 / 2); o.l0_l16 = take(kHid * kPad0 / 2); o.l1_h16 = take(kHid * kPad1 / 2); o.l1_l16 = take(kHid * kPad1 / 2);
+    o.l2_h16 = take(kHid * kPad1 / 2); o.l2_l16 = take(kHid * kPad1 / 2); o.l0_asc = take(1); o.l1_asc = take(1); o.l2_asc = take(1);
     o.total = p;
     return o;
 }
@@ -136,6 +142,150 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_MINBLOCKS) k_tokens(con
     }
     __syncwarp();  // the row's key / value tile is reused by the next row of this warp
     }
+}
+
+// ------------------------------------------------------------------------------------------------ tokens + attention, R rows per warp
+// k_tokens is bound by the shared-memory data pipe (ncu, profiles/r01h: LSU wavefronts 88.5 % of peak, 620 per row): 240 of them fetch the
+// per-token affine maps (23 lanes x 16 B = 3 wavefronts per float4), 184 are the broadcast key / value reads of the attention, ~90 the key /
+// value tile stores (scalar key stores at a 12-word lane stride conflict 3-way).  This version carries R rows through the AFFINE phase together --
+// every map element fetched from shared memory serves R rows -- while the attention phase still runs one row at a time (its registers, p[23] and
+// ctx[20], are not duplicated), and stores keys as float4 / float4 / float2 (conflict-free at that stride): 184 + 240 / R + ~24 wavefronts per row.
+#ifndef MM_TOK_ROWS
+#define MM_TOK_ROWS 2
+#endif
+#ifndef MM_TOK_R_MINBLOCKS
+#define MM_TOK_R_MINBLOCKS (MM_TOK_ROWS <= 2 ? 4 : 3)
+#endif
+template <int R>
+__global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int nrows) {
+    const PolicyOffsets o = policy_offsets();
+    extern __shared__ __align__(16) float tk_smem[];
+    float (*s_m)[kTok][4] = reinterpret_cast<float (*)[kTok][4]>(tk_smem);                        // [60][23][4]
+    float (*s_b)[kTok] = reinterpret_cast<float (*)[kTok]>(tk_smem + 60 * kTok * 4);               // [60][23]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tk_smem + 60 * kTok * 5 + w * (R * kTok * 32);                                   // per warp: R rows x 23 tokens x (12 key + 20 value)
+    for (int i = threadIdx.x; i < 60 * kTok * 4; i += blockDim.x) (&s_m[0][0][0])[i] = wts[o.tokm + i];
+    for (int i = threadIdx.x; i < 60 * kTok; i += blockDim.x) (&s_b[0][0])[i] = wts[o.tokb + i];
+    __syncthreads();
+    const bool on = lane < kTok;
+    const int a = on ? lane : 0;
+    const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
+#pragma unroll 1
+    for (int row0 = (blockIdx.x * kTokWarps + w) * R; row0 < nrows; row0 += gridDim.x * kTokWarps * R) {
+        float x[R][4];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) x[r][c] = (c < nd && row0 + r < nrows) ? obs[(size_t)(row0 + r) * kObs + c0 + c] : 0.f;
+        // ---- affine phase: one shared-memory fetch of map row j serves all R rows
+        float q[R][kKQ], tok[R][kEmb];
+        {
+            float kk[R][12];
+#pragma unroll
+            for (int d = 0; d < kKQ; d++) {
+                const float4 m = *reinterpret_cast<const float4*>(&s_m[20 + d][a][0]);
+                const float b = s_b[20 + d][a];
+#pragma unroll
+                for (int r = 0; r < R; r++) kk[r][d] = fmaf(x[r][3], m.w, fmaf(x[r][2], m.z, fmaf(x[r][1], m.y, fmaf(x[r][0], m.x, b))));
+            }
+            if (on) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    float* kt = tile + (r * kTok + a) * 32;
+                    *reinterpret_cast<float4*>(kt) = make_float4(kk[r][0], kk[r][1], kk[r][2], kk[r][3]);
+                    *reinterpret_cast<float4*>(kt + 4) = make_float4(kk[r][4], kk[r][5], kk[r][6], kk[r][7]);
+                    *reinterpret_cast<float2*>(kt + 8) = make_float2(kk[r][8], kk[r][9]);
+                }
+            }
+        }
+#pragma unroll
+        for (int d4 = 0; d4 < kEmb / 4; d4++) {
+            float vv[R][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 m = *reinterpret_cast<const float4*>(&s_m[40 + 4 * d4 + i][a][0]);
+                const float b = s_b[40 + 4 * d4 + i][a];
+#pragma unroll
+                for (int r = 0; r < R; r++) vv[r][i] = fmaf(x[r][3], m.w, fmaf(x[r][2], m.z, fmaf(x[r][1], m.y, fmaf(x[r][0], m.x, b))));
+            }
+            if (on) {
+#pragma unroll
+                for (int r = 0; r < R; r++) *reinterpret_cast<float4*>(tile + (r * kTok + a) * 32 + 12 + 4 * d4) = make_float4(vv[r][0], vv[r][1], vv[r][2], vv[r][3]);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < kKQ; d++) {
+            const float4 m = *reinterpret_cast<const float4*>(&s_m[30 + d][a][0]);
+            const float b = s_b[30 + d][a];
+#pragma unroll
+            for (int r = 0; r < R; r++) q[r][d] = fmaf(x[r][3], m.w, fmaf(x[r][2], m.z, fmaf(x[r][1], m.y, fmaf(x[r][0], m.x, b))));
+        }
+#pragma unroll
+        for (int d = 0; d < kEmb; d++) {
+            const float4 m = *reinterpret_cast<const float4*>(&s_m[d][a][0]);
+            const float b = s_b[d][a];
+#pragma unroll
+            for (int r = 0; r < R; r++) tok[r][d] = fmaf(x[r][3], m.w, fmaf(x[r][2], m.z, fmaf(x[r][1], m.y, fmaf(x[r][0], m.x, b))));
+        }
+        __syncwarp();
+        // ---- attention phase, one row at a time (networks.py:75-82)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float* kt = tile + r * kTok * 32;
+            float p[kTok];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int b = 0; b < kTok; b++) {
+                const float4 k0 = *reinterpret_cast<const float4*>(kt + b * 32), k1 = *reinterpret_cast<const float4*>(kt + b * 32 + 4);
+                const float2 k2 = *reinterpret_cast<const float2*>(kt + b * 32 + 8);
+                float acc = q[r][0] * k0.x;
+                acc = fmaf(q[r][1], k0.y, acc); acc = fmaf(q[r][2], k0.z, acc); acc = fmaf(q[r][3], k0.w, acc);
+                acc = fmaf(q[r][4], k1.x, acc); acc = fmaf(q[r][5], k1.y, acc); acc = fmaf(q[r][6], k1.z, acc); acc = fmaf(q[r][7], k1.w, acc);
+                acc = fmaf(q[r][8], k2.x, acc); acc = fmaf(q[r][9], k2.y, acc);
+                p[b] = acc * 0.31622776601683794f;  // 1/sqrt(10)
+                mx = fmaxf(mx, p[b]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int b = 0; b < kTok; b++) { p[b] = expf(p[b] - mx); sum += p[b]; }
+            const float inv = 1.f / sum;
+            float ctx[kEmb];
+#pragma unroll
+            for (int d = 0; d < kEmb; d++) ctx[d] = 0.f;
+#pragma unroll
+            for (int b = 0; b < kTok; b++) {
+                const float pb = p[b] * inv;
+#pragma unroll
+                for (int d4 = 0; d4 < kEmb / 4; d4++) {
+                    const float4 vv = *reinterpret_cast<const float4*>(kt + b * 32 + 12 + 4 * d4);
+                    ctx[4 * d4] = fmaf(pb, vv.x, ctx[4 * d4]); ctx[4 * d4 + 1] = fmaf(pb, vv.y, ctx[4 * d4 + 1]);
+                    ctx[4 * d4 + 2] = fmaf(pb, vv.z, ctx[4 * d4 + 2]); ctx[4 * d4 + 3] = fmaf(pb, vv.w, ctx[4 * d4 + 3]);
+                }
+            }
+            if (on && row0 + r < nrows) {  // residual (networks.py:82); lane a owns columns 20a .. 20a+19 of the row
+                float4* oh = reinterpret_cast<float4*>(x0 + (size_t)(row0 + r) * kX0 + a * kEmb);
+#pragma unroll
+                for (int d4 = 0; d4 < kEmb / 4; d4++)
+                    oh[d4] = make_float4(tok[r][4 * d4] + ctx[4 * d4], tok[r][4 * d4 + 1] + ctx[4 * d4 + 1], tok[r][4 * d4 + 2] + ctx[4 * d4 + 2], tok[r][4 * d4 + 3] + ctx[4 * d4 + 3]);
+            }
+        }
+        __syncwarp();  // the tiles are rewritten by the next R rows of this warp
+    }
+}
+constexpr int kTokRSmem = (60 * kTok * 5 + kTokWarps * MM_TOK_ROWS * kTok * 32) * (int)sizeof(float);
+static cudaError_t launch_tokens_any(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
+#if MM_TOK_ROWS >= 2
+    static PerDeviceFlag configured;
+    if (configured.first_time()) {
+        cudaError_t e = cudaFuncSetAttribute(k_tokens_r<MM_TOK_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTokRSmem);
+        if (e != cudaSuccess) { configured.retract(); return e; }
+    }
+    const int per_block = kTokWarps * MM_TOK_ROWS;
+    k_tokens_r<MM_TOK_ROWS><<<min((R + per_block - 1) / per_block, 148 * 8), kTokWarps * 32, kTokRSmem, stream>>>(obs, wts, x0, R);
+#else
+    k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
+#endif
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ tokens + attention, backward
@@ -336,10 +486,7 @@ __global__ void __launch_bounds__(kTrThreads) k_tokens_bwd_reduce(const float* _
 
 int tokens_bwd_blocks() { return 148 * 4; }
 size_t tokens_bwd_scratch_floats(int R) { return (size_t)R * kTok * 40; }
-cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
-    k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
-    return cudaGetLastError();
-}
+cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) { return launch_tokens_any(wts, obs, R, x0, stream); }
 cudaError_t launch_tokens_bwd(const float* wts, const float* obs, const float* dout, int R, float* dy40, float* part, cudaStream_t stream) {
     static PerDeviceFlag configured;
     if (configured.first_time()) {
@@ -479,17 +626,21 @@ cudaError_t launch_critic(const float* wts, const float* obs, int E, float* valu
 
 int policy_offsets_host(int32_t* out) {
     const PolicyOffsets o = policy_offsets();
-    const int v[32] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
+    const int v[MM_POLICY_N_OFFSETS] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
                        o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, o.l0_whi, o.l0_wlo, o.l1_whi, o.l1_wlo, o.l2_whi, o.l2_wlo,
-                       o.c0_wt, o.c1_wt, o.tokm, o.tokb};
-    for (int i = 0; i < 32; i++) out[i] = v[i];
+                       o.c0_wt, o.c1_wt, o.tokm, o.tokb, o.l0_h16, o.l0_l16, o.l1_h16, o.l1_l16, o.l2_h16, o.l2_l16, o.l0_asc, o.l1_asc, o.l2_asc};
+    for (int i = 0; i < MM_POLICY_N_OFFSETS; i++) out[i] = v[i];
     return 0;
 }
 
 cudaError_t launch_linear_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int M, int K, const float* head_w,
                              const float* head_b, const HeadArgs* heads, cudaStream_t stream);
+cudaError_t launch_linear_f16x3(const float* x, const void* w_hi, const void* w_lo, int n_rows_w, int kpad, const float* acc_scale, const float* bias, float* y, int ldy,
+                                int M, int K, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, float* heads_part,
+                                cudaStream_t stream);
 
-// flags bit 0: trunk GEMMs on tcgen05 (3xTF32) instead of the fp32 SIMT tiles; bit 1: critic on a forked side stream
+// flags bit 0: trunk GEMMs on tcgen05 instead of the fp32 SIMT tiles; bit 1: critic on a forked side stream; bit 2 (with bit 0): the
+// 3xFP16 N-split kernel (mm_linear16.cu, two CTAs per SM) instead of the 3xTF32 one (mm_policy_tc.cu)
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
                           uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter,
                           int flags, const uint64_t* counter_dev, cudaStream_t stream) {
@@ -502,6 +653,7 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
     float* x0 = scratch;                      // [R,460]
     float* h1 = scratch + (size_t)R * kX0;    // [R,264]
     float* h2 = h1 + (size_t)R * kHid;        // [R,264]
+    float* hpart = h2 + (size_t)R * kHid;     // [R,2,8] partial head sums of the two column halves (3xFP16 path)
     // flags bit 1: the critic only reads obs, so it runs on a side stream forked from / joined to `stream` by events (legal inside a
     // stream capture, where it becomes a parallel branch of the graph) and overlaps the actor's token + trunk kernels.  The stream and
     // the two events are created once per host thread, on the first (eager) call.
@@ -524,8 +676,14 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, side>>>(obs, wts, value, E);
         if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
     }
-    k_tokens<<<min((R + kTokWarps - 1) / kTokWarps, 148 * 8), kTokWarps * 32, 0, stream>>>(obs, wts, x0, R);
-    if (flags & 1) {
+    { cudaError_t e = launch_tokens_any(wts, obs, R, x0, stream); if (e != cudaSuccess) return e; }
+    if ((flags & 5) == 5) {
+        cudaError_t e;
+        if ((e = launch_linear_f16x3(x0, wts + o.l0_h16, wts + o.l0_l16, kHid, kPad0, wts + o.l0_asc, wts + o.l0_b, h1, kHid, R, kX0, nullptr, nullptr, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;
+        if ((e = launch_linear_f16x3(h1, wts + o.l1_h16, wts + o.l1_l16, kHid, kPad1, wts + o.l1_asc, wts + o.l1_b, h2, kHid, R, kHid, nullptr, nullptr, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;
+        // last layer: each column half contracts its part of the row with the six head rows; k_heads_finish adds the halves, masks, samples
+        if ((e = launch_linear_f16x3(h2, wts + o.l2_h16, wts + o.l2_l16, kHid, kPad1, wts + o.l2_asc, wts + o.l2_b, nullptr, kHid, R, kHid, nullptr, wts + o.head_w, wts + o.head_b, &ha, hpart, stream)) != cudaSuccess) return e;
+    } else if (flags & 1) {
         cudaError_t e;
         if ((e = launch_linear_tc(x0, wts + o.l0_whi, wts + o.l0_wlo, wts + o.l0_b, h1, R, kX0, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;
         if ((e = launch_linear_tc(h1, wts + o.l1_whi, wts + o.l1_wlo, wts + o.l1_b, h2, R, kHid, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;

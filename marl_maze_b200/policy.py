@@ -6,6 +6,7 @@ launches mm_policy_forward.  Used by PPO.get_action / PPO.get_batch; autograd ne
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -14,11 +15,12 @@ from . import _abi
 from .networks import FEATURE_DIMS, EMBEDDING_DIM
 
 _NAMES = ["proj_w", "proj_b", "proj_col", "proj_dim", "att_k", "att_q", "att_v", "l0_w", "l0_b", "l1_w", "l1_b", "l2_w", "l2_b",
-          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo", "c0_wt", "c1_wt", "tokm", "tokb"]
+          "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo", "c0_wt", "c1_wt", "tokm", "tokb",
+          "l0_h16", "l0_l16", "l1_h16", "l1_l16", "l2_h16", "l2_l16", "l0_asc", "l1_asc", "l2_asc"]
 
 
 def offsets() -> dict:
-    out = (C.c_int32 * 32)()
+    out = (C.c_int32 * len(_NAMES))()   # MM_POLICY_N_OFFSETS
     _abi.check(_abi.lib().mm_policy_offsets(out), "mm_policy_offsets")
     return {n: int(out[i]) for i, n in enumerate(_NAMES)}
 
@@ -26,6 +28,23 @@ def offsets() -> dict:
 def _tf32_rn(x: torch.Tensor) -> torch.Tensor:
     """Nearest TF32 value (10 explicit mantissa bits, ties away from zero) -- same rounding as cvt.rna.tf32.f32 on the device."""
     return ((x.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
+def f16_split(w: torch.Tensor, kpad: int | None = None):
+    """The operand form of mm_linear_f16x3 / MM_POLICY_FP16_SPLIT: (hi, lo, acc_scale) with hi = fp16(2^e w), lo = fp16(2^e w - hi) (both round
+    to nearest; fp16 [n][kpad], zero padded columns) and acc_scale = 2^-e as a one-element fp32 DEVICE tensor.  e puts the largest |w| in
+    [256, 512): exact scaling, every hi / lo a normal fp16 number unless |w| < 2^-23 max|w|.  No host synchronisation."""
+    w = w.detach().to(torch.float32)
+    n, k = w.shape
+    kpad = k if kpad is None else kpad
+    m = w.abs().max().clamp_min(1e-30)
+    e = torch.floor(torch.log2(512.0 / m)).clamp(-14.0, 24.0)
+    ws = w * torch.exp2(e)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+    if kpad != k:
+        hi = torch.nn.functional.pad(hi, (0, kpad - k)); lo = torch.nn.functional.pad(lo, (0, kpad - k))
+    return hi.contiguous(), lo.contiguous(), torch.exp2(-e).reshape(1).to(torch.float32)
 
 
 def pack_weights(actor, critic, device=None) -> torch.Tensor:
@@ -57,6 +76,12 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
             put(f"l{i}_w", w); put(f"l{i}_b", actor.layers[i].bias)
             hi = _tf32_rn(w)
             put(f"l{i}_whi", hi); put(f"l{i}_wlo", _tf32_rn(w - hi))
+            kpad = (w.shape[1] + 31) // 32 * 32
+            h16, l16, asc = f16_split(w, kpad)               # fp16 [264][kpad]: two halves per float slot of the flat buffer
+            n16 = h16.numel() // 2
+            buf[o[f"l{i}_h16"]:o[f"l{i}_h16"] + n16] = h16.reshape(-1).view(torch.float32)
+            buf[o[f"l{i}_l16"]:o[f"l{i}_l16"] + n16] = l16.reshape(-1).view(torch.float32)
+            buf[o[f"l{i}_asc"]:o[f"l{i}_asc"] + 1] = asc
         put("head_w", torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)); put("head_b", torch.cat([actor.move_head.bias, actor.mark_head.bias]))
         for i in range(3):
             put(f"c{i}_w", critic.layers[i].weight); put(f"c{i}_b", critic.layers[i].bias)
@@ -72,7 +97,8 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
 
 
 class PolicyRunner:
-    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0, tensor_cores: bool = True, overlap_critic: bool = True):
+    def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0, tensor_cores: bool = True, overlap_critic: bool = True,
+                 fp16_split: bool | None = None):
         self.lib = _abi.lib()
         self.E, self.device, self.env_offset, self.seed = int(num_envs), torch.device(device), int(env_offset), int(seed) & (2**64 - 1)
         self.actor, self.critic = actor, critic
@@ -81,7 +107,10 @@ class PolicyRunner:
         self.counter = 0
         self.counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)  # added to `counter` on the device (CUDA-graph replays)
         self.launches = 0
-        self.flags = (1 if tensor_cores else 0) | (2 if overlap_critic else 0)  # MM_POLICY_TCGEN05 | MM_POLICY_OVERLAP_CRITIC
+        if fp16_split is None:   # default: the 3xFP16 two-CTA-per-SM kernel; MARL_MAZE_TF32_TRUNK=1 keeps the 3xTF32 one (A/B runs)
+            fp16_split = os.environ.get("MARL_MAZE_TF32_TRUNK", "0") != "1"
+        # MM_POLICY_TCGEN05 | MM_POLICY_OVERLAP_CRITIC | MM_POLICY_FP16_SPLIT
+        self.flags = (1 if tensor_cores else 0) | (2 if overlap_critic else 0) | (4 if (tensor_cores and fp16_split) else 0)
 
     def refresh(self):
         """Re-pack after an optimiser step -- in place, so that captured CUDA graphs keep pointing at live weights."""
@@ -119,5 +148,6 @@ class PolicyRunner:
         _abi.check(self.lib.mm_policy_forward(p(self.weights), p(obs), p(masks), E, p(self.scratch), p(actions_in), p(actions_out), p(logp),
                                               p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(counter),
                                               self.flags, p(self.counter_dev), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
-        self.launches += (4 if self.flags & 1 else 5) + (1 if want_value else 0)  # tokens + 3 trunk layers (+ heads on the SIMT path) + critic
+        # tokens + 3 trunk layers (+ heads on the SIMT path, + k_heads_finish on the 3xFP16 path) + critic
+        self.launches += (5 if (self.flags & 5) == 5 else 4 if self.flags & 1 else 5) + (1 if want_value else 0)
         return (actions_in if actions_in is not None else actions_out), logp, (value if want_value else None)

@@ -160,6 +160,35 @@ def linear_tc(x, w_split, mode, bias=None, gate_bits=None, out=None, col0=0, wan
     return (out, bits) if want_bits else out
 
 
+def linear_f16(x, w_split16, bias, out=None, want_bits=False):
+    """relu(x @ W^T + bias) through the 3xFP16 kernel (mm_linear_f16x3): W [n<=264, k] given as policy.f16_split(W, kpad) = (hi16, lo16,
+    acc_scale) with kpad = k rounded up to 32.  want_bits=True also returns the ReLU pattern [rows, 9] int32 (see linear_tc)."""
+    w_hi, w_lo, asc = w_split16
+    rows, k = x.shape
+    n, kpad = w_hi.shape
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w_hi.dtype == w_lo.dtype == torch.float16 and w_lo.shape == w_hi.shape
+    assert kpad == (k + 31) // 32 * 32 and w_hi.is_contiguous() and w_lo.is_contiguous() and asc.dtype == torch.float32 and asc.is_cuda
+    if out is None:
+        out = torch.empty(rows, n, device=x.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.shape == (rows, n)
+    bits = torch.empty(rows, 9, device=x.device, dtype=torch.int32) if want_bits else None
+    _abi.check(_abi.lib().mm_linear_f16x3(_ptr(x), rows, k, _ptr(w_hi), _ptr(w_lo), n, kpad, _ptr(asc), _ptr(bias.detach().contiguous()), _ptr(out), n, _ptr(bits),
+                                          _stream(x)), "mm_linear_f16x3")
+    return (out, bits) if want_bits else out
+
+
+FWD_FP16 = __import__("os").environ.get("MARL_MAZE_TF32_TRUNK", "0") != "1"   # forward GEMMs of the update on the 3xFP16 kernel (default)
+
+
+def fwd_relu(x, w, bias, want_bits=False):
+    """relu(x @ w^T + bias) through whichever forward GEMM the fused update uses (3xFP16 by default, 3xTF32 with MARL_MAZE_TF32_TRUNK=1):
+    what tests call to reproduce the fused forward's own ReLU gates."""
+    if FWD_FP16:
+        from .policy import f16_split
+        return linear_f16(x, f16_split(w, (w.shape[1] + 31) // 32 * 32), bias, want_bits=want_bits)
+    return linear_tc(x, tf32_split(w), MM_LINEAR_RELU, bias=bias.detach().contiguous(), want_bits=want_bits)
+
+
 def ppo_heads_loss(h2, head_w, head_b, masks, actions, old_logp, adv, clip, scale):
     """-> (loss [] , joint log-prob [E], dz2 [2E,264], dhead_w [6,264], dhead_b [6]); see mm_ppo_heads_loss in the header."""
     E = old_logp.shape[0]
@@ -187,8 +216,10 @@ def trunk_splits(actor):
     if cached is None or cached[0] != key:
         with torch.no_grad():
             w0t = ws[0].t().contiguous()
+            from .policy import f16_split
             data = dict(fwd=[tf32_split(w) for w in ws], t1=tf32_split(ws[1].t()), t2=tf32_split(ws[2].t()),
-                        t0=[tf32_split(w0t[c0:c0 + 264]) for c0 in range(0, w0t.shape[0], 264)])
+                        t0=[tf32_split(w0t[c0:c0 + 264]) for c0 in range(0, w0t.shape[0], 264)],
+                        fwd16=[f16_split(w, (w.shape[1] + 31) // 32 * 32) for w in ws])
         cached = (key, data)
         actor._k5_splits = cached
     return cached[1]
@@ -205,9 +236,14 @@ class _ActorTrunkLoss(torch.autograd.Function):
         """x0 [2E,460], inv None -- or x0 = the few DISTINCT embedding rows [U<=8,460] and inv [2E] the row of each agent (Actor.embed_parts)."""
         src = x0.detach().contiguous()
         x0 = src if inv is None else src.index_select(0, inv)
-        h0, bits0 = linear_tc(x0, sp["fwd"][0], MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
-        h1, bits1 = linear_tc(h0, sp["fwd"][1], MM_LINEAR_RELU, bias=b1.detach().contiguous(), want_bits=True)
-        h2 = linear_tc(h1, sp["fwd"][2], MM_LINEAR_RELU, bias=b2.detach().contiguous())
+        if FWD_FP16:   # forward GEMMs: 3xFP16, two CTAs per SM (the data / weight gradients below need TF32's exponent range)
+            h0, bits0 = linear_f16(x0, sp["fwd16"][0], b0, want_bits=True)
+            h1, bits1 = linear_f16(h0, sp["fwd16"][1], b1, want_bits=True)
+            h2 = linear_f16(h1, sp["fwd16"][2], b2)
+        else:
+            h0, bits0 = linear_tc(x0, sp["fwd"][0], MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
+            h1, bits1 = linear_tc(h0, sp["fwd"][1], MM_LINEAR_RELU, bias=b1.detach().contiguous(), want_bits=True)
+            h2 = linear_tc(h1, sp["fwd"][2], MM_LINEAR_RELU, bias=b2.detach().contiguous())
         loss, logp, dz2, dwh, dbh = ppo_heads_loss(h2, wh, bh, masks, actions, old_logp, adv, clip, scale)
         del h2
         dw2, db2 = wgrad(dz2, h1)
@@ -287,8 +323,13 @@ class _CriticLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xpad, w0, b0, w1, b1, w2, b2, rtg, scale):
         w0p = torch.nn.functional.pad(w0.detach(), (0, xpad.shape[1] - w0.shape[1]))
-        h0, bits0 = linear_tc(xpad, tf32_split(w0p), MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
-        h1 = linear_tc(h0, tf32_split(w1), MM_LINEAR_RELU, bias=b1.detach().contiguous())
+        if FWD_FP16:
+            from .policy import f16_split
+            h0, bits0 = linear_f16(xpad, f16_split(w0p, (w0p.shape[1] + 31) // 32 * 32), b0, want_bits=True)
+            h1 = linear_f16(h0, f16_split(w1, (w1.shape[1] + 31) // 32 * 32), b1)
+        else:
+            h0, bits0 = linear_tc(xpad, tf32_split(w0p), MM_LINEAR_RELU, bias=b0.detach().contiguous(), want_bits=True)
+            h1 = linear_tc(h0, tf32_split(w1), MM_LINEAR_RELU, bias=b1.detach().contiguous())
         v = torch.addmv(b2.detach(), h1, w2.detach()[0])
         diff = v - rtg
         loss = (diff * diff).sum() * scale

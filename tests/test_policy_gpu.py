@@ -14,7 +14,15 @@ TOL = dict(rtol=1e-5, atol=2e-6)
 # Raw LOGITS of the tensor-core path: tcgen05 accumulates its K = 460/264-long sums with truncation inside the tensor core, which
 # leaves ~1e-6 relative (max 4e-6 absolute, tools/k4_accuracy.py) on the logits -- 10x the fp32 SIMT path, still far inside the
 # north-star bar on the quantities it names (log-probs and values: 1e-5 relative, asserted with TOL for BOTH paths below).
-TOL_LOGITS = {False: TOL, True: dict(rtol=1e-5, atol=8e-6)}
+TOL_LOGITS = {"simt_fp32": TOL, "tcgen05_3xtf32": dict(rtol=1e-5, atol=8e-6), "tcgen05_3xfp16": dict(rtol=1e-5, atol=8e-6)}
+PATHS = ["simt_fp32", "tcgen05_3xtf32", "tcgen05_3xfp16"]
+
+
+def _runner(actor, critic, E, path, **kw):
+    """The three trunk implementations behind mm_policy_forward: fp32 SIMT tiles, 3xTF32 tcgen05 (mm_policy_tc.cu), 3xFP16 tcgen05 with two
+    CTAs per SM (mm_linear16.cu, the default)."""
+    from marl_maze_b200.policy import PolicyRunner
+    return PolicyRunner(actor, critic, E, "cuda", tensor_cores=path != "simt_fp32", fp16_split=path == "tcgen05_3xfp16", **kw)
 
 
 def _nets(seed, faithful=True):
@@ -25,15 +33,14 @@ def _nets(seed, faithful=True):
     return actor, critic, asd, csd
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["simt_fp32", "tcgen05_3xtf32"])
+@pytest.mark.parametrize("tc", PATHS)
 @pytest.mark.parametrize("seed", [11, 12])
 def test_policy_kernel_vs_reference_golden(seed, tc):
-    from marl_maze_b200.policy import PolicyRunner
     Z = np.load(os.path.join(GOLDEN, "ppo_kats.npz"))
     obs, masks, acts = Z["net/obs"], Z["net/masks"], Z["net/actions"]
     actor, critic, _, _ = _nets(seed)
     E = obs.shape[0]
-    run = PolicyRunner(actor, critic, E, "cuda", tensor_cores=tc)
+    run = _runner(actor, critic, E, tc)
     logits = torch.zeros(E, 2, 6, device="cuda")
     _, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), actions_in=torch.from_numpy(acts).cuda(), logits=logits)
     lg = logits.cpu().numpy()
@@ -46,16 +53,15 @@ def test_policy_kernel_vs_reference_golden(seed, tc):
     assert np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], want[fin], **TOL)
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["simt_fp32", "tcgen05_3xtf32"])
+@pytest.mark.parametrize("tc", PATHS)
 @pytest.mark.parametrize("faithful", [True, False])
 def test_policy_kernel_vs_oracle_random_obs_and_sampling(faithful, tc):
-    from marl_maze_b200.policy import PolicyRunner
     actor, critic, asd, csd = _nets(5, faithful)
     rng = np.random.default_rng(3)
     E = 3000
     obs = rng.random((E, 2, 65)).astype(np.float32)
     masks = (rng.random((E, 2, 6)) < 0.6).astype(np.uint8); masks[:, :, 0] |= (masks[:, :, :5].sum(-1) == 0).astype(np.uint8)
-    run = PolicyRunner(actor, critic, E, "cuda", seed=9, tensor_cores=tc)
+    run = _runner(actor, critic, E, tc, seed=9)
     logits = torch.zeros(E, 2, 6, device="cuda")
     act, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(masks).cuda(), logits=logits)
     act = act.cpu().numpy()
@@ -105,7 +111,7 @@ def _ppo_pth_nets():
     return Z, actor, critic
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["simt_fp32", "tcgen05"])
+@pytest.mark.parametrize("tc", PATHS)
 def test_kat5_reference_checkpoint_through_mm_policy_forward(tc):
     """SURVEY 8c KAT(5) through the C ABI: the reference's own PPO.pth, packed by policy.pack_weights, evaluated by mm_policy_forward on
     the four facing one-hots -- against the logits the REFERENCE's networks.py computes from the same file (and the survey's printed
@@ -115,7 +121,7 @@ def test_kat5_reference_checkpoint_through_mm_policy_forward(tc):
     # --- the four facings.  Rows are agents; the kernel takes [E,2,65], so the 4 probes are laid out as 2 envs x 2 agents
     x = torch.from_numpy(Z["kat5/obs"]).cuda().view(2, 2, 65).contiguous()
     masks = torch.ones(2, 2, 6, dtype=torch.uint8, device="cuda")
-    run = PolicyRunner(actor, critic, 2, "cuda", tensor_cores=tc)
+    run = _runner(actor, critic, 2, tc)
     logits = torch.zeros(2, 2, 6, device="cuda")
     run.forward(x, masks, logits=logits)
     lg = logits.cpu().numpy().reshape(4, 6)
@@ -125,7 +131,7 @@ def test_kat5_reference_checkpoint_through_mm_policy_forward(tc):
     # --- recorded observations / actions
     obs, mk, acts = Z["trace/obs"], Z["trace/masks"], Z["trace/actions"]
     E = obs.shape[0]
-    run = PolicyRunner(actor, critic, E, "cuda", tensor_cores=tc)
+    run = _runner(actor, critic, E, tc)
     logits = torch.zeros(E, 2, 6, device="cuda")
     _, logp, val = run.forward(torch.from_numpy(obs).cuda(), torch.from_numpy(mk).cuda(), actions_in=torch.from_numpy(acts).cuda(), logits=logits)
     lg = logits.cpu().numpy()

@@ -65,6 +65,27 @@ def _loss_inputs(E, g, wide_ratio=True):
     return masks, actions, adv
 
 
+@pytest.mark.parametrize("rows,n,k", [(1000, 264, 460), (4133, 264, 264), (129, 64, 132), (5000, 64, 64), (300, 196, 264), (128, 128, 36)])
+def test_linear_f16x3_matches_fp64(rows, n, k):
+    """mm_linear_f16x3 (3xFP16 on tcgen05, N-split tiles, two CTAs per SM) against fp64: the trunk shapes, the critic's, ragged row counts,
+    a single-half width (n <= 128) and a second half narrower than 144; the ReLU bit words; weights spanning four decades."""
+    from marl_maze_b200.policy import f16_split
+    from marl_maze_b200.update import linear_f16
+    g = torch.Generator(device="cuda"); g.manual_seed(rows + n + k)
+    x = torch.randn(rows, k, device="cuda", generator=g) * (torch.rand(rows, 1, device="cuda", generator=g) * 4)
+    w = torch.randn(n, k, device="cuda", generator=g) * 10 ** (torch.rand(n, 1, device="cuda", generator=g) * 4 - 3) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=g) * 0.1
+    y, bits = linear_f16(x, f16_split(w, (k + 31) // 32 * 32), b, want_bits=True)
+    ref = torch.relu(x.double() @ w.double().t() + b.double())
+    scale = float((x.double().abs() @ w.double().abs().t()).max())        # the size of the sums that produced the outputs
+    err = float((y.double() - ref).abs().max())
+    assert err < 3e-6 * scale, (err, scale)
+    # bit c*32+b of the row = y[row][32c+b] > 0, zero beyond column n
+    want = torch.zeros(rows, 9 * 32, dtype=torch.bool, device="cuda"); want[:, :n] = y > 0
+    got = ((bits.view(rows, 9, 1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).bool().view(rows, 288)
+    assert torch.equal(got[:, :((n + 31) // 32) * 32], want[:, :((n + 31) // 32) * 32])
+
+
 def test_ppo_heads_loss_matches_autograd():
     """Loss, joint log-probs and every gradient of mm_ppo_heads_loss against the reference formulas under torch fp64 autograd, with
     ratios on both sides of (and exactly inside) the clip range."""
@@ -137,12 +158,12 @@ def test_fused_actor_loss_gradients_match_autograd(faithful):
     # ReLU'(0): an fp32 pre-activation within rounding of zero may land on the other side than the fp64 one, and that single (row, unit)
     # then carries a gradient in one computation and none in the other -- a legitimate difference between ANY two float evaluations, as
     # large as the gradient element itself.  Take it out of the comparison: every reference below uses the fused forward's own gates.
-    from marl_maze_b200.update import linear_tc, tf32_split, MM_LINEAR_RELU
+    from marl_maze_b200.update import fwd_relu
     with torch.no_grad():
         from marl_maze_b200.update import token_embed
         hf, gates = (actor.embed(obs) if faithful else token_embed(actor, obs)).contiguous(), []   # the embedding path actor_loss takes
         for lin in actor.layers:
-            hf = linear_tc(hf, tf32_split(lin.weight), MM_LINEAR_RELU, bias=lin.bias.detach().contiguous())
+            hf = fwd_relu(hf, lin.weight, lin.bias)
             gates.append(hf > 0)
 
     def loss_ref(a, dt, old):   # Actor.forward + PPO.get_log_probs + the clipped surrogate in dtype dt (Actor.trunk itself casts to fp32)
@@ -279,7 +300,7 @@ def test_fused_critic_loss_matches_autograd():
     """update.critic_loss (K5 GEMM kernels for the critic's hidden layers) against Critic + MSE under torch autograd in fp64."""
     import copy
     from marl_maze_b200.networks import Critic
-    from marl_maze_b200.update import critic_loss, critic_fused_available, pad_critic_obs, linear_tc, tf32_split, MM_LINEAR_RELU
+    from marl_maze_b200.update import critic_loss, critic_fused_available, pad_critic_obs, fwd_relu
     torch.manual_seed(41)
     critic = Critic(2, hidden_sizes=[64, 64]).cuda()
     assert critic_fused_available(critic)
@@ -294,8 +315,8 @@ def test_fused_critic_loss_matches_autograd():
     # same ReLU gates in the reference as in the fused forward (see test_fused_actor_loss_gradients_match_autograd)
     with torch.no_grad():
         w0p = torch.nn.functional.pad(critic.layers[0].weight, (0, 2))
-        h0 = linear_tc(xpad, tf32_split(w0p), MM_LINEAR_RELU, bias=critic.layers[0].bias.detach().contiguous())
-        h1 = linear_tc(h0, tf32_split(critic.layers[1].weight), MM_LINEAR_RELU, bias=critic.layers[1].bias.detach().contiguous())
+        h0 = fwd_relu(xpad, w0p, critic.layers[0].bias)
+        h1 = fwd_relu(h0, critic.layers[1].weight, critic.layers[1].bias)
     x = obs.double().reshape(n, 130)
     r0 = ref.layers[0](x) * (h0 > 0)
     r1 = ref.layers[1](r0) * (h1 > 0)

@@ -32,6 +32,10 @@ def kernels():
     y = torch.empty(R, 264, device=dev)
     out["fwd_460_ms"] = timeit(lambda: U.linear_tc(x0, s0, U.MM_LINEAR_RELU, bias=b, out=y))
     out["fwd_264_ms"] = timeit(lambda: U.linear_tc(h, s1, U.MM_LINEAR_RELU, bias=b, out=y))
+    from marl_maze_b200.policy import f16_split
+    s0h, s1h = f16_split(w0, 480), f16_split(w1, 288)
+    out["fwd16_460_ms"] = timeit(lambda: U.linear_f16(x0, s0h, b, out=y))
+    out["fwd16_264_ms"] = timeit(lambda: U.linear_f16(h, s1h, b, out=y))
     _, bits = U.linear_tc(h, s1, U.MM_LINEAR_RELU, bias=b, want_bits=True)
     out["dgrad_264_ms"] = timeit(lambda: U.linear_tc(dz, s1t, U.MM_LINEAR_GATE, gate_bits=bits, out=y))
     out["plain_264_dz_ms"] = timeit(lambda: U.linear_tc(dz, s1t, U.MM_LINEAR_PLAIN, out=y))
