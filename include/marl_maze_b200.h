@@ -160,10 +160,12 @@ int mm_gae(const float *reward, const float *value, const uint8_t *done, const f
  *   logp [E] f32 = joint log-prob of both agents' actions (PPO.py:118,121); value [E] f32 (may be NULL); logits_out [E][2][6]
  *   f32 (may be NULL; 5 move logits + mark logit, unmasked).
  */
-#define MM_POLICY_N_OFFSETS 41
+#define MM_POLICY_N_OFFSETS 44
 int mm_policy_offsets(int32_t *out /* [MM_POLICY_N_OFFSETS]: the blocks listed above, then c0_wt, c1_wt (critic weights transposed), tokm, tokb
                                       (per-token affine maps), l{0,1,2}_{h16,l16} (FP16 hi / lo split of 2^e W, fp16 [264][kpad] with kpad = 480,
-                                      288, 288, two halves per float slot) and l{0,1,2}_asc (the scalar 2^-e) -- read by MM_POLICY_FP16_SPLIT */);
+                                      288, 288, two halves per float slot) and l{0,1,2}_asc (the scalar 2^-e) -- read by MM_POLICY_FP16_SPLIT; lh_h16, lh_l16,
+                                      lh_asc: the same split of the six head rows, fp16 [16][288] (rows 6.., columns 264.. zero) -- read by
+                                      MM_POLICY_FUSED_TRUNK */);
 /* critic only: value [E] = Critic(obs [E][2][65]) (networks.py:96-102); used for the bootstrap value V(s_T) */
 int mm_critic_forward(const float *weights, const float *obs, int n_envs, float *value, void *stream);
 size_t mm_sizeof_policy_scratch(int n_envs);
@@ -177,6 +179,8 @@ int mm_counter_add(uint64_t *counter_dev, uint64_t v, void *stream);
 #define MM_POLICY_OVERLAP_CRITIC 2 /* flags: run the critic on an internal side stream forked from / joined to `stream` (capturable) */
 #define MM_POLICY_FP16_SPLIT 4 /* flags (with MM_POLICY_TCGEN05): the 3xFP16 kernel -- kind::f16 MMAs on the fp16 hi/lo split of the operands, 128 x 128|144
                                   tiles, two CTAs per SM (csrc/mm_linear16.cu) -- instead of the 3xTF32 one */
+#define MM_POLICY_FUSED_TRUNK 8 /* flags (with MM_POLICY_TCGEN05 | MM_POLICY_FP16_SPLIT): the three trunk layers, the heads and the sampling as ONE persistent
+                                   kernel, activations resident in shared memory between the layers (csrc/mm_trunk_fused.cu) */
 
 /*
  * K5 -- building blocks of the PPO actor update (PPO.py:58-85: loss.backward() through Actor.layers), SURVEY 8(f).1.

@@ -20,6 +20,7 @@ int policy_offsets_host(int32_t* out);
 cudaError_t launch_linear_f16x3(const float* x, const void* w_hi, const void* w_lo, int n_rows_w, int kpad, const float* acc_scale, const float* bias, float* y, int ldy,
                                 int M, int K, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, float* heads_part,
                                 cudaStream_t stream);
+void trunk_fused_set_profile_buffer(unsigned long long* p);
 cudaError_t launch_selftest_div(int amax, int bmax, unsigned long long* mismatches, cudaStream_t stream);
 cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream);
 __global__ void k_load_layouts(ulonglong2*, ulonglong2*, uint4*, int, int, int, int, const uint8_t*, const int32_t*, uint16_t*);
@@ -56,6 +57,8 @@ static StepParams make_params(const mm_state* st) {
 extern "C" {
 
 int mm_abi_version(void) { return 1; }
+/* developer hook (not in the public header): cycle counters of the fused trunk kernel in -DMM_TF_PROFILE builds, [148][16] u64 */
+int mm_debug_trunk_profile_buffer(unsigned long long* p) { trunk_fused_set_profile_buffer(p); return MM_OK; }
 #ifndef MM_SRC_HASH
 #define MM_SRC_HASH "unknown"
 #endif

@@ -31,6 +31,9 @@ struct PolicyOffsets {
     // FP16 hi/lo splits of 2^e * W for the three trunk layers (mm_linear16.cu): fp16 [264][kpad] each, kpad = K rounded up to 32 (480, 288,
     // 288; zero padded), stored in this fp32 buffer (two halves per float slot); l*_asc = the device scalar 2^-e
     int l0_h16, l0_l16, l1_h16, l1_l16, l2_h16, l2_l16, l0_asc, l1_asc, l2_asc;
+    // the six head rows (5 move + 1 mark) as a fourth "layer" of the fused trunk kernel: fp16 hi / lo of 2^e [move_head; mark_head], [16][288] (rows 6.. and
+    // columns 264.. zero), and the scalar 2^-e
+    int lh_h16, lh_l16, lh_asc;
     int total;
 };
 constexpr int kPad0 = 480, kPad1 = 288;   // K = 460 / 264 rounded up to the 32-element k-block
@@ -48,6 +51,7 @@ __host__ __device__ inline PolicyOffsets policy_offsets() {
     o.tokm = take(60 * kTok * 4); o.tokb = take(60 * kTok);
     o.l0_h16 = take(kHid * kPad0 / 2); o.l0_l16 = take(kHid * kPad0 / 2); o.l1_h16 = take(kHid * kPad1 / 2); o.l1_l16 = take(kHid * kPad1 / 2);
     o.l2_h16 = take(kHid * kPad1 / 2); o.l2_l16 = take(kHid * kPad1 / 2); o.l0_asc = take(1); o.l1_asc = take(1); o.l2_asc = take(1);
+    o.lh_h16 = take(16 * kPad1 / 2); o.lh_l16 = take(16 * kPad1 / 2); o.lh_asc = take(1);
     o.total = p;
     return o;
 }
@@ -156,6 +160,13 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_MINBLOCKS) k_tokens(con
 #ifndef MM_TOK_R_MINBLOCKS
 #define MM_TOK_R_MINBLOCKS (MM_TOK_ROWS <= 2 ? 4 : 3)
 #endif
+// floats per token in the per-warp key / value tile: 12 key (10 used) + 20 value = 32, padded to 36 -- at a 128-byte lane stride the
+// float4 stores of the 23 lanes all fell into the same four banks (ncu, profiles/r02h: 21 M bank conflicts, 186 store wavefronts per row
+// instead of 24); 144 bytes puts the 8 lanes of a quarter-warp on 8 different 16-byte bank groups
+#ifndef MM_TOK_TSTRIDE
+#define MM_TOK_TSTRIDE 36
+#endif
+constexpr int kTokTS = MM_TOK_TSTRIDE;
 template <int R>
 __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ x0, int nrows) {
     const PolicyOffsets o = policy_offsets();
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
     float (*s_m)[kTok][4] = reinterpret_cast<float (*)[kTok][4]>(tk_smem);                        // [60][23][4]
     float (*s_b)[kTok] = reinterpret_cast<float (*)[kTok]>(tk_smem + 60 * kTok * 4);               // [60][23]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = tk_smem + 60 * kTok * 5 + w * (R * kTok * 32);                                   // per warp: R rows x 23 tokens x (12 key + 20 value)
+    float* tile = tk_smem + 60 * kTok * 5 + w * (R * kTok * kTokTS);                                   // per warp: R rows x 23 tokens x (12 key + 20 value)
     for (int i = threadIdx.x; i < 60 * kTok * 4; i += blockDim.x) (&s_m[0][0][0])[i] = wts[o.tokm + i];
     for (int i = threadIdx.x; i < 60 * kTok; i += blockDim.x) (&s_b[0][0])[i] = wts[o.tokb + i];
     __syncthreads();
@@ -191,7 +202,7 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
             if (on) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    float* kt = tile + (r * kTok + a) * 32;
+                    float* kt = tile + (r * kTok + a) * kTokTS;
                     *reinterpret_cast<float4*>(kt) = make_float4(kk[r][0], kk[r][1], kk[r][2], kk[r][3]);
                     *reinterpret_cast<float4*>(kt + 4) = make_float4(kk[r][4], kk[r][5], kk[r][6], kk[r][7]);
                     *reinterpret_cast<float2*>(kt + 8) = make_float2(kk[r][8], kk[r][9]);
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
             }
             if (on) {
 #pragma unroll
-                for (int r = 0; r < R; r++) *reinterpret_cast<float4*>(tile + (r * kTok + a) * 32 + 12 + 4 * d4) = make_float4(vv[r][0], vv[r][1], vv[r][2], vv[r][3]);
+                for (int r = 0; r < R; r++) *reinterpret_cast<float4*>(tile + (r * kTok + a) * kTokTS + 12 + 4 * d4) = make_float4(vv[r][0], vv[r][1], vv[r][2], vv[r][3]);
             }
         }
 #pragma unroll
@@ -231,13 +242,13 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
         // ---- attention phase, one row at a time (networks.py:75-82)
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float* kt = tile + r * kTok * 32;
+            const float* kt = tile + r * kTok * kTokTS;
             float p[kTok];
             float mx = -INFINITY;
 #pragma unroll
             for (int b = 0; b < kTok; b++) {
-                const float4 k0 = *reinterpret_cast<const float4*>(kt + b * 32), k1 = *reinterpret_cast<const float4*>(kt + b * 32 + 4);
-                const float2 k2 = *reinterpret_cast<const float2*>(kt + b * 32 + 8);
+                const float4 k0 = *reinterpret_cast<const float4*>(kt + b * kTokTS), k1 = *reinterpret_cast<const float4*>(kt + b * kTokTS + 4);
+                const float2 k2 = *reinterpret_cast<const float2*>(kt + b * kTokTS + 8);
                 float acc = q[r][0] * k0.x;
                 acc = fmaf(q[r][1], k0.y, acc); acc = fmaf(q[r][2], k0.z, acc); acc = fmaf(q[r][3], k0.w, acc);
                 acc = fmaf(q[r][4], k1.x, acc); acc = fmaf(q[r][5], k1.y, acc); acc = fmaf(q[r][6], k1.z, acc); acc = fmaf(q[r][7], k1.w, acc);
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
                 const float pb = p[b] * inv;
 #pragma unroll
                 for (int d4 = 0; d4 < kEmb / 4; d4++) {
-                    const float4 vv = *reinterpret_cast<const float4*>(kt + b * 32 + 12 + 4 * d4);
+                    const float4 vv = *reinterpret_cast<const float4*>(kt + b * kTokTS + 12 + 4 * d4);
                     ctx[4 * d4] = fmaf(pb, vv.x, ctx[4 * d4]); ctx[4 * d4 + 1] = fmaf(pb, vv.y, ctx[4 * d4 + 1]);
                     ctx[4 * d4 + 2] = fmaf(pb, vv.z, ctx[4 * d4 + 2]); ctx[4 * d4 + 3] = fmaf(pb, vv.w, ctx[4 * d4 + 3]);
                 }
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
         __syncwarp();  // the tiles are rewritten by the next R rows of this warp
     }
 }
-constexpr int kTokRSmem = (60 * kTok * 5 + kTokWarps * MM_TOK_ROWS * kTok * 32) * (int)sizeof(float);
+constexpr int kTokRSmem = (60 * kTok * 5 + kTokWarps * MM_TOK_ROWS * kTok * kTokTS) * (int)sizeof(float);
 static cudaError_t launch_tokens_any(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
 #if MM_TOK_ROWS >= 2
     static PerDeviceFlag configured;
@@ -628,7 +639,7 @@ int policy_offsets_host(int32_t* out) {
     const PolicyOffsets o = policy_offsets();
     const int v[MM_POLICY_N_OFFSETS] = {o.proj_w, o.proj_b, o.proj_col, o.proj_dim, o.att_k, o.att_q, o.att_v, o.l0_w, o.l0_b, o.l1_w, o.l1_b, o.l2_w, o.l2_b,
                        o.head_w, o.head_b, o.c0_w, o.c0_b, o.c1_w, o.c1_b, o.c2_w, o.c2_b, o.total, o.l0_whi, o.l0_wlo, o.l1_whi, o.l1_wlo, o.l2_whi, o.l2_wlo,
-                       o.c0_wt, o.c1_wt, o.tokm, o.tokb, o.l0_h16, o.l0_l16, o.l1_h16, o.l1_l16, o.l2_h16, o.l2_l16, o.l0_asc, o.l1_asc, o.l2_asc};
+                       o.c0_wt, o.c1_wt, o.tokm, o.tokb, o.l0_h16, o.l0_l16, o.l1_h16, o.l1_l16, o.l2_h16, o.l2_l16, o.l0_asc, o.l1_asc, o.l2_asc, o.lh_h16, o.lh_l16, o.lh_asc};
     for (int i = 0; i < MM_POLICY_N_OFFSETS; i++) out[i] = v[i];
     return 0;
 }
@@ -639,8 +650,12 @@ cudaError_t launch_linear_f16x3(const float* x, const void* w_hi, const void* w_
                                 int M, int K, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, float* heads_part,
                                 cudaStream_t stream);
 
+cudaError_t launch_trunk_fused(const float* x0, const void* const w16[4][2], const float* const asc[4], const float* const bias[4], const HeadArgs& heads, int M,
+                               cudaStream_t stream);
+
 // flags bit 0: trunk GEMMs on tcgen05 instead of the fp32 SIMT tiles; bit 1: critic on a forked side stream; bit 2 (with bit 0): the
-// 3xFP16 N-split kernel (mm_linear16.cu, two CTAs per SM) instead of the 3xTF32 one (mm_policy_tc.cu)
+// 3xFP16 N-split kernel (mm_linear16.cu, two CTAs per SM) instead of the 3xTF32 one (mm_policy_tc.cu); bit 3 (with bits 0 and 2): the three
+// trunk layers + heads as ONE persistent kernel with the activations resident in shared memory (mm_trunk_fused.cu)
 cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* masks, int E, float* scratch, const uint8_t* actions_in,
                           uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter,
                           int flags, const uint64_t* counter_dev, cudaStream_t stream) {
@@ -677,7 +692,13 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
     }
     { cudaError_t e = launch_tokens_any(wts, obs, R, x0, stream); if (e != cudaSuccess) return e; }
-    if ((flags & 5) == 5) {
+    if ((flags & 13) == 13) {
+        const void* const w16[4][2] = {{wts + o.l0_h16, wts + o.l0_l16}, {wts + o.l1_h16, wts + o.l1_l16}, {wts + o.l2_h16, wts + o.l2_l16}, {wts + o.lh_h16, wts + o.lh_l16}};
+        const float* const asc[4] = {wts + o.l0_asc, wts + o.l1_asc, wts + o.l2_asc, wts + o.lh_asc};
+        const float* const bias[4] = {wts + o.l0_b, wts + o.l1_b, wts + o.l2_b, wts + o.head_b};
+        cudaError_t e = launch_trunk_fused(x0, w16, asc, bias, ha, R, stream);
+        if (e != cudaSuccess) return e;
+    } else if ((flags & 5) == 5) {
         cudaError_t e;
         if ((e = launch_linear_f16x3(x0, wts + o.l0_h16, wts + o.l0_l16, kHid, kPad0, wts + o.l0_asc, wts + o.l0_b, h1, kHid, R, kX0, nullptr, nullptr, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;
         if ((e = launch_linear_f16x3(h1, wts + o.l1_h16, wts + o.l1_l16, kHid, kPad1, wts + o.l1_asc, wts + o.l1_b, h2, kHid, R, kHid, nullptr, nullptr, nullptr, nullptr, nullptr, stream)) != cudaSuccess) return e;

@@ -16,7 +16,7 @@ from .networks import FEATURE_DIMS, EMBEDDING_DIM
 
 _NAMES = ["proj_w", "proj_b", "proj_col", "proj_dim", "att_k", "att_q", "att_v", "l0_w", "l0_b", "l1_w", "l1_b", "l2_w", "l2_b",
           "head_w", "head_b", "c0_w", "c0_b", "c1_w", "c1_b", "c2_w", "c2_b", "total", "l0_whi", "l0_wlo", "l1_whi", "l1_wlo", "l2_whi", "l2_wlo", "c0_wt", "c1_wt", "tokm", "tokb",
-          "l0_h16", "l0_l16", "l1_h16", "l1_l16", "l2_h16", "l2_l16", "l0_asc", "l1_asc", "l2_asc"]
+          "l0_h16", "l0_l16", "l1_h16", "l1_l16", "l2_h16", "l2_l16", "l0_asc", "l1_asc", "l2_asc", "lh_h16", "lh_l16", "lh_asc"]
 
 
 def offsets() -> dict:
@@ -82,7 +82,12 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
             buf[o[f"l{i}_h16"]:o[f"l{i}_h16"] + n16] = h16.reshape(-1).view(torch.float32)
             buf[o[f"l{i}_l16"]:o[f"l{i}_l16"] + n16] = l16.reshape(-1).view(torch.float32)
             buf[o[f"l{i}_asc"]:o[f"l{i}_asc"] + 1] = asc
-        put("head_w", torch.cat([actor.move_head.weight, actor.mark_head.weight], 0)); put("head_b", torch.cat([actor.move_head.bias, actor.mark_head.bias]))
+        head_w = torch.cat([actor.move_head.weight, actor.mark_head.weight], 0).detach().to(dev, torch.float32)
+        put("head_w", head_w); put("head_b", torch.cat([actor.move_head.bias, actor.mark_head.bias]))
+        h16, l16, asc = f16_split(torch.nn.functional.pad(head_w, (0, 0, 0, 10)), 288)   # the heads as a fourth layer of the fused trunk kernel: [16][288]
+        buf[o["lh_h16"]:o["lh_h16"] + h16.numel() // 2] = h16.reshape(-1).view(torch.float32)
+        buf[o["lh_l16"]:o["lh_l16"] + l16.numel() // 2] = l16.reshape(-1).view(torch.float32)
+        buf[o["lh_asc"]:o["lh_asc"] + 1] = asc
         for i in range(3):
             put(f"c{i}_w", critic.layers[i].weight); put(f"c{i}_b", critic.layers[i].bias)
         put("c0_wt", critic.layers[0].weight.t().contiguous()); put("c1_wt", critic.layers[1].weight.t().contiguous())
@@ -98,7 +103,7 @@ def pack_weights(actor, critic, device=None) -> torch.Tensor:
 
 class PolicyRunner:
     def __init__(self, actor, critic, num_envs: int, device, env_offset: int = 0, seed: int = 0, tensor_cores: bool = True, overlap_critic: bool = True,
-                 fp16_split: bool | None = None):
+                 fp16_split: bool | None = None, fused_trunk: bool | None = None):
         self.lib = _abi.lib()
         self.E, self.device, self.env_offset, self.seed = int(num_envs), torch.device(device), int(env_offset), int(seed) & (2**64 - 1)
         self.actor, self.critic = actor, critic
@@ -109,8 +114,11 @@ class PolicyRunner:
         self.launches = 0
         if fp16_split is None:   # default: the 3xFP16 two-CTA-per-SM kernel; MARL_MAZE_TF32_TRUNK=1 keeps the 3xTF32 one (A/B runs)
             fp16_split = os.environ.get("MARL_MAZE_TF32_TRUNK", "0") != "1"
-        # MM_POLICY_TCGEN05 | MM_POLICY_OVERLAP_CRITIC | MM_POLICY_FP16_SPLIT
-        self.flags = (1 if tensor_cores else 0) | (2 if overlap_critic else 0) | (4 if (tensor_cores and fp16_split) else 0)
+        if fused_trunk is None:  # default: the three trunk layers + heads as one persistent kernel; MARL_MAZE_FUSED_TRUNK=0 keeps one kernel per layer
+            fused_trunk = os.environ.get("MARL_MAZE_FUSED_TRUNK", "1") != "0"
+        fused_trunk = bool(fused_trunk and tensor_cores and fp16_split)
+        # MM_POLICY_TCGEN05 | MM_POLICY_OVERLAP_CRITIC | MM_POLICY_FP16_SPLIT | MM_POLICY_FUSED_TRUNK
+        self.flags = (1 if tensor_cores else 0) | (2 if overlap_critic else 0) | (4 if (tensor_cores and fp16_split) else 0) | (8 if fused_trunk else 0)
 
     def refresh(self):
         """Re-pack after an optimiser step -- in place, so that captured CUDA graphs keep pointing at live weights."""
@@ -148,6 +156,6 @@ class PolicyRunner:
         _abi.check(self.lib.mm_policy_forward(p(self.weights), p(obs), p(masks), E, p(self.scratch), p(actions_in), p(actions_out), p(logp),
                                               p(value if want_value else None), p(logits), self.env_offset, C.c_uint64(self.seed), C.c_uint64(counter),
                                               self.flags, p(self.counter_dev), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mm_policy_forward")
-        # tokens + 3 trunk layers (+ heads on the SIMT path, + k_heads_finish on the 3xFP16 path) + critic
-        self.launches += (5 if (self.flags & 5) == 5 else 4 if self.flags & 1 else 5) + (1 if want_value else 0)
+        # tokens + (fused trunk | 3 trunk layers (+ heads on the SIMT path, + k_heads_finish on the 3xFP16 path)) + critic
+        self.launches += (2 if (self.flags & 13) == 13 else 5 if (self.flags & 5) == 5 else 4 if self.flags & 1 else 5) + (1 if want_value else 0)
         return (actions_in if actions_in is not None else actions_out), logp, (value if want_value else None)

@@ -14,15 +14,17 @@ TOL = dict(rtol=1e-5, atol=2e-6)
 # Raw LOGITS of the tensor-core path: tcgen05 accumulates its K = 460/264-long sums with truncation inside the tensor core, which
 # leaves ~1e-6 relative (max 4e-6 absolute, tools/k4_accuracy.py) on the logits -- 10x the fp32 SIMT path, still far inside the
 # north-star bar on the quantities it names (log-probs and values: 1e-5 relative, asserted with TOL for BOTH paths below).
-TOL_LOGITS = {"simt_fp32": TOL, "tcgen05_3xtf32": dict(rtol=1e-5, atol=8e-6), "tcgen05_3xfp16": dict(rtol=1e-5, atol=8e-6)}
-PATHS = ["simt_fp32", "tcgen05_3xtf32", "tcgen05_3xfp16"]
+TOL_LOGITS = {"simt_fp32": TOL, "tcgen05_3xtf32": dict(rtol=1e-5, atol=8e-6), "tcgen05_3xfp16": dict(rtol=1e-5, atol=8e-6),
+              "tcgen05_fused_trunk": dict(rtol=1e-5, atol=8e-6)}
+PATHS = ["simt_fp32", "tcgen05_3xtf32", "tcgen05_3xfp16", "tcgen05_fused_trunk"]
 
 
 def _runner(actor, critic, E, path, **kw):
-    """The three trunk implementations behind mm_policy_forward: fp32 SIMT tiles, 3xTF32 tcgen05 (mm_policy_tc.cu), 3xFP16 tcgen05 with two
-    CTAs per SM (mm_linear16.cu, the default)."""
+    """The four trunk implementations behind mm_policy_forward: fp32 SIMT tiles, 3xTF32 tcgen05 (mm_policy_tc.cu), 3xFP16 tcgen05 with two
+    CTAs per SM (mm_linear16.cu), and the three layers + heads as one persistent 3xFP16 kernel (mm_trunk_fused.cu, the default)."""
     from marl_maze_b200.policy import PolicyRunner
-    return PolicyRunner(actor, critic, E, "cuda", tensor_cores=path != "simt_fp32", fp16_split=path == "tcgen05_3xfp16", **kw)
+    return PolicyRunner(actor, critic, E, "cuda", tensor_cores=path != "simt_fp32", fp16_split=path in ("tcgen05_3xfp16", "tcgen05_fused_trunk"),
+                        fused_trunk=path == "tcgen05_fused_trunk", **kw)
 
 
 def _nets(seed, faithful=True):
