@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(L16_THREADS, 2) k_linear_f16x3(const __grid_co
     uint64_t* tmem_full = a_free + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
     const int tile = blockIdx.x / args.n_split, half = blockIdx.x - tile * args.n_split;
     const int m0 = tile * L16_BM;
     const int n0 = half * L16_NSPLIT0;
@@ -108,26 +108,30 @@ __global__ void __launch_bounds__(L16_THREADS, 2) k_linear_f16x3(const __grid_co
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer
+        {  // ===== TMA producer (the whole warp runs the loop, one elected lane issues: see elect_one)
             const uint32_t w_tx = 2u * (uint32_t)n_mma * L16_WROW;   // the boxes are n_mma rows tall (host: one map pair per half)
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % L16_STAGES, sa = kb & 1;
                 const int k0 = kb * L16_BK;
                 mbar_wait(&a_free[sa], ((kb >> 1) & 1) ^ 1);      // the splitter has read the tile that used this slot two k-blocks ago
-                mbar_expect_tx(&a_full[sa], L16_A_BYTES);
-                tma_load_2d(smem + L16_A_OFF + sa * L16_A_BYTES, &maps.a, k0, m0, &a_full[sa]);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[sa], L16_A_BYTES);
+                    tma_load_2d(smem + L16_A_OFF + sa * L16_A_BYTES, &maps.a, k0, m0, &a_full[sa]);
+                }
                 mbar_wait(&empty[s], ((kb / L16_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full[s], w_tx);
                 uint8_t* st = smem + s * L16_W_BYTES;
-                tma_load_2d(st, &maps.w_hi[half], k0, n0, &full[s]);
-                tma_load_2d(st + L16_WHALF, &maps.w_lo[half], k0, n0, &full[s]);
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], w_tx);
+                    tma_load_2d(st, &maps.w_hi[half], k0, n0, &full[s]);
+                    tma_load_2d(st + L16_WHALF, &maps.w_lo[half], k0, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer: D[128 x n_mma] += A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T, two K = 16 steps per k-block
+        {  // ===== MMA issuer (whole warp loops, one elected lane issues): D[128 x n_mma] += A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T, two K = 16 steps per k-block
             const uint32_t idesc = l16_idesc(L16_BM, n_mma);
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % L16_STAGES;
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(L16_THREADS, 2) k_linear_f16x3(const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * L16_W_BYTES);
                 const uint64_t b_hi = l16_desc(st), b_lo = l16_desc(st + L16_WHALF);
+                if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 2; k++) {  // UMMA_K = 16 halves = 32 bytes: advance the start address inside the 64-byte swizzle row
                     const uint64_t o = (uint64_t)(k * 2);
@@ -146,8 +151,9 @@ __global__ void __launch_bounds__(L16_THREADS, 2) k_linear_f16x3(const __grid_co
                     umma_f16_ts(tmem_base, ta_hi, b_lo + o, idesc, 1u);
                 }
                 umma_commit(&empty[s]);  // frees the weight stage AND the operand columns when these MMAs have read them
+                }
             }
-            umma_commit(tmem_full);
+            if (elect_one()) umma_commit(tmem_full);
         }
     } else {
         // ===== splitter: thread = row (its TMEM lane); the two warps of a lane quarter take k-columns 0..15 and 16..31 of the k-block

@@ -284,8 +284,16 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
     }
 }
 constexpr int kTokRSmem = (60 * kTok * 5 + kTokWarps * MM_TOK_ROWS * kTok * kTokTS) * (int)sizeof(float);
+// -DMM_TOK_MMA=0 keeps the SIMT token kernel (A/B runs); the default is the HMMA version (mm_tokens_mma.cu)
+#ifndef MM_TOK_MMA
+#define MM_TOK_MMA 1
+#endif
+cudaError_t launch_tokens_mma(const float* wts, const float* obs, int R, float* x0, int off_tokm, int off_tokb, int off_col, int off_dim, cudaStream_t stream);
 static cudaError_t launch_tokens_any(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
-#if MM_TOK_ROWS >= 2
+#if MM_TOK_MMA
+    const PolicyOffsets o = policy_offsets();
+    return launch_tokens_mma(wts, obs, R, x0, o.tokm, o.tokb, o.proj_col, o.proj_dim, stream);
+#elif MM_TOK_ROWS >= 2
     static PerDeviceFlag configured;
     if (configured.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(k_tokens_r<MM_TOK_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTokRSmem);

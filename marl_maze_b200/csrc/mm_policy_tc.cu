@@ -107,7 +107,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     uint64_t* a_free = a_full + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_free + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
     const int nkb = (K + TC_BK - 1) / TC_BK;
 
@@ -124,22 +124,26 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer
+        {  // ===== TMA producer (the whole warp runs the loop, one elected lane issues: see elect_one)
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % TC_STAGES;
                 const int k0 = kb * TC_BK;
                 uint8_t* st = smem + s * TC_STAGE_BYTES;
 #if MM_TC_A_TMEM
                 mbar_wait(a_free, (kb & 1) ^ 1);              // the splitter has read the previous activation tile out of the slot
-                mbar_expect_tx(a_full, TC_A_BYTES);
-                tma_load_2d(smem + TC_A_SLOT_OFF, &maps.a, k0, m0, a_full);
+                if (elect_one()) {
+                    mbar_expect_tx(a_full, TC_A_BYTES);
+                    tma_load_2d(smem + TC_A_SLOT_OFF, &maps.a, k0, m0, a_full);
+                }
                 mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+                if (elect_one()) {
                 mbar_expect_tx(&full[s], TC_W_BYTES);
 #else
                 mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+                if (elect_one()) {
                 mbar_expect_tx(&full[s], TC_STAGE_BYTES - TC_A_BYTES);  // the A_lo slot is produced in-kernel
                 tma_load_2d(st, &maps.a, k0, m0, &full[s]);
 #endif
@@ -147,10 +151,11 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 tma_load_2d(st + TC_W_OFF + TC_B1_BYTES, &maps.w2_hi, k0, TC_N1, &full[s]);
                 tma_load_2d(st + TC_W_OFF + TC_B1_BYTES + TC_B2_BYTES, &maps.w1_lo, k0, 0, &full[s]);
                 tma_load_2d(st + TC_W_OFF + 2 * TC_B1_BYTES + TC_B2_BYTES, &maps.w2_lo, k0, TC_N1, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer: D[128 x 272] (two N chunks) += A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T
+        {  // ===== MMA issuer (whole warp loops, one elected lane issues): D[128 x 272] (two N chunks) += A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T
             constexpr uint32_t id1 = umma_idesc_tf32(TC_BM, TC_N1), id2 = umma_idesc_tf32(TC_BM, TC_N2);
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % TC_STAGES;
@@ -158,6 +163,7 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
                 mbar_wait(&split_done[s], (kb / TC_STAGES) & 1);  // A tile rewritten as hi, lo tile written (fenced to the async proxy)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
+                if (elect_one()) {
 #if !MM_TC_A_TMEM
                 const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TC_A_BYTES);
 #endif
@@ -185,8 +191,9 @@ k_linear_tf32x3(const __grid_constant__ TcMaps maps, const float* __restrict__ b
 #endif
                 }
                 umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+                }
             }
-            umma_commit(tmem_full);      // accumulator complete
+            if (elect_one()) umma_commit(tmem_full);      // accumulator complete
         }
     } else {
         // ===== splitter (main loop): 128 threads turn each landed fp32 A tile into (hi in place, lo beside it)

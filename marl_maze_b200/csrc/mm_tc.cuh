@@ -64,6 +64,16 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* v)
 __device__ __forceinline__ uint32_t tf32_rn_bits(float x) {  // cvt.rna.tf32.f32 on finite values, on the integer pipe
     return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
 }
+// One lane of a fully active warp.  The TMA-producer and MMA-issuer warps run their loops with ALL lanes (warp-uniform control flow, indices and
+// addresses, so the compiler keeps the operands of UTMALDG / UTCHMMA in uniform registers) and only ISSUE under this predicate.  With the loops inside
+// `if (lane == 0)` every tcgen05.mma was compiled into an ELECT + 6 x R2UR.BROADCAST "waterfall" loop, ~85 clocks of issue time per MMA -- more than a
+// 128 x 144 x 16 MMA takes to execute (profiles/r02m: 70.7 -> 49.6 kclk per 128-row tile of the fused trunk kernel from this change alone).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }   // provably warp-uniform for the compiler
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

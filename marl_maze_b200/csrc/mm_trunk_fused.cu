@@ -109,14 +109,6 @@ __device__ __forceinline__ void tf_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// One lane of a fully active warp.  The producer and MMA warps run their loops with ALL lanes (warp-uniform control flow, indices and addresses, so the
-// compiler keeps the operands of UTMALDG / UTCHMMA in uniform registers) and only issue under this predicate: with the loops inside `if (lane == 0)` every
-// tcgen05.mma was wrapped in an ELECT + 6 x R2UR.BROADCAST "waterfall" loop, ~85 clocks of issue time per MMA -- more than the MMA takes to execute.
-__device__ __forceinline__ bool tf_elect_one() {
-    uint32_t pred;
-    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void tf_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
 // -DMM_TF_PROFILE: per-CTA cycle counters of where each role waits (written to args.prof [blocks][16] u64); tools/trunk_profile.py
@@ -199,7 +191,7 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_free + 1);
     float* s_bias = reinterpret_cast<float*>(smem + TF_BIAS_OFF);   // [3][264] + [8]
 
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // the shuffle tells the compiler it is warp-uniform
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < TF_WSTAGES; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], TF_CLUSTER); }   // every CTA of the cluster frees a stage
         for (int s = 0; s < TF_ASLOTS; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_free[s], 32 * TF_EPI_WARPS); }
@@ -243,7 +235,7 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                             for (; a_issued < want; a_issued++, ait++) {
                                 const int sa = ait % TF_ASLOTS;
                                 TF_PROF_WAIT(1, mbar_wait(&a_free[sa], ((ait / TF_ASLOTS) & 1) ^ 1));
-                                if (tf_elect_one()) {
+                                if (elect_one()) {
                                     mbar_expect_tx(&a_full[sa], TF_A_BYTES);
                                     tma_load_2d(hlo + sa * TF_A_BYTES, &maps.a, a_issued * TF_BK, m0, &a_full[sa]);
                                 }
@@ -257,7 +249,7 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                             const CUtensorMap* mh = layer == 3 ? &maps.wh[0] : &maps.w[layer][half][0];
                             const CUtensorMap* ml = layer == 3 ? &maps.wh[1] : &maps.w[layer][half][1];
                             const int n0 = layer == 3 ? 0 : half * TF_N0;
-                            if (tf_elect_one()) {
+                            if (elect_one()) {
                                 mbar_expect_tx(&w_full[s], 2u * (uint32_t)n_rows * TF_WROW);   // the whole tile: this CTA's part + the peer's
                                 if (TF_CLUSTER > 1) {
                                     const int part = n_rows / TF_CLUSTER, r0 = (int)crank * part;
@@ -319,7 +311,7 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                             if (layer == 0) { ta_hi = tmem_base + TF_TMEM_A_COL + (uint32_t)(os * 32 + k * 8); ta_lo = ta_hi + 16; }
                             else { ta_hi = tmem_base + TF_TMEM_H_COL + (uint32_t)(kb * 16 + k * 8); a_lo = tf_desc(smem_u32(hlo + kb * TF_H_KB_BYTES)) + o; }
                             const int kstep = kb * 2 + k;
-                            if (tf_elect_one())
+                            if (elect_one())
 #pragma unroll
                             for (int prod = 0; prod < 3; prod++) {   // hi.hi, lo.hi, hi.lo
                                 for (int half = 0; half < nh; half++) {
@@ -334,12 +326,12 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                         }
                         for (int half = 0; half < nh; half++) {
                             const int s = wit % TF_WSTAGES;
-                            if (tf_elect_one()) { if (TF_CLUSTER > 1) tf_commit_mc(&w_empty[s], cmask); else umma_commit(&w_empty[s]); }
+                            if (elect_one()) { if (TF_CLUSTER > 1) tf_commit_mc(&w_empty[s], cmask); else umma_commit(&w_empty[s]); }
                             wit++;
                         }
-                        if (layer == 0) { if (tf_elect_one()) umma_commit(&op_free[os]); oit++; }
+                        if (layer == 0) { if (elect_one()) umma_commit(&op_free[os]); oit++; }
                     }
-                    if (tf_elect_one()) umma_commit(d_full);
+                    if (elect_one()) umma_commit(d_full);
                 }
             }
 #ifdef MM_TF_PROFILE

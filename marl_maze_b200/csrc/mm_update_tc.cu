@@ -63,7 +63,7 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
     uint64_t* tmem_full = split_done + WG_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
     const int tiles = n_mt * n_nt;
     const int tile = blockIdx.x % tiles, slab = blockIdx.x / tiles;  // the tiles of one slab are neighbours: they share their H / dZ boxes in L2
     const int mt = tile % n_mt, nt = tile / n_mt;
@@ -87,30 +87,33 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer: 4 dZ boxes + 9 H boxes per stage, out-of-range columns / rows arrive as zeros
+        {  // ===== TMA producer (the whole warp runs the loop, one elected lane issues: see elect_one): 4 dZ boxes + 9 H boxes per stage, out-of-range columns / rows arrive as zeros
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % WG_STAGES;
                 mbar_wait(&empty[s], ((kb / WG_STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * WG_STAGE_BYTES;
-                mbar_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
                 const int r0 = (kb0 + kb) * WG_BK;
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
 #pragma unroll
-                for (int j = 0; j < WG_M / 32; j++) tma_load_2d(st + j * WG_BOX_BYTES, &maps.a, mt * WG_M + 32 * j, r0, &full[s]);
+                    for (int j = 0; j < WG_M / 32; j++) tma_load_2d(st + j * WG_BOX_BYTES, &maps.a, mt * WG_M + 32 * j, r0, &full[s]);
 #pragma unroll
-                for (int j = 0; j < WG_N / 32; j++) tma_load_2d(st + WG_A_BYTES + j * WG_BOX_BYTES, &maps.b, nt * WG_N + 32 * j, r0, &full[s]);
+                    for (int j = 0; j < WG_N / 32; j++) tma_load_2d(st + WG_A_BYTES + j * WG_BOX_BYTES, &maps.b, nt * WG_N + 32 * j, r0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer: D[128 x 288] += dZ_hi^T H_hi + dZ_lo^T H_hi + dZ_hi^T H_lo
+        {  // ===== MMA issuer (whole warp loops, one elected lane issues): D[128 x 288] += dZ_hi^T H_hi + dZ_lo^T H_hi + dZ_hi^T H_lo
             constexpr uint32_t id1 = umma_idesc_tf32_mn(WG_M, WG_N1), id2 = umma_idesc_tf32_mn(WG_M, WG_N2);
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % WG_STAGES;
                 mbar_wait(&split_done[s], (kb / WG_STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * WG_STAGE_BYTES);
+                if (elect_one()) {
 #pragma unroll
                 for (int g = 0; g < WG_BK / 8; g++) {  // UMMA_K = 8 rows = 1024 bytes down every box
                     const uint32_t o = g * 1024u;
@@ -127,8 +130,9 @@ k_wgrad_tf32x3(const __grid_constant__ WgMaps maps, float* __restrict__ part, in
                     umma_tf32_ts(tmem_base + WG_N1, ta_hi, b2_lo, id2, 1u);
                 }
                 umma_commit(&empty[s]);
+                }
             }
-            umma_commit(tmem_full);
+            if (elect_one()) umma_commit(tmem_full);
         }
     } else {
         // ===== splitter, 8 warps.  H boxes: 2304 float4 per stage over 256 threads; thread t owns float4 t + 256 q, i.e. box q, row t/8,
