@@ -57,7 +57,7 @@ static_assert((2 * TF_WSTAGES + 2 * TF_ASLOTS + 2 * TF_OPS + 3) * 8 + 4 <= 512, 
 constexpr int TF_BIAS_FLOATS = 3 * TF_N + 8;                      // three trunk biases + the six head biases
 constexpr uint32_t TF_SMEM_BYTES = TF_BIAS_OFF + TF_BIAS_FLOATS * 4 + 1024 /*alignment slack*/;
 static_assert(TF_SMEM_BYTES <= 232448, "one CTA per SM");
-constexpr int TF_EPI_WARPS = 8, TF_THREADS = 64 + 32 * TF_EPI_WARPS;
+constexpr int TF_EPI_WARPS = 8, TF_THREADS = 64 + 32 * TF_EPI_WARPS + 32;   // + the activation-tile producer warp
 // TMEM: D columns 0..271 | hi plane of the activations 272..407 (136 columns = 272 fp16 k-elements) | layer-0 operand ring 408 + 32 * stage
 constexpr uint32_t TF_TMEM_COLS = 512, TF_TMEM_H_COL = 272, TF_TMEM_A_COL = 408;
 static_assert(TF_TMEM_A_COL + 32 * TF_OPS <= TF_TMEM_COLS, "operand ring fits");
@@ -218,29 +218,15 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
     if (TF_CLUSTER > 1) tf_cluster_sync();   // the peer's barriers are initialised before anything of ours can land on them
 
     if (warp == 0) {
-        {  // ===== TMA producer (whole warp loops, one elected lane issues)
-            uint32_t wit = 0, ait = 0, t_local = 0;
+        {  // ===== weight producer (whole warp loops, one elected lane issues)
+            uint32_t wit = 0, t_local = 0;
             TF_PROF_DECL;
             for (int pair = pair0; pair < n_pairs; pair += pair_stride, t_local++) {
-                const int m0 = (pair * TF_CLUSTER + (int)crank) * TF_BM;
-                // the landing slots alias the lo plane: the previous tile's head MMAs (the 4th d_full completion of that tile) must be done
-                if (t_local) TF_PROF_WAIT(0, mbar_wait(d_full, (4 * t_local - 1) & 1));
-                int a_issued = 0;
+                // the weight stream does not depend on the tile: this warp runs ahead across layer and tile boundaries, bounded only by the ring
                 for (int layer = 0; layer < 4; layer++) {
                     const int nkb = layer == 0 ? kTfNKB0 : TF_HKB;
                     for (int kb = 0; kb < nkb; kb++) {
                         const int k0 = kb * TF_BK;
-                        if (layer == 0) {   // activation tiles run ahead of the weight ring by up to TF_ASLOTS k-blocks
-                            const int want = min(kTfNKB0, kb + TF_ASLOTS);
-                            for (; a_issued < want; a_issued++, ait++) {
-                                const int sa = ait % TF_ASLOTS;
-                                TF_PROF_WAIT(1, mbar_wait(&a_free[sa], ((ait / TF_ASLOTS) & 1) ^ 1));
-                                if (elect_one()) {
-                                    mbar_expect_tx(&a_full[sa], TF_A_BYTES);
-                                    tma_load_2d(hlo + sa * TF_A_BYTES, &maps.a, a_issued * TF_BK, m0, &a_full[sa]);
-                                }
-                            }
-                        }
                         for (int half = 0; half < (layer == 3 ? 1 : 2); half++) {
                             const int s = wit % TF_WSTAGES;
                             TF_PROF_WAIT(2, mbar_wait(&w_empty[s], ((wit / TF_WSTAGES) & 1) ^ 1));
@@ -266,7 +252,30 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                 }
             }
 #ifdef MM_TF_PROFILE
-            if (lane == 0) for (int i = 0; i < 3; i++) args.prof[blockIdx.x * 16 + i] = (unsigned long long)pf[i];
+            if (lane == 0) args.prof[blockIdx.x * 16 + 2] = (unsigned long long)pf[2];
+#endif
+        }
+    } else if (warp == 2 + TF_EPI_WARPS) {
+        {  // ===== activation-tile producer (layer 0): its own warp, so that a full landing ring never holds the weight stream back
+            uint32_t ait = 0, t_local = 0;
+            TF_PROF_DECL;
+            for (int pair = pair0; pair < n_pairs; pair += pair_stride, t_local++) {
+                const int m0 = (pair * TF_CLUSTER + (int)crank) * TF_BM;
+                // The landing slots alias the lo plane: the previous tile's head MMAs (the 4th d_full completion of that tile) must be done.  A parity
+                // wait only tells two consecutive phases apart and this warp can be several phases behind: it follows all four completions in order.
+                if (t_local)
+                    for (int i = 0; i < 4; i++) TF_PROF_WAIT(0, mbar_wait(d_full, (4 * (t_local - 1) + i) & 1));
+                for (int kb = 0; kb < kTfNKB0; kb++, ait++) {
+                    const int sa = ait % TF_ASLOTS;
+                    TF_PROF_WAIT(1, mbar_wait(&a_free[sa], ((ait / TF_ASLOTS) & 1) ^ 1));
+                    if (elect_one()) {
+                        mbar_expect_tx(&a_full[sa], TF_A_BYTES);
+                        tma_load_2d(hlo + sa * TF_A_BYTES, &maps.a, kb * TF_BK, m0, &a_full[sa]);
+                    }
+                }
+            }
+#ifdef MM_TF_PROFILE
+            if (lane == 0) for (int i = 0; i < 2; i++) args.prof[blockIdx.x * 16 + i] = (unsigned long long)pf[i];
 #endif
         }
     } else if (warp == 1) {
