@@ -51,7 +51,8 @@ typedef struct mm_state {
     void *env_grid, *env_hdr, *env_episode, *agent_a, *agent_b;
     int32_t n_envs, n_pool, smax, max_timestep;
     int32_t env_offset;   /* global id of env 0 of this shard (keys the per-env random streams; 0 on one GPU) */
-    int32_t reserved;
+    int32_t vision;       /* Agent(..., vision_range=r), maze_agent.py:16: byte 0 = agent 0's r, byte 1 = agent 1's; 1 <= r <= 4 (the stored grids keep a
+                             wall border of MM_PAD = r + 1 cells); 0 in a byte = the reference default 4 */
 } mm_state;
 
 int mm_abi_version(void);
@@ -102,6 +103,10 @@ int mm_generate(const mm_state *st, int first, int n, int side_lo, int side_hi, 
  * most of every SM to the kernels it runs beside */
 int mm_generate_ex(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
                 uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, int max_blocks, void *stream);
+/* as mm_generate_ex for the slots i of [first, first + n) with only[i] != 0 (only == NULL: all): the incremental pool refill -- the reference builds one
+ * maze per reset (maze.py:57), so between two rollouts only the pool slots whose mazes were consumed are built anew, the others stay */
+int mm_generate_masked(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
+                uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, int max_blocks, const uint8_t *only, void *stream);
 
 /*
  * Maze.reset() (maze.py:55-72) + Agent.reset() (maze_agent.py:59-79) for every env with reset_mask[e] != 0

@@ -145,8 +145,6 @@ class PPO:
             body()
         self._rollouts += 1
         maze._obs, maze._masks = obs[T], masks[T]
-        if self.prefetch_pool:  # the next rollout's mazes are carved on a side stream while the statistics and the update run
-            maze.prefetch_pool()
 
         # episode statistics for the progress prints (PPO.py:36-43): lengths of finished episodes and their shortest paths
         episode_lens, k_ep, e_ep = finished_episodes(done)
@@ -155,6 +153,8 @@ class PPO:
         b_shortest = spl_all[(e_ep + k_ep * E) % eng.P]
         solved, keys, rsum = torch.stack([(reward == 1).sum(), (reward == 0.5).sum(), reward.sum()]).tolist()
         self.last_stats = dict(env_steps=T * E, episodes=n_ep, solved=int(solved), keys=int(keys), mean_reward_per_step=rsum / (T * E), horizon=T, num_envs=E)
+        if self.prefetch_pool:  # the mazes this rollout consumed are rebuilt on a side stream, in place, while the update runs (after the statistics
+            maze.prefetch_pool()   # above: they read the consumed slots' headers)
         N = T * E
         return (obs[:T].reshape(N, 2, 65), actions.reshape(N, 2, 2).float(), logp.reshape(N), b_shortest.cpu().numpy(), episode_lens.cpu().numpy(),
                 masks[:T].reshape(N, 2, 6).bool(), adv.reshape(N), values[:T].reshape(N))

@@ -8,7 +8,7 @@ namespace mm {
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream);
 cudaError_t launch_gae(const float*, const float*, const uint8_t*, const float*, float*, float*, int, int, double, double, cudaStream_t);
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
-                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, cudaStream_t stream);
+                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, cudaStream_t stream);
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
                           int, const uint64_t*, cudaStream_t);
 cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream);
@@ -40,8 +40,9 @@ static int cuda_status(cudaError_t e) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
     return MM_ERR_CUDA;
 }
+static int vision_of(const mm_state* st, int a) { const int v = (st->vision >> (8 * a)) & 0xff; return v ? v : 4; }   // 0 = the reference default
 static bool state_ok(const mm_state* st) {
-    return st && st->n_envs > 0 && st->n_pool > 0 && st->smax >= 3 && st->smax <= MM_MAX_SIDE && st->max_timestep > 0 && st->pool_grid && st->pool_d2e &&
+    return st && vision_of(st, 0) <= 4 && vision_of(st, 1) <= 4 && (st->vision >> 16) == 0 && st->n_envs > 0 && st->n_pool > 0 && st->smax >= 3 && st->smax <= MM_MAX_SIDE && st->max_timestep > 0 && st->pool_grid && st->pool_d2e &&
            st->pool_hdr && st->env_grid && st->env_hdr && st->env_episode && st->agent_a && st->agent_b;
 }
 static StepParams make_params(const mm_state* st) {
@@ -51,6 +52,18 @@ static StepParams make_params(const mm_state* st) {
     p.agent_a = (uint4*)st->agent_a; p.agent_b = (uint32_t*)st->agent_b;
     p.E = st->n_envs; p.P = st->n_pool; p.rows = st->smax + 2 * MM_PAD; p.smax = st->smax; p.max_t = st->max_timestep; p.env_offset = st->env_offset;
     p.inv_max_t = 1.0f / (float)st->max_timestep;
+    for (int a = 0; a < 2; a++) {   // the ray features' values, in the reference's own float64 arithmetic (see StepParams)
+        const int R = vision_of(st, a);
+        p.vr[a] = R;
+        const double distance = 1.0 / R;                                   // maze_agent.py:148
+        double acc = 0.0;
+        for (int c = 0; c < 5; c++) { p.de_tab[a][c] = 0.f; p.mk_tab[a][c] = 0.f; }
+        for (int c = 1; c <= R; c++) {
+            acc += 1.0 / R;                                                // maze_agent.py:264,267
+            p.mk_tab[a][c] = (float)acc;
+            p.de_tab[a][c] = c == R ? 1.0f : (float)(1.0 - (R - c) * distance);   // maze_agent.py:151,180
+        }
+    }
     return p;
 }
 
@@ -100,14 +113,18 @@ int mm_load_layouts(const mm_state* st, int first, int n, const uint8_t* layouts
     return cuda_status(cudaGetLastError());
 }
 
-int mm_generate_ex(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
-                   int id_mod, int id_mul, void* scratch, int max_blocks, void* stream) {
+int mm_generate_masked(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
+                       int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, void* stream) {
     if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 4 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
         id_mod < 0 || (n && !scratch) || max_blocks < 0)
         return MM_ERR_BAD_ARG;
     if (n == 0) return MM_OK;
-    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks,
+    return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks, only,
                                        (cudaStream_t)stream));
+}
+int mm_generate_ex(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
+                   int id_mod, int id_mul, void* scratch, int max_blocks, void* stream) {
+    return mm_generate_masked(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks, nullptr, stream);
 }
 int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
                 int id_mod, int id_mul, void* scratch, void* stream) {

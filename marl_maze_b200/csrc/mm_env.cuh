@@ -56,6 +56,12 @@ struct StepParams {
     int obs_vec4;                          // obs pointer is 16-byte aligned: whole-warp float4 copy-out allowed
     float inv_max_t;                       // correctly rounded 1/max_t (host: 1.0f / (float)max_t)
     uint64_t action_seed;
+    // Agent(..., vision_range=r) per agent, 1 <= r <= 4 (maze_agent.py:16) and the ray features' values: the reference accumulates
+    // 1/r per marked cell and writes 1 - j * (1/r) for a dead end at distance j, in float64 (maze_agent.py:148,180,264,267); the host builds the
+    // float32 casts of exactly those sums / differences: de_tab[a][c] for dead-end code c (0 = none or at distance r, r = wall adjacent, else r - j),
+    // mk_tab[a][c] for c marked cells along a ray.  r = 4 gives 0, .25, .5, .75, 1 in both.
+    int vr[2];
+    float de_tab[2][5], mk_tab[2][5];
 };
 
 struct Agent {

@@ -32,10 +32,11 @@ struct PhiloxStream {
 
 __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglong2* pool_d2e, uint4* pool_hdr, int first, int n, int rows, int smax,
                                                 int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base, int id_mod, int id_mul,
-                                                uint16_t* scratch) {
+                                                uint16_t* scratch, const uint8_t* __restrict__ only) {
     // grid-stride over mazes: a full grid for an inline build, a few blocks per SM for a background build that trickles along beside
     // other kernels (each thread's serial carve holds its residency slot for milliseconds)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (only && !only[i]) continue;   // incremental refill: this slot's maze has not been consumed, it stays
     const int p = first + i;
     uint16_t* q = scratch + (size_t)i * smax * smax;  // DFS stack, then BFS queue
     const uint32_t maze_id = id_mod ? id_base + (uint32_t)(i % id_mod) * (uint32_t)id_mul + (uint32_t)(i / id_mod) : id_base + (uint32_t)i;
@@ -186,11 +187,11 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
 }
 
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed,
-                            uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, cudaStream_t stream) {
+                            uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, cudaStream_t stream) {
     int blocks = (n + 63) / 64;
     if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
     k_generate<<<blocks, 64, 0, stream>>>((ulonglong2*)st->pool_grid, (ulonglong2*)st->pool_d2e, (uint4*)st->pool_hdr, first, n,
-                                                 st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, (uint16_t*)scratch);
+                                                 st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, (uint16_t*)scratch, only);
     return cudaGetLastError();
 }
 

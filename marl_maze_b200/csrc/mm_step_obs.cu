@@ -44,21 +44,22 @@ constexpr int kThreads = MM_K2_THREADS;
 #endif
 
 // One axis ray seen from the agent.  cw: bit j-1 = wall (or out of bounds) at distance j, j = 1..5.
-// latopen: bit j-1 = a cell left or right of the ray cell at distance j is open, j = 1..4.
-// Returns n = number of visible cells (maze_agent.py:218-225) and the dead-end code de in quarters
-// (get_dead_ends, maze_agent.py:143-181: 4 = wall adjacent, 4-j = dead end seen at distance j, 0 = none).
-__device__ __forceinline__ void ray_eval(uint32_t cw, uint32_t latopen, uint32_t own_open, int& n, int& de) {
-    n = __ffs(cw | 0x10u) - 1;
+// latopen: bit j-1 = a cell left or right of the ray cell at distance j is open, j = 1..4.  R = the agent's vision_range (1..4).
+// Returns n = number of visible cells (maze_agent.py:218-225) and the dead-end code de in units of 1/R
+// (get_dead_ends, maze_agent.py:143-181: R = wall adjacent, R-j = dead end seen at distance j, 0 = none; StepParams::de_tab maps it to the value).
+__device__ __forceinline__ void ray_eval(uint32_t cw, uint32_t latopen, uint32_t own_open, int R, int& n, int& de) {
+    const uint32_t RM = (1u << R) - 1u;
+    n = __ffs(cw | (1u << R)) - 1;
     const uint32_t open = ~cw;
-    const uint32_t FWD = (open >> 1) & 0xfu;                // neighbour ahead of cell j is open
-    const uint32_t BACK = ((open << 1) | own_open) & 0xfu;  // neighbour behind cell j is open
-    const uint32_t LAT = latopen & 0xfu;
-    const uint32_t CNT1 = ~LAT & (BACK ^ FWD) & 0xfu;        // exactly one open neighbour
-    const uint32_t BRK0 = (LAT | (~CNT1 & ~FWD)) & 0xfu;     // a turn, or a wall ahead without being a dead end
+    const uint32_t FWD = (open >> 1) & RM;                  // neighbour ahead of cell j is open
+    const uint32_t BACK = ((open << 1) | own_open) & RM;    // neighbour behind cell j is open
+    const uint32_t LAT = latopen & RM;
+    const uint32_t CNT1 = ~LAT & (BACK ^ FWD) & RM;          // exactly one open neighbour
+    const uint32_t BRK0 = (LAT | (~CNT1 & ~FWD)) & RM;       // a turn, or a wall ahead without being a dead end
     const uint32_t ev = BRK0 | CNT1;
-    const int j = __ffs(ev);                                // first event along the ray (0 = none within 4)
-    int d = (j && ((CNT1 >> (j - 1)) & 1u)) ? 4 - j : 0;
-    de = (cw & 1u) ? 4 : d;
+    const int j = __ffs(ev);                                // first event along the ray (0 = none within R)
+    int d = (j && ((CNT1 >> (j - 1)) & 1u)) ? R - j : 0;
+    de = (cw & 1u) ? R : d;
 }
 
 // Where does (dx,dy) lie relative to the agent: j = 0 same cell, 1.. distance along axis ray `dir`, 99 = off-axis.
@@ -354,7 +355,7 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
         uint32_t N32 = 0, DE32 = 0, OWN32 = 0, OTH32 = 0, NB = 0;
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-            ray_eval(cw[d], lat[d], own_open, n[d], de[d]);
+            ray_eval(cw[d], lat[d], own_open, p.vr[a], n[d], de[d]);
             const uint32_t vm = (1u << n[d]) - 1u;
             N32 |= (uint32_t)n[d] << (8 * d);
             DE32 |= (uint32_t)de[d] << (8 * d);
@@ -448,9 +449,9 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 so[i] = (f == i) ? 1.f : 0.f;
-                so[4 + i] = 0.25f * (float)((DEr >> (8 * i)) & 0xffu);
-                so[8 + i] = 0.25f * (float)((OWNr >> (8 * i)) & 0xffu);
-                so[12 + i] = 0.25f * (float)((OTHr >> (8 * i)) & 0xffu);
+                so[4 + i] = p.de_tab[a][(DEr >> (8 * i)) & 0xffu];      // 1 - j / vision_range, or 1 (wall), or 0
+                so[8 + i] = p.mk_tab[a][(OWNr >> (8 * i)) & 0xffu];     // marked cells along the ray, 1 / vision_range each
+                so[12 + i] = p.mk_tab[a][(OTHr >> (8 * i)) & 0xffu];
                 so[16 + i] = (float)((s_vr >> i) & 1u);
                 so[20 + i] = (float)((s_od >> i) & 1u);
                 so[24 + i] = (float)((keyr >> i) & 1u);

@@ -33,12 +33,15 @@ class MazeEngine:
     """
 
     def __init__(self, num_envs: int, smax: int = 25, max_timestep: int = 1200, pool_size: Optional[int] = None,
-                 device: str | torch.device = "cuda", env_offset: int = 0):
+                 device: str | torch.device = "cuda", env_offset: int = 0, vision=(4, 4)):
         self.lib = _abi.lib()
         if not torch.cuda.is_available():
             raise _abi.MMError("MazeEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         if not (3 <= smax <= MAX_SIDE):
             raise ValueError(f"smax must be in [3, {MAX_SIDE}]")
+        if len(vision) != 2 or not all(1 <= int(v) <= 4 for v in vision):
+            raise ValueError("vision = (agent 0's, agent 1's) vision_range, each 1..4 (the stored grids keep a wall border of vision_range + 1 = 5 cells)")
+        self.vision = (int(vision[0]), int(vision[1]))
         self.device = torch.device(device)
         self.E, self.smax, self.max_timestep = int(num_envs), int(smax), int(max_timestep)
         self.P = int(pool_size) if pool_size else self.E
@@ -57,7 +60,7 @@ class MazeEngine:
         self.st = _abi.MMState(self.pool_grid.data_ptr(), self.pool_d2e.data_ptr(), self.pool_hdr.data_ptr(),
                                self.env_grid.data_ptr(), self.env_hdr.data_ptr(), self.env_episode.data_ptr(),
                                self.agent_a.data_ptr(), self.agent_b.data_ptr(),
-                               self.E, self.P, self.smax, self.max_timestep, int(env_offset), 0)
+                               self.E, self.P, self.smax, self.max_timestep, int(env_offset), self.vision[0] | (self.vision[1] << 8))
         self.obs = torch.zeros(self.E, 2, OBS_DIM, dtype=torch.float32, device=self.device)
         self.masks = torch.zeros(self.E, 2, MASK_DIM, dtype=torch.uint8, device=self.device)
         self.reward = torch.zeros(self.E, dtype=torch.float32, device=self.device)
@@ -107,43 +110,42 @@ class MazeEngine:
             torch.cuda.current_stream(self.device).synchronize()  # d_lay / d_hdr die here
 
     def generate(self, seed: int, side_range=(13, 13), rand_start: bool = True, difficulty: int = 1, first: int = 0,
-                 count: Optional[int] = None, id_base: int = 0, id_mod: int = 0, id_mul: int = 0):
-        """K1: fill pool entries [first, first+count) with freshly generated mazes (maze.py:170-273)."""
+                 count: Optional[int] = None, id_base: int = 0, id_mod: int = 0, id_mul: int = 0, only: Optional[torch.Tensor] = None,
+                 max_blocks: int = 0):
+        """K1: fill pool entries [first, first+count) with freshly generated mazes (maze.py:170-273).  only: u8 [count], build slot i only where
+        only[i] != 0 (the incremental refill); max_blocks: cap on the thread blocks in flight (a background build on a side stream)."""
         n = self.P - first if count is None else count
+        if only is not None:
+            assert only.dtype == torch.uint8 and only.is_contiguous() and only.numel() == n and only.device == self.pool_hdr.device
         scratch = self._get_scratch(self.lib.mm_sizeof_generate_scratch(n, self.smax))
-        _abi.check(self.lib.mm_generate(C.byref(self.st), first, n, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
-                                        C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(scratch), self._stream()), "mm_generate")
+        _abi.check(self.lib.mm_generate_masked(C.byref(self.st), first, n, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
+                                               C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(scratch),
+                                               int(max_blocks), _ptr(only), self._stream()), "mm_generate_masked")
         self.launches += 1
 
-    def generate_staged(self, seed: int, side_range=(13, 13), rand_start: bool = True, difficulty: int = 1, id_base: int = 0, id_mod: int = 0,
-                        id_mul: int = 0):
-        """K1 for the WHOLE pool into a second set of pool buffers, on a side stream: the serial carve (latency-bound, ~25 ms for the 393 k
-        mazes of a config-3 rollout) overlaps whatever the caller does next (the PPO update).  `commit_staged()` makes it the live pool."""
-        if getattr(self, "_stage", None) is None:
-            with torch.cuda.device(self.device):
-                bufs = [torch.zeros_like(t) for t in (self.pool_grid, self.pool_d2e, self.pool_hdr)]
-                st = _abi.MMState(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), self.env_grid.data_ptr(), self.env_hdr.data_ptr(),
-                                  self.env_episode.data_ptr(), self.agent_a.data_ptr(), self.agent_b.data_ptr(), self.E, self.P, self.smax,
-                                  self.max_timestep, self.st.env_offset, 0)
-                scratch = torch.empty(int(self.lib.mm_sizeof_generate_scratch(self.P, self.smax)), dtype=torch.uint8, device=self.device)
-                self._stage = dict(bufs=bufs, st=st, scratch=scratch, stream=torch.cuda.Stream(self.device), event=torch.cuda.Event())
-        sg = self._stage
-        sg["stream"].wait_stream(torch.cuda.current_stream(self.device))  # a previous commit may still be reading the staging buffers
-        with torch.cuda.stream(sg["stream"]):
+    def consumed_slots(self) -> torch.Tensor:
+        """u8 [P]: 1 for the pool slots whose maze an episode has started on since the last refill (slot p = e + k*E is episode k of env e)."""
+        K = self.P // self.E
+        ep = self.env_episode.view(torch.int32)
+        return (torch.arange(K, device=self.device, dtype=torch.int32).view(K, 1) < ep.view(1, self.E)).to(torch.uint8).reshape(-1).contiguous()
+
+    def generate_background(self, only: Optional[torch.Tensor], **kw):
+        """K1 on a side stream, in place (the slots in `only` are not read again before the next refill): the serial carve overlaps whatever the caller
+        does next (the PPO update).  `wait_background()` orders the current stream behind it."""
+        if getattr(self, "_bg", None) is None:
+            self._bg = dict(stream=torch.cuda.Stream(self.device), event=torch.cuda.Event())
+        bg = self._bg
+        bg["stream"].wait_stream(torch.cuda.current_stream(self.device))   # the mask, and everything that still reads the consumed slots
+        if only is not None:
+            only.record_stream(bg["stream"])
+        with torch.cuda.stream(bg["stream"]):
             # at most 3 blocks of 64 carving threads per SM: each holds its residency slot for milliseconds, and a full grid would keep the
-            # kernels of the main stream waiting for slots (measured: a concurrent GEMM was delayed by the whole 13 ms)
-            _abi.check(self.lib.mm_generate_ex(C.byref(sg["st"]), 0, self.P, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
-                                               C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(sg["scratch"]),
-                                               148 * 3, C.c_void_p(sg["stream"].cuda_stream)), "mm_generate_ex")
-            sg["event"].record(sg["stream"])
-        self.launches += 1
+            # kernels of the main stream waiting for slots
+            self.generate(only=only, max_blocks=148 * 3, **kw)
+            bg["event"].record(bg["stream"])
 
-    def commit_staged(self):
-        """Copy the staged pool over the live one on the current stream (0.5 GB device-to-device at config 3: ~0.2 ms)."""
-        sg = self._stage
-        torch.cuda.current_stream(self.device).wait_event(sg["event"])
-        for live, staged in zip((self.pool_grid, self.pool_d2e, self.pool_hdr), sg["bufs"]):
-            live.copy_(staged)
+    def wait_background(self):
+        torch.cuda.current_stream(self.device).wait_event(self._bg["event"])
 
     # ------------------------------------------------------------------ env API
     def reset(self, mask: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None, masks: Optional[torch.Tensor] = None):

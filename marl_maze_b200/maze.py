@@ -59,7 +59,7 @@ class Maze:
         if self.engine is None:
             smax = self.side_range[1] * 2 - 1
             self.engine = MazeEngine(self.num_envs, smax=smax, max_timestep=self.max_timestep, pool_size=self.num_envs * self.pool_episodes,
-                                     device=self.device, env_offset=self.env_offset)
+                                     device=self.device, env_offset=self.env_offset, vision=tuple(a.vision_range for a in self.agents))
             self.refill_pool()
         return self.engine
 
@@ -73,21 +73,30 @@ class Maze:
         return dict(seed=(self.seed + _splitmix64(g)) & _M64 if g else self.seed & _M64, side_range=self.side_range, rand_start=self.rand_start,
                     difficulty=self.difficulty, id_base=self.env_offset * self.pool_episodes, id_mod=self.num_envs, id_mul=self.pool_episodes)
 
+    def _refill_mask(self):
+        """The slots the next refill builds anew.  The reference builds ONE maze per reset (maze.py:57); a rollout draws its mazes from pool slots
+        (env e, episode k), so between two refills only the slots an episode actually started on are consumed -- at config 3 that is 65 613 of
+        393 216 -- and only those are rebuilt (with the new refill's seed); the others keep their unseen mazes.  Refill 0 builds everything."""
+        return None if getattr(self, "_built_engine", None) != id(self.engine) else self.engine.consumed_slots()   # a new engine's pool is empty
+
     def prefetch_pool(self):
-        """Start generating the NEXT pool (the one the next refill_pool() would build) on a side stream, into staging buffers."""
-        if self.engine is None or getattr(self, "_staged", None) == (id(self.engine), self._generation):
+        """Start building the NEXT refill (the slots this rollout consumed) on a side stream, in place.  Only for callers that reset every env
+        before they step again (PPO.get_batch does, PPO.py:104): the consumed slots include the mazes of the episodes still open."""
+        if self.engine is None or getattr(self, "_staged", None) == (id(self.engine), self._generation) or getattr(self, "_built_engine", None) != id(self.engine):
             return
-        self.engine.generate_staged(**self._pool_args())
+        self.engine.generate_background(self._refill_mask(), **self._pool_args())
         self._staged = (id(self.engine), self._generation)
 
     def refill_pool(self):
-        """Generate a fresh pool (K1).  Only between episodes of ALL envs: a live episode reads its maze's exit field from the pool."""
+        """Refill the pool (K1): everything the first time, afterwards the consumed slots only.  Only between episodes of ALL envs: a live episode
+        reads its maze's exit field from the pool."""
         eng = self.engine
         if getattr(self, "_staged", None) == (id(eng), self._generation):
-            eng.commit_staged()       # built ahead by prefetch_pool(): same ids, same mazes
+            eng.wait_background()     # built ahead by prefetch_pool(): same seed, same slots, same mazes
         else:
-            eng.generate(**self._pool_args())
+            eng.generate(only=self._refill_mask(), **self._pool_args())
         self._staged = None
+        self._built_engine = id(eng)
         eng.env_episode.zero_()
         self._generation += 1
         self._resets_since_fill = 0

@@ -18,8 +18,9 @@ DIRECTIONS = ["north", "east", "south", "west"]
 
 class Agent:
     def __init__(self, name, brain, color, mark_color, tag, vision_range=4):
-        if vision_range != 4:
-            raise NotImplementedError("the step kernel is specialised for vision_range=4 (the reference default, maze_agent.py:16)")
+        if not (isinstance(vision_range, int) and 1 <= vision_range <= 4):
+            raise NotImplementedError("vision_range must be 1..4 (maze_agent.py:16 default 4): the packed grids keep a wall border of 5 = vision_range + 1 "
+                                      "cells around every maze and an agent's window is the 11 rows / 11 bit columns around it")
         if tag not in (2, 3):
             raise ValueError("tags 2 and 3 are the two cell values the grid encodes for marks (main.py:18-19)")
         self.maze = None

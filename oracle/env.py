@@ -39,6 +39,8 @@ def load_lib():
     sig = {
         "omaze_new": (vp, [i32] * 8),
         "omaze_free": (None, [vp]),
+        "omaze_set_vision": (None, [vp, i32, i32]),
+        "obatch_set_vision": (None, [vp, i32, i32]),
         "omaze_seed": (None, [vp, u64]),
         "omaze_seed_philox": (None, [vp, u64, u32]),
         "omaze_build": (None, [vp]),
@@ -78,11 +80,13 @@ class OracleMaze:
     """One literal reference environment: Maze(agents=(tag 2, tag 3), ...) of maze.py:22."""
 
     def __init__(self, max_timestep=3500, difficulty=1, rand_start=False, rand_sizes=False, rand_range=(6, 12),
-                 default_size=(8, 8), _handle=None):
+                 default_size=(8, 8), _handle=None, vision=(4, 4)):
         self.lib = load_lib()
         self._own = _handle is None
         self.h = _handle or self.lib.omaze_new(max_timestep, difficulty, int(rand_start), int(rand_sizes),
                                                rand_range[0], rand_range[1], default_size[0], default_size[1])
+        if _handle is None and tuple(vision) != (4, 4):   # Agent(..., vision_range=r), maze_agent.py:16
+            self.lib.omaze_set_vision(self.h, int(vision[0]), int(vision[1]))
         self.obs = np.zeros((2, OBS_DIM), np.float32)
         self.masks = np.zeros((2, 6), np.uint8)
 
@@ -145,10 +149,12 @@ class OracleMaze:
 class OracleBatch:
     """E literal environments behind the same host contract as the CUDA path (maze pool + auto-reset)."""
 
-    def __init__(self, E: int, P: int, max_timestep: int = 1200, threads: int = 1):
+    def __init__(self, E: int, P: int, max_timestep: int = 1200, threads: int = 1, vision=(4, 4)):
         self.lib = load_lib()
         self.E, self.P, self.threads = E, P, threads
         self.h = self.lib.obatch_new(E, P, max_timestep)
+        if tuple(vision) != (4, 4):
+            self.lib.obatch_set_vision(self.h, int(vision[0]), int(vision[1]))
         self.obs = np.zeros((E, 2, OBS_DIM), np.float32)
         self.masks = np.zeros((E, 2, 6), np.uint8)
         self.reward = np.zeros(E, np.float32)

@@ -25,7 +25,7 @@
 
 #define OBS_DIM 65
 #define N_AGENTS 2
-#define VISION 4 /* maze_agent.py:16 vision_range=4 */
+#define VISION_DEFAULT 4 /* maze_agent.py:16 vision_range=4; per agent (Agent.__init__), see omaze_set_vision */
 
 static const int DELTAS[4][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}}; /* maze.py:19, maze_agent.py:7 */
 
@@ -127,6 +127,7 @@ static int rng_randint(Rng *r, int a, int b) { return a + (int)rng_below(r, (uin
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
     int x, y, direction, tag;
+    int vision;                                 /* vision_range, maze_agent.py:16,19 */
     int has_last_mark, lm_x, lm_y;              /* last_mark_pos (None | tuple) */
     int knows_end, sees_end, other_knows_end;
     int next_move_to_exit[4];
@@ -168,7 +169,7 @@ static void route_copy(OAgent *dst, const OAgent *src) { /* [dir for dir in self
 
 static void agent_init(OAgent *a, int tag) { /* maze_agent.py:16-57 */
     memset(a, 0, sizeof(*a));
-    a->tag = tag; a->direction = 2; a->exit_len = -1; a->route_none = 1;
+    a->tag = tag; a->vision = VISION_DEFAULT; a->direction = 2; a->exit_len = -1; a->route_none = 1;
     for (int i = 0; i < 4; i++) a->memory[i] = -1;
     a->width_est = a->height_est = 1;
     /* other_last_seen = None until the first reset; never read before that */
@@ -183,6 +184,8 @@ OMaze *omaze_new(int max_timestep, int difficulty, int rand_start, int rand_size
     m->rng.kind = 0; mt_seed_u64(&m->rng.mt, 0);
     return m;
 }
+/* Agent(..., vision_range=r) per agent (maze_agent.py:16): how far the rays of get_visibility_features / get_dead_ends reach */
+void omaze_set_vision(OMaze *m, int r0, int r1) { m->agents[0].vision = r0; m->agents[1].vision = r1; }
 void omaze_free(OMaze *m) {
     if (!m) return;
     for (int i = 0; i < N_AGENTS; i++) free(m->agents[i].route);
@@ -384,7 +387,7 @@ static void get_visibility_features(OMaze *m, int self_idx, Vis *v) { /* maze_ag
     for (int dir = 0; dir < 4; dir++) { /* :215-269 */
         int nx = s->x, ny = s->y;
         const int ad = (dir + s->direction) % 4;
-        for (int j = 1; j <= VISION; j++) {
+        for (int j = 1; j <= s->vision; j++) {
             nx += DELTAS[ad][0]; ny += DELTAS[ad][1];
             if (nx < 0 || nx >= m->width || ny < 0 || ny >= m->height || LAY(m, nx, ny) == 1) break;
             if (nx == m->end_x && ny == m->end_y) { /* :227-233 */
@@ -415,8 +418,8 @@ static void get_visibility_features(OMaze *m, int self_idx, Vis *v) { /* maze_ag
                 }
             }
             int cell = LAY(m, nx, ny);
-            if (cell == s->tag) v->own_mark[dir] += 1.0 / VISION;       /* :263-264 */
-            else if (cell > 1) v->others_mark[dir] += 1.0 / VISION;    /* :266-267 */
+            if (cell == s->tag) v->own_mark[dir] += 1.0 / s->vision;       /* :263-264 */
+            else if (cell > 1) v->others_mark[dir] += 1.0 / s->vision;    /* :266-267 */
             update_maze_minmax(s, ad, nx, ny);                          /* :269 */
         }
     }
@@ -431,12 +434,12 @@ static void get_dead_ends(OMaze *m, OAgent *s, double dead[4], int move_mask[4])
     int nb0[4], nb[4];
     agent_neighbors(m, s, s->x, s->y, nb0);
     for (int d = 0; d < 4; d++) dead[d] = nb0[d] ? 0.0 : 1.0;
-    const double distance = 1.0 / VISION;
+    const double distance = 1.0 / s->vision;
     for (int d = 0; d < 4; d++) {
         if (dead[d] == 1.0) continue;
         int nx = s->x, ny = s->y;
         const int *dl = DELTAS[(d + s->direction) % 4];
-        for (int j = 1; j <= VISION; j++) {
+        for (int j = 1; j <= s->vision; j++) {
             nx += dl[0]; ny += dl[1];
             agent_neighbors(m, s, nx, ny, nb);
             if (nb[(d + 1) % 4] || nb[pymod4(d - 1)]) break;
@@ -629,6 +632,7 @@ OBatch *obatch_new(int E, int P, int max_timestep) {
     b->dir_episode = (int *)calloc(E, sizeof(int));
     return b;
 }
+void obatch_set_vision(OBatch *b, int r0, int r1) { for (int e = 0; e < b->E; e++) omaze_set_vision(b->envs[e], r0, r1); }
 void obatch_free(OBatch *b) {
     if (!b) return;
     for (int e = 0; e < b->E; e++) omaze_free(b->envs[e]);

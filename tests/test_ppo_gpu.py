@@ -157,21 +157,42 @@ def test_cuda_graph_rollout_equals_eager_rollout(tmp_path):
 
 
 def test_prefetched_pool_equals_inline_generation(tmp_path):
-    """get_batch starts carving the NEXT rollout's mazes on a side stream (Maze.prefetch_pool) and the next refill copies them in; the
-    rollouts must be exactly those of generating the pool inline."""
+    """get_batch starts carving the NEXT rollout's mazes on a side stream (Maze.prefetch_pool, in place: the consumed slots) and the next refill
+    only waits for it; the rollouts must be exactly those of refilling the pool inline."""
     outs = {}
     for mode in (False, True):
         brain, agents, maze = _make(128, tmp_path / f"p{int(mode)}", batch_size=128 * 24 - 2, horizon=24, prefetch_pool=mode)
         res = []
         for _ in range(3):
             b = brain.get_batch()
-            res.append([b[0].clone(), b[1].clone(), b[2].clone(), b[5].clone(), b[6].clone(), b[7].clone(), maze.engine.pool_hdr.clone()])
+            res.append([b[0].clone(), b[1].clone(), b[2].clone(), b[5].clone(), b[6].clone(), b[7].clone(), torch.as_tensor(b[3].astype("int64"))])
         outs[mode] = res
         assert (getattr(maze, "_staged", None) is not None) == mode
     for r_a, r_b in zip(outs[False], outs[True]):
         for x, y in zip(r_a, r_b):
-            assert torch.equal(x, y)
-    assert not torch.equal(outs[True][0][6], outs[True][1][6])  # every rollout runs on new mazes
+            assert torch.equal(x, y)   # observations, actions, log-probs, masks, advantages, values, shortest paths of the finished episodes
+    assert not torch.equal(outs[True][0][0], outs[True][1][0])  # every rollout runs on new mazes
+
+
+def test_incremental_refill_rebuilds_consumed_slots_only(tmp_path):
+    """The reference builds one maze per reset (maze.py:57).  Between two rollouts the pool refill rebuilds exactly the slots (env e, episode k) an
+    episode started on -- k < env_episode[e] -- with the new refill's seed; the other slots keep their (unseen) mazes."""
+    brain, agents, maze = _make(64, tmp_path / "inc", batch_size=64 * 130 - 2, horizon=130)   # max_timestep 120 < horizon: every env consumes >= 2 slots
+    brain.get_batch()
+    eng = maze.engine
+    E, K = eng.E, eng.P // eng.E
+    hdr0 = eng.pool_hdr.view(torch.int32).view(K, E, 4).clone()
+    grid0 = eng.pool_grid.view(K, E, -1).clone()
+    used = eng.env_episode.view(torch.int32).clone()              # episodes started per env in that rollout
+    assert int(used.min()) >= 2 and int(used.max()) <= K
+    brain.get_batch()                                             # refills first
+    hdr1 = eng.pool_hdr.view(torch.int32).view(K, E, 4)
+    grid1 = eng.pool_grid.view(K, E, -1)
+    consumed = torch.arange(K, device=used.device).view(K, 1) < used.view(1, E)
+    same_grid = (grid0 == grid1).all(-1)
+    assert bool(same_grid[~consumed].all()) and bool((hdr0 == hdr1).all(-1)[~consumed].all())      # untouched slots: identical mazes
+    assert float(same_grid[consumed].float().mean()) < 0.05                                         # consumed slots: new mazes (same id, new seed)
+    assert bool((hdr0[..., 3] == hdr1[..., 3]).all())                                               # the slot's maze id is its (env, episode) key
 
 
 @pytest.mark.parametrize("faithful", [True, False], ids=["column0_projection", "indexed_projection"])

@@ -35,7 +35,33 @@ TRACES = [
     ("s49_guided", 8, 3, 2000, "guided", dict(rand_range=[25, 25], max_timestep=1200)),
 ]
 
+# Agent(..., vision_range=r) per agent (maze_agent.py:16,148,165,218,264).  (name, maze_seed, action_seed, steps, policy, kwargs, vision)
+VISION_TRACES = [
+    ("v33_guided", 400, 0, 2000, "guided", {}, (3, 3)),
+    ("v22_uniform", 401, 1, 1500, "uniform", dict(max_timestep=300), (2, 2)),
+    ("v11_slow", 402, 2, 1500, "guided_slow", dict(rand_range=[5, 8], max_timestep=300), (1, 1)),
+    ("v42_guided", 403, 3, 2000, "guided", {}, (4, 2)),
+    ("v13_slow", 404, 4, 2000, "guided_slow", dict(rand_range=[6, 13], difficulty=2, max_timestep=400), (1, 3)),
+]
+
 MAXS = 64
+
+
+def make_vision_traces():
+    """tests/golden/env_traces_vision.npz: the reference with vision_range != 4 (per agent)."""
+    blob, names = {}, []
+    for name, ms, as_, n, pol, kw, vis in VISION_TRACES:
+        tr = rh.run_trace(ms, as_, n, maze_kw=kw, policy=pol, vision=vis)
+        for k, v in pack_trace(tr).items():
+            blob[f"{name}/{k}"] = v
+        cfg = dict(rh.MAIN_PY_KW); cfg.update(kw)
+        blob[f"{name}/cfg"] = np.asarray([ms, as_, n, cfg["max_timestep"], cfg["difficulty"], int(cfg["rand_start"]), int(cfg["rand_sizes"]),
+                                          cfg["rand_range"][0], cfg["rand_range"][1], cfg["default_size"][0], cfg["default_size"][1]], np.int64)
+        blob[f"{name}/vision"] = np.asarray(vis, np.int32)
+        names.append(name)
+        print(f"{name}: vision={vis} steps={n} episodes={len(tr['mazes'])} dones={int(np.sum(tr['done']))} reward_sum={sum(tr['reward'])}")
+    blob["names"] = np.asarray(names)
+    np.savez_compressed(os.path.join(OUT, "env_traces_vision.npz"), **blob)
 
 
 def pack_trace(tr):
@@ -142,8 +168,10 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__" and "--ppo" not in sys.argv and "--upd" not in sys.argv and "--kat5" not in sys.argv:
+if __name__ == "__main__" and "--ppo" not in sys.argv and "--upd" not in sys.argv and "--kat5" not in sys.argv and "--vision" not in sys.argv:
     main()
+if __name__ == "__main__" and "--vision" in sys.argv:
+    make_vision_traces()
 
 
 def make_ppo_kats():

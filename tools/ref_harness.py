@@ -69,11 +69,11 @@ MAIN_PY_KW = dict(max_timestep=1200, rand_sizes=True, rand_range=[12, 13], rand_
                   difficulty=1, default_size=[4, 4])  # main.py:20
 
 
-def make_env(**maze_kw):
-    """Reference Maze with two Agents tagged 2 and 3 (main.py:18-20)."""
+def make_env(vision=(4, 4), **maze_kw):
+    """Reference Maze with two Agents tagged 2 and 3 (main.py:18-20); vision = the agents' vision_range (maze_agent.py:16)."""
     ref_maze, ref_agent = load_reference()
     brain = _DummyBrain()
-    agents = (ref_agent.Agent("RED", brain, None, None, 2), ref_agent.Agent("BLUE", brain, None, None, 3))
+    agents = (ref_agent.Agent("RED", brain, None, None, 2, vision_range=vision[0]), ref_agent.Agent("BLUE", brain, None, None, 3, vision_range=vision[1]))
     kw = dict(MAIN_PY_KW)
     kw.update(maze_kw)
     return ref_maze.Maze(agents=agents, **kw)
@@ -115,7 +115,7 @@ def legal_random_action(rng: random.Random, masks):
     return act
 
 
-def run_trace(maze_seed: int, action_seed: int, n_steps: int, maze_kw=None, policy="uniform"):
+def run_trace(maze_seed: int, action_seed: int, n_steps: int, maze_kw=None, policy="uniform", vision=(4, 4)):
     """Runs the reference for n_steps env-steps with reset-on-done, exactly like PPO.get_batch's
     loop (PPO.py:104-141) minus the networks.  Returns a dict of python lists:
 
@@ -127,7 +127,7 @@ def run_trace(maze_seed: int, action_seed: int, n_steps: int, maze_kw=None, poli
       episode_of[i]       : episode index step i belongs to
     """
     with contextlib.redirect_stdout(io.StringIO()):
-        env = make_env(**(maze_kw or {}))
+        env = make_env(vision=vision, **(maze_kw or {}))
         random.seed(maze_seed)
         rng = random.Random(action_seed)
         out = dict(mazes=[], emit_obs=[], emit_masks=[], actions=[], reward=[], done=[], step_obs=[],
