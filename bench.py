@@ -460,12 +460,22 @@ def ppo_iteration_leg(torch, dist, world, rank, local, args):
         stats = dict(brain.last_stats)
         upd, upd_ms = timed(lambda: brain.update(batch))
         del batch
+    ar_ms = None
+    if world > 1:   # the collective on its own: both gradient buckets (actor 1.06 MB, critic 50 KB), as one optimiser step issues them, 25 steps per update
+        def ar_step():
+            h_a = brain._allreduce_start(brain.actor); h_c = brain._allreduce_start(brain.critic)
+            brain._allreduce_finish(h_a); brain._allreduce_finish(h_c)
+        for _ in range(5):
+            ar_step()
+        _, ms25 = timed(lambda: [ar_step() for _ in range(25)])
+        ar_ms = ms25
     steps = E * T * world
     out = {"what": f"config[2]: {E} mazes x 2 agents per GPU, T = {T}, side 25: PPO rollout (K4 policy forward + fused sampling, K2 step + obs, per step; K3 GAE) "
                    "then the 5 x 5 minibatch update (K5)",
            "n_gpus": world, "envs_per_gpu": E, "horizon": T, "rollout_ms": roll_ms, "update_ms": upd_ms,
            "rollout_agent_steps_per_s": 2.0 * steps / (roll_ms * 1e-3), "iteration_env_steps_per_s": steps / ((roll_ms + upd_ms) * 1e-3),
-           "allreduce_ms": getattr(brain, "last_allreduce_ms", None), "optimizer_steps": upd.get("steps") if isinstance(upd, dict) else None,
+           "allreduce_ms": ar_ms, "allreduce_what": None if ar_ms is None else "25 x (actor + critic gradient bucket, NCCL AVG) timed on their own; inside the update the "
+           "actor's bucket is in flight while the critic's forward / backward runs", "optimizer_steps": upd.get("steps") if isinstance(upd, dict) else None,
            "episodes": stats.get("episodes"), "mem_GB": torch.cuda.max_memory_allocated() / 1e9}
     try:
         with open(os.path.join(ROOT, "profiles", "k4_tensor_pipe.json")) as f:

@@ -212,17 +212,49 @@ class PPO:
                 g["lr"] *= 0.997
 
     # ------------------------------------------------------------------ training
-    def _allreduce_grads(self, module):
+    def _bucket(self, module):
+        """The module's persistent flat gradient bucket: one fp32 buffer over all its parameters plus a view per parameter."""
+        key = id(module)
+        if not hasattr(self, "_buckets"):
+            self._buckets = {}
+        bk = self._buckets.get(key)
+        params = list(module.parameters())
+        if bk is None or bk["n"] != sum(p.numel() for p in params) or bk["flat"].device != params[0].device:
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+            views, o = [], 0
+            for p in params:
+                views.append(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+            bk = self._buckets[key] = dict(flat=flat, views=views, n=flat.numel())
+        return bk, params
+
+    def _allreduce_start(self, module):
+        """Start the mean all-reduce of the module's gradients (PPO.py:76-78,82-84 see single-process gradients: the mean over ranks of per-rank minibatch
+        means).  The gradients are packed into the persistent flat bucket by ONE multi-tensor copy and reduced by ONE asynchronous collective (NCCL: on
+        its own stream, averaging inside the collective) -- whatever the caller launches next (the critic's forward / backward after the actor's
+        bucket) overlaps it.  `_allreduce_finish` makes the current stream wait and points every p.grad at its slice of the bucket: no copy back."""
         d = _dist()
         if d is None or d.get_world_size() == 1:
+            return None
+        bk, params = self._bucket(module)
+        live = [(p, v) for p, v in zip(params, bk["views"]) if p.grad is not None]
+        torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
+        avg = d.get_backend() == "nccl"   # gloo has no AVG
+        work = d.all_reduce(bk["flat"], op=d.ReduceOp.AVG if avg else d.ReduceOp.SUM, async_op=True)
+        return dict(work=work, live=live, flat=bk["flat"], avg=avg, world=d.get_world_size())
+
+    @staticmethod
+    def _allreduce_finish(h):
+        if h is None:
             return
-        grads = [p.grad for p in module.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])  # one bucket: 1.06 MB actor / 50 KB critic, latency-bound on NVSwitch
-        d.all_reduce(flat)
-        flat /= d.get_world_size()
-        o = 0
-        for g in grads:
-            g.copy_(flat[o:o + g.numel()].view_as(g)); o += g.numel()
+        h["work"].wait()
+        if not h["avg"]:
+            h["flat"] /= h["world"]
+        for p, v in h["live"]:
+            p.grad = v
+
+    def _allreduce_grads(self, module):
+        """Blocking form (tests, callers outside update)."""
+        self._allreduce_finish(self._allreduce_start(module))
 
     def _normalise(self, adv):
         """(adv - mean) / (unbiased std + 1e-10), PPO.py:47, statistics over every rank's samples."""
@@ -279,9 +311,7 @@ class PPO:
                         loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
                     loss.backward()
                     a_sum += loss.detach()
-                self._allreduce_grads(self.actor)
-                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
-                self.actor_optim.step()
+                h_actor = self._allreduce_start(self.actor)   # overlaps the critic's forward / backward below (the two networks share nothing)
                 self.critic_optim.zero_grad(set_to_none=True)
                 for s0 in range(start, start + n, self.micro_batch):
                     s1 = min(s0 + self.micro_batch, start + n)
@@ -291,7 +321,11 @@ class PPO:
                         loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
                     loss.backward()
                     c_sum += loss.detach()
-                self._allreduce_grads(self.critic)
+                h_critic = self._allreduce_start(self.critic)
+                self._allreduce_finish(h_actor)
+                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
+                self.actor_optim.step()
+                self._allreduce_finish(h_critic)
                 torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad)
                 self.critic_optim.step()
                 stats["steps"] += 1
