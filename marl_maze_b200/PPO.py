@@ -40,6 +40,16 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
+def _static_row_grouping():
+    from . import networks
+    return networks.static_row_grouping()
+
+
+def _row_grouping_overflow() -> bool:
+    from . import networks
+    return networks.row_grouping_overflow()
+
+
 def finished_episodes(done: torch.Tensor):
     """From done [T,E] (uint8 / bool): (length, index of the episode within its env, env) of every finished episode, in (time, env)
     order.  Finished episodes are sparse in [T,E]: one nonzero() (sorted by env, then time), then everything on the short list."""
@@ -60,7 +70,7 @@ class PPO:
     def __init__(self, agent_amount, epochs=500, batch_size=15000, lr=0.0002, discount_rate=0.99, lam=0.95, updates_per_batch=5, clip=0.2, max_grad=0.5,
                  *, device=None, horizon: Optional[int] = None, seed: int = 3234, model_path: Optional[str] = MODEL_PATH, faithful_projection: bool = True,
                  verbose: bool = True, micro_batch: int = 1 << 20, update_tf32: bool = False, use_cuda_graph: bool = True,
-                 fused_update: bool = True, prefetch_pool: bool = False):
+                 fused_update: bool = True, prefetch_pool: bool = False, graph_update: Optional[bool] = None):
         if agent_amount != 2:
             raise NotImplementedError("two agents (README.md:34)")
         self.maze = None  # injected by Maze.__init__ (maze.py:40-42)
@@ -70,8 +80,16 @@ class PPO:
         self.critic = Critic(agent_amount, hidden_sizes=[64, 64]).to(self.device)
         # torch.optim.Adam exactly as in the reference (PPO.py:20-21).  (fused=True was tried for its launch count and changed the training
         # trajectory from the first update on -- the plain implementation is the one that tracks the autograd reference path.)
-        self.actor_optim = torch.optim.Adam(self.actor.parameters(), lr=lr)
-        self.critic_optim = torch.optim.Adam(self.critic.parameters(), lr=lr)
+        # On a GPU with use_cuda_graph the optimisers are built capturable (step counts and the learning rate live on the device) so that a whole
+        # optimiser step of the update can be replayed as a CUDA graph (_update, small minibatches); the update rule is the same Adam, the bias
+        # corrections are evaluated in fp32 on the device instead of in float64 on the host.  Checkpoints keep the reference's format (see
+        # save_parameters / load_parameters).
+        cap = bool(use_cuda_graph and fused_update and self.device.type == "cuda")
+        mk = (lambda ps: torch.optim.Adam(ps, lr=torch.tensor(float(lr), device=self.device), capturable=True)) if cap else (lambda ps: torch.optim.Adam(ps, lr=lr))
+        self.actor_optim = mk(self.actor.parameters())
+        self.critic_optim = mk(self.critic.parameters())
+        self._ug = None   # captured update graphs (see _update)
+        self.graph_update = graph_update   # None: follow use_cuda_graph; False: eager update steps (tests: same optimiser, no graph)
         self.epochs, self.batch_size, self.lr, self.discount_rate, self.lam = epochs, batch_size, lr, discount_rate, lam
         self.updates_per_batch, self.mbatch_size, self.clip, self.max_grad = updates_per_batch, batch_size // 5, clip, max_grad
         self.horizon, self.seed, self.model_path, self.verbose, self.micro_batch = horizon, seed, model_path, verbose, micro_batch
@@ -276,6 +294,10 @@ class PPO:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
+    # minibatches of at most this many env-steps replay their optimiser step as a CUDA graph (launch-bound regime: at the reference's own
+    # configuration an optimiser step is ~150 small launches, 7.5 ms eager against < 1 ms of GPU work); larger ones are compute-bound
+    GRAPH_UPDATE_MAX_MINIBATCH = 1 << 18
+
     def _update(self, batch):
         b_obs, b_actions, b_log_probs, _, _, b_masks, b_advs, b_vals = batch
         N = b_obs.shape[0]
@@ -285,51 +307,93 @@ class PPO:
         index_list = torch.randperm(N, device=self.device, generator=g)
         used = min(self.batch_size, N)
         mb = max(1, self.mbatch_size if self.batch_size <= N else N // 5)
+        fused = self.fused_update and _upd.fused_available(self.actor)
+        fused_critic = self.fused_update and _upd.critic_fused_available(self.critic)
+        graphed = bool(self.use_cuda_graph and self.graph_update is not False and fused and fused_critic and self.device.type == "cuda" and mb <= self.GRAPH_UPDATE_MAX_MINIBATCH
+                       and all(gr.get("capturable", False) for opt in (self.actor_optim, self.critic_optim) for gr in opt.param_groups))
         # The reference shuffles ONCE per train iteration and walks the same minibatches in every update epoch (PPO.py:48-55): gather the
         # used part of the rollout into that order once, and every minibatch / micro-batch below is a contiguous view.
         sel = index_list[:used]
-        p_obs, p_act, p_masks, p_logp, p_adv, p_rtg = (t.index_select(0, sel) for t in (b_obs, b_actions, b_masks, b_log_probs, b_advs, b_rtgs))
-        stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0)
-        a_sum = torch.zeros((), device=self.device); c_sum = torch.zeros((), device=self.device)   # summed on the device: no sync per micro-batch
-        fused = self.fused_update and _upd.fused_available(self.actor)
-        fused_critic = self.fused_update and _upd.critic_fused_available(self.critic)
-        p_xpad = _upd.pad_critic_obs(p_obs) if fused_critic else None
+        srcs = (b_obs, b_actions, b_masks, b_log_probs, b_advs, b_rtgs)
+        if graphed:  # static buffers: the captured graphs hold their addresses across update() calls
+            key = (used, mb, self.micro_batch, tuple(t.dtype for t in srcs), id(self.actor_optim), id(self.critic_optim))
+            if self._ug is None or self._ug["key"] != key:
+                self._ug = dict(key=key, bufs=[torch.empty((used,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in srcs],
+                                xpad=torch.empty(used, _upd.CRITIC_IN + 2, dtype=torch.float32, device=self.device),
+                                a_sum=torch.zeros((), device=self.device), c_sum=torch.zeros((), device=self.device), graphs={}, pool=None, warm=False)
+            ug = self._ug
+            _upd.token_layout(self.device, self.actor.projection.faithful)   # host -> device copies happen here, never inside a capture
+            for t, dst in zip(srcs, ug["bufs"]):
+                torch.index_select(t, 0, sel, out=dst)
+            p_obs, p_act, p_masks, p_logp, p_adv, p_rtg = ug["bufs"]
+            ug["xpad"].copy_(_upd.pad_critic_obs(p_obs))
+            p_xpad, a_sum, c_sum = ug["xpad"], ug["a_sum"], ug["c_sum"]
+            a_sum.zero_(); c_sum.zero_()
+        else:
+            p_obs, p_act, p_masks, p_logp, p_adv, p_rtg = (t.index_select(0, sel) for t in srcs)
+            a_sum = torch.zeros((), device=self.device); c_sum = torch.zeros((), device=self.device)   # summed on the device: no sync per micro-batch
+            p_xpad = _upd.pad_critic_obs(p_obs) if fused_critic else None
+        stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0, graphed=graphed)
+
+        def step(start, n):
+            """One optimiser step on minibatch [start, start + n): launches only (no host synchronisation), so it can be captured."""
+            self.actor_optim.zero_grad(set_to_none=True)
+            for s0 in range(start, start + n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
+                s1 = min(s0 + self.micro_batch, start + n)
+                m_obs, m_act, m_masks, adv = p_obs[s0:s1], p_act[s0:s1], p_masks[s0:s1], p_adv[s0:s1]
+                if fused:  # K5: trunk + heads + clipped surrogate, forward and backward, in hand-written kernels (update.py)
+                    loss, _ = _upd.actor_loss(self.actor, m_obs.reshape(-1, m_obs.shape[-1]), m_masks.reshape(-1, 6), m_act.reshape(-1, 2),
+                                              p_logp[s0:s1], adv, self.clip, 1.0 / n)
+                else:
+                    cur = self.joint_log_probs(m_obs, m_act, m_masks)
+                    ratio = torch.exp(cur - p_logp[s0:s1])
+                    loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
+                loss.backward()
+                a_sum.add_(loss.detach())
+            h_actor = self._allreduce_start(self.actor)   # overlaps the critic's forward / backward below (the two networks share nothing)
+            self.critic_optim.zero_grad(set_to_none=True)
+            for s0 in range(start, start + n, self.micro_batch):
+                s1 = min(s0 + self.micro_batch, start + n)
+                if fused_critic:  # K5 GEMM kernels for the two hidden layers, forward and backward (update._CriticLoss)
+                    loss = _upd.critic_loss(self.critic, p_xpad[s0:s1], p_rtg[s0:s1], 1.0 / n)
+                else:
+                    loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
+                loss.backward()
+                c_sum.add_(loss.detach())
+            h_critic = self._allreduce_start(self.critic)
+            self._allreduce_finish(h_actor)
+            torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
+            self.actor_optim.step()
+            self._allreduce_finish(h_critic)
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad)
+            self.critic_optim.step()
+
         for _ in range(self.updates_per_batch):
             self.decay_lr()
             for start in range(0, used, mb):
                 n = min(mb, used - start)
-                self.actor_optim.zero_grad(set_to_none=True)
-                for s0 in range(start, start + n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
-                    s1 = min(s0 + self.micro_batch, start + n)
-                    m_obs, m_act, m_masks, adv = p_obs[s0:s1], p_act[s0:s1], p_masks[s0:s1], p_adv[s0:s1]
-                    if fused:  # K5: trunk + heads + clipped surrogate, forward and backward, in hand-written kernels (update.py)
-                        loss, _ = _upd.actor_loss(self.actor, m_obs.reshape(-1, m_obs.shape[-1]), m_masks.reshape(-1, 6), m_act.reshape(-1, 2),
-                                                  p_logp[s0:s1], adv, self.clip, 1.0 / n)
-                    else:
-                        cur = self.joint_log_probs(m_obs, m_act, m_masks)
-                        ratio = torch.exp(cur - p_logp[s0:s1])
-                        loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
-                    loss.backward()
-                    a_sum += loss.detach()
-                h_actor = self._allreduce_start(self.actor)   # overlaps the critic's forward / backward below (the two networks share nothing)
-                self.critic_optim.zero_grad(set_to_none=True)
-                for s0 in range(start, start + n, self.micro_batch):
-                    s1 = min(s0 + self.micro_batch, start + n)
-                    if fused_critic:  # K5 GEMM kernels for the two hidden layers, forward and backward (update._CriticLoss)
-                        loss = _upd.critic_loss(self.critic, p_xpad[s0:s1], p_rtg[s0:s1], 1.0 / n)
-                    else:
-                        loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
-                    loss.backward()
-                    c_sum += loss.detach()
-                h_critic = self._allreduce_start(self.critic)
-                self._allreduce_finish(h_actor)
-                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
-                self.actor_optim.step()
-                self._allreduce_finish(h_critic)
-                torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad)
-                self.critic_optim.step()
+                if not graphed:
+                    step(start, n)
+                elif not ug["warm"]:   # the very first step runs eagerly: lazy kernel attributes, Adam's state tensors
+                    with _static_row_grouping():
+                        step(start, n)
+                    ug["warm"] = True
+                else:
+                    gk = (start, n)
+                    if gk not in ug["graphs"]:   # one graph per minibatch position (the same five positions in every epoch and every update)
+                        torch.cuda.synchronize(self.device)
+                        gr = torch.cuda.CUDAGraph()
+                        with _static_row_grouping(), torch.cuda.graph(gr, pool=ug["pool"]):
+                            step(start, n)
+                        if ug["pool"] is None:
+                            ug["pool"] = gr.pool()
+                        ug["graphs"][gk] = gr
+                    ug["graphs"][gk].replay()
                 stats["steps"] += 1
         stats["actor_loss"], stats["critic_loss"] = float(a_sum), float(c_sum)
+        if graphed and _row_grouping_overflow():
+            raise RuntimeError("update graph: an observation batch had more than 4 distinct obs[:, 0:4] prefixes (not environment observations); "
+                               "run with use_cuda_graph=False")
         return stats
 
     def train(self):
@@ -365,14 +429,26 @@ class PPO:
             if isinstance(o, (list, tuple)):
                 return type(o)(cpu(v) for v in o)
             return o
+        def plain(opt):  # the reference's optimisers are plain torch.optim.Adam (PPO.py:20-21): float learning rate, not capturable, step counts on the CPU
+            sd = cpu(opt.state_dict())
+            for gr in sd["param_groups"]:
+                gr["lr"] = float(gr["lr"]); gr["capturable"] = False
+            return sd
         torch.save({"actor": cpu(self.actor.state_dict()), "critic": cpu(self.critic.state_dict()),
-                    "actor_optim": cpu(self.actor_optim.state_dict()), "critic_optim": cpu(self.critic_optim.state_dict())}, self.model_path)
+                    "actor_optim": plain(self.actor_optim), "critic_optim": plain(self.critic_optim)}, self.model_path)
 
     def load_parameters(self):
         if self.model_path and os.path.exists(self.model_path):
             sd = torch.load(self.model_path, map_location=self.device)
             self.actor.load_state_dict(sd["actor"]); self.critic.load_state_dict(sd["critic"])
-            self.actor_optim.load_state_dict(sd["actor_optim"]); self.critic_optim.load_state_dict(sd["critic_optim"])
+            for opt, osd in ((self.actor_optim, sd["actor_optim"]), (self.critic_optim, sd["critic_optim"])):
+                cap = bool(opt.param_groups[0].get("capturable", False))   # ours may be capturable (device-side step counts and learning rate)
+                for gr in osd["param_groups"]:
+                    gr["capturable"] = cap
+                opt.load_state_dict(osd)
+                if cap:
+                    for gr in opt.param_groups:
+                        gr["lr"] = torch.as_tensor(float(gr["lr"]), dtype=torch.float32, device=self.device)
             if self.verbose:
                 print("successfuly loaded existing parameters")
             return True

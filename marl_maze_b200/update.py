@@ -84,6 +84,20 @@ def token_maps(actor):
     return torch.einsum("jd,adc->jac", stack, pw).contiguous(), (stack @ pb.t()).contiguous()
 
 
+_TOKEN_LAYOUT = {}
+
+
+def token_layout(device, faithful):
+    """(first observation column, width) of the 23 feature tokens as device tensors -- host -> device once per (device, projection mode): nothing in
+    the update may copy from the host during a CUDA-graph capture (PPO._update calls this before it captures)."""
+    from .networks import FEATURE_DIMS
+    ck = (str(torch.device(device)), bool(faithful))
+    if ck not in _TOKEN_LAYOUT:
+        cols = [0 if faithful else sum(FEATURE_DIMS[:i]) for i in range(len(FEATURE_DIMS))]
+        _TOKEN_LAYOUT[ck] = (torch.tensor(cols, dtype=torch.float32, device=device), torch.tensor(FEATURE_DIMS, dtype=torch.float32, device=device))
+    return _TOKEN_LAYOUT[ck]
+
+
 class TokenEmbed(torch.autograd.Function):
     """Projection + attention of every row by the token kernels: forward = K4's k_tokens, backward = k_tokens_bwd (gradients at the
     per-token maps; autograd carries them on to the parameters through token_maps)."""
@@ -97,9 +111,9 @@ class TokenEmbed(torch.autograd.Function):
         buf = torch.zeros(o["total"], dtype=torch.float32, device=obs.device)   # K4 buffer layout; the token kernels read these four blocks only
         buf[o["tokm"]:o["tokm"] + tokm.numel()] = tokm.detach().reshape(-1)
         buf[o["tokb"]:o["tokb"] + tokb.numel()] = tokb.detach().reshape(-1)
-        cols = [0 if faithful else sum(FEATURE_DIMS[:i]) for i in range(len(FEATURE_DIMS))]
-        buf[o["proj_col"]:o["proj_col"] + len(cols)] = torch.tensor(cols, dtype=torch.float32, device=obs.device)
-        buf[o["proj_dim"]:o["proj_dim"] + len(cols)] = torch.tensor(FEATURE_DIMS, dtype=torch.float32, device=obs.device)
+        d_cols, d_dims = token_layout(obs.device, faithful)
+        buf[o["proj_col"]:o["proj_col"] + d_cols.numel()] = d_cols
+        buf[o["proj_dim"]:o["proj_dim"] + d_dims.numel()] = d_dims
         x0 = torch.empty(obs.shape[0], 460, device=obs.device, dtype=torch.float32)
         _abi.check(_abi.lib().mm_tokens_forward(_ptr(buf), _ptr(obs), obs.shape[0], _ptr(x0), _stream(obs)), "mm_tokens_forward")
         ctx.save_for_backward(obs, buf)

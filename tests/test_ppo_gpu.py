@@ -174,6 +174,27 @@ def test_prefetched_pool_equals_inline_generation(tmp_path):
     assert not torch.equal(outs[True][0][0], outs[True][1][0])  # every rollout runs on new mazes
 
 
+@pytest.mark.parametrize("faithful", [True, False], ids=["column0_projection", "indexed_projection"])
+def test_graphed_update_equals_eager_update(tmp_path, faithful):
+    """the optimiser steps of PPO.update (PPO.py:51-85) replayed as CUDA graphs -- one graph per minibatch position, captured in the
+    first update and replayed in every later epoch and update -- against the same steps launched eagerly with the same (capturable) Adam: identical
+    parameters after two rollouts + updates, same losses, and the graphs were really used."""
+    outs = {}
+    for mode in (False, True):
+        brain, agents, maze = _make(256, tmp_path / f"g{int(mode)}", batch_size=256 * 40 // 5 * 5, horizon=40, faithful_projection=faithful, graph_update=mode)
+        stats = []
+        for _ in range(2):
+            stats.append(brain.update(brain.get_batch()))
+        assert all(st["graphed"] == mode for st in stats) and stats[0]["steps"] == 25
+        if mode:
+            assert len(brain._ug["graphs"]) == 5      # five minibatch positions, each captured once and replayed 9 or 10 times
+        outs[mode] = ([p.detach().clone() for p in list(brain.actor.parameters()) + list(brain.critic.parameters())], stats)
+    for a, b in zip(outs[False][0], outs[True][0]):
+        assert torch.equal(a, b)
+    for sa, sb in zip(outs[False][1], outs[True][1]):
+        assert sa["actor_loss"] == sb["actor_loss"] and sa["critic_loss"] == sb["critic_loss"]
+
+
 def test_incremental_refill_rebuilds_consumed_slots_only(tmp_path):
     """The reference builds one maze per reset (maze.py:57).  Between two rollouts the pool refill rebuilds exactly the slots (env e, episode k) an
     episode started on -- k < env_episode[e] -- with the new refill's seed; the other slots keep their (unseen) mazes."""
