@@ -245,20 +245,28 @@ class PPO:
             bk = self._buckets[key] = dict(flat=flat, views=views, n=flat.numel())
         return bk, params
 
-    def _allreduce_start(self, module):
-        """Start the mean all-reduce of the module's gradients (PPO.py:76-78,82-84 see single-process gradients: the mean over ranks of per-rank minibatch
-        means).  The gradients are packed into the persistent flat bucket by ONE multi-tensor copy and reduced by ONE asynchronous collective (NCCL: on
-        its own stream, averaging inside the collective) -- whatever the caller launches next (the critic's forward / backward after the actor's
-        bucket) overlaps it.  `_allreduce_finish` makes the current stream wait and points every p.grad at its slice of the bucket: no copy back."""
-        d = _dist()
-        if d is None or d.get_world_size() == 1:
-            return None
+    def _pack(self, module):
+        """Copy the module's gradients into its persistent flat bucket with ONE multi-tensor copy; returns the (parameter, bucket view) pairs."""
         bk, params = self._bucket(module)
         live = [(p, v) for p, v in zip(params, bk["views"]) if p.grad is not None]
         torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
+        return dict(live=live, flat=bk["flat"])
+
+    def _reduce_async(self, h):
+        """Mean all-reduce of a packed bucket as ONE asynchronous collective (NCCL: on its own stream, averaging inside the collective)."""
+        d = _dist()
         avg = d.get_backend() == "nccl"   # gloo has no AVG
-        work = d.all_reduce(bk["flat"], op=d.ReduceOp.AVG if avg else d.ReduceOp.SUM, async_op=True)
-        return dict(work=work, live=live, flat=bk["flat"], avg=avg, world=d.get_world_size())
+        h.update(work=d.all_reduce(h["flat"], op=d.ReduceOp.AVG if avg else d.ReduceOp.SUM, async_op=True), avg=avg, world=d.get_world_size())
+        return h
+
+    def _allreduce_start(self, module):
+        """Start the mean all-reduce of the module's gradients (PPO.py:76-78,82-84 see single-process gradients: the mean over ranks of per-rank minibatch
+        means): pack + one asynchronous collective -- whatever the caller launches next (the critic's forward / backward after the actor's bucket)
+        overlaps it.  `_allreduce_finish` makes the current stream wait and points every p.grad at its slice of the bucket: no copy back."""
+        d = _dist()
+        if d is None or d.get_world_size() == 1:
+            return None
+        return self._reduce_async(self._pack(module))
 
     @staticmethod
     def _allreduce_finish(h):
@@ -335,8 +343,8 @@ class PPO:
             p_xpad = _upd.pad_critic_obs(p_obs) if fused_critic else None
         stats = dict(actor_loss=0.0, critic_loss=0.0, steps=0, graphed=graphed)
 
-        def step(start, n):
-            """One optimiser step on minibatch [start, start + n): launches only (no host synchronisation), so it can be captured."""
+        def seg_actor(start, n):
+            """Actor forward / backward on minibatch [start, start + n): launches only (no host synchronisation), so it can be captured."""
             self.actor_optim.zero_grad(set_to_none=True)
             for s0 in range(start, start + n, self.micro_batch):  # gradient accumulation bounds activation memory; the sum equals the minibatch mean
                 s1 = min(s0 + self.micro_batch, start + n)
@@ -350,7 +358,8 @@ class PPO:
                     loss = -(torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv)).sum() / n
                 loss.backward()
                 a_sum.add_(loss.detach())
-            h_actor = self._allreduce_start(self.actor)   # overlaps the critic's forward / backward below (the two networks share nothing)
+
+        def seg_critic(start, n):
             self.critic_optim.zero_grad(set_to_none=True)
             for s0 in range(start, start + n, self.micro_batch):
                 s1 = min(s0 + self.micro_batch, start + n)
@@ -360,13 +369,62 @@ class PPO:
                     loss = ((self.get_state_values(p_obs[s0:s1]) - p_rtg[s0:s1]) ** 2).sum() / n
                 loss.backward()
                 c_sum.add_(loss.detach())
-            h_critic = self._allreduce_start(self.critic)
-            self._allreduce_finish(h_actor)
+
+        def seg_opt():
             torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad)
             self.actor_optim.step()
-            self._allreduce_finish(h_critic)
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad)
             self.critic_optim.step()
+
+        multi = _dist() is not None and _dist().get_world_size() > 1
+
+        def step(start, n):
+            """One optimiser step, eagerly.  The two networks share nothing: the critic's forward / backward runs while the actor's gradient bucket is
+            being reduced, and both optimisers step once both buckets are back (same result as the reference's actor-then-critic order)."""
+            seg_actor(start, n)
+            h_a = self._allreduce_start(self.actor)
+            seg_critic(start, n)
+            h_c = self._allreduce_start(self.critic)
+            self._allreduce_finish(h_a); self._allreduce_finish(h_c)
+            seg_opt()
+
+        def capture(fn):
+            torch.cuda.synchronize(self.device)
+            gr = torch.cuda.CUDAGraph()
+            # thread_local: NCCL's watchdog thread polls its events while we capture; only this thread's calls must be capture-safe
+            with _static_row_grouping(), torch.cuda.graph(gr, pool=ug["pool"], capture_error_mode="thread_local" if multi else "global"):
+                out = fn()
+            if ug["pool"] is None:
+                ug["pool"] = gr.pool()
+            return gr, out
+
+        def graph_step(start, n):
+            """The same step as CUDA graphs, one set per minibatch position (the same positions in every epoch and every update).  One rank: a single
+            graph.  Several ranks: the collectives stay OUTSIDE the graphs (graph: actor fwd / bwd + bucket pack | NCCL | graph: critic + pack | NCCL |
+            graph: clip + Adam on the bucket views) -- capturing the NCCL calls themselves hung the 2-GPU run."""
+            gk = (start, n)
+            if not multi:
+                if gk not in ug["graphs"]:
+                    ug["graphs"][gk] = capture(lambda: step(start, n))[0]
+                ug["graphs"][gk].replay()
+                return
+            if gk not in ug["graphs"]:
+                g_a, h_a = capture(lambda: (seg_actor(start, n), self._pack(self.actor))[1])
+                g_a.replay(); self._reduce_async(h_a)
+                g_c, h_c = capture(lambda: (seg_critic(start, n), self._pack(self.critic))[1])
+                g_c.replay(); self._reduce_async(h_c)
+                self._allreduce_finish(h_a); self._allreduce_finish(h_c)   # p.grad -> bucket views: what the optimiser graph reads
+                g_o, _ = capture(seg_opt)
+                g_o.replay()
+                ug["graphs"][gk] = (g_a, h_a, g_c, h_c, g_o)
+                return
+            g_a, h_a, g_c, h_c, g_o = ug["graphs"][gk]
+            g_a.replay(); self._reduce_async(h_a)
+            g_c.replay(); self._reduce_async(h_c)
+            h_a["work"].wait(); h_c["work"].wait()
+            if not h_a["avg"]:
+                h_a["flat"] /= h_a["world"]; h_c["flat"] /= h_c["world"]
+            g_o.replay()
 
         for _ in range(self.updates_per_batch):
             self.decay_lr()
@@ -374,21 +432,12 @@ class PPO:
                 n = min(mb, used - start)
                 if not graphed:
                     step(start, n)
-                elif not ug["warm"]:   # the very first step runs eagerly: lazy kernel attributes, Adam's state tensors
+                elif not ug["warm"]:   # the very first step runs eagerly: lazy kernel attributes, Adam's state tensors, NCCL's communicator
                     with _static_row_grouping():
                         step(start, n)
                     ug["warm"] = True
                 else:
-                    gk = (start, n)
-                    if gk not in ug["graphs"]:   # one graph per minibatch position (the same five positions in every epoch and every update)
-                        torch.cuda.synchronize(self.device)
-                        gr = torch.cuda.CUDAGraph()
-                        with _static_row_grouping(), torch.cuda.graph(gr, pool=ug["pool"]):
-                            step(start, n)
-                        if ug["pool"] is None:
-                            ug["pool"] = gr.pool()
-                        ug["graphs"][gk] = gr
-                    ug["graphs"][gk].replay()
+                    graph_step(start, n)
                 stats["steps"] += 1
         stats["actor_loss"], stats["critic_loss"] = float(a_sum), float(c_sum)
         if graphed and _row_grouping_overflow():
