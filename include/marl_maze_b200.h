@@ -104,9 +104,12 @@ int mm_generate(const mm_state *st, int first, int n, int side_lo, int side_hi, 
 int mm_generate_ex(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
                 uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, int max_blocks, void *stream);
 /* as mm_generate_ex for the slots i of [first, first + n) with only[i] != 0 (only == NULL: all): the incremental pool refill -- the reference builds one
- * maze per reset (maze.py:57), so between two rollouts only the pool slots whose mazes were consumed are built anew, the others stay */
+ * maze per reset (maze.py:57), so between two rollouts only the pool slots whose mazes were consumed are built anew, the others stay.
+ * height_cells > 0: rectangular mazes, Maze(default_size=[w, h]) with rand_sizes False (maze.py:26-27,171-178): every maze is 2*side_lo-1 wide and
+ * 2*height_cells-1 high (both <= smax) and no size is drawn; 0: square mazes of a drawn side as in mm_generate */
 int mm_generate_masked(const mm_state *st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
-                uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, int max_blocks, const uint8_t *only, void *stream);
+                uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void *scratch, int max_blocks, const uint8_t *only, int height_cells,
+                void *stream);
 
 /*
  * Maze.reset() (maze.py:55-72) + Agent.reset() (maze_agent.py:59-79) for every env with reset_mask[e] != 0
@@ -114,6 +117,10 @@ int mm_generate_masked(const mm_state *st, int first, int n, int side_lo, int si
  * first observations/masks.   obs: [E][2][65] f32, masks: [E][2][6] u8.
  */
 int mm_reset(const mm_state *st, const uint8_t *reset_mask, float *obs, uint8_t *masks, void *stream);
+/* One agent of one env, from the host: reset != 0 = Agent.reset(x, y) (maze_agent.py:59-79: position, facing south, flags, memory, route and bounding box
+ * cleared; time_from_last_seen kept), reset == 0 = Agent.move(x, y, direction) (maze_agent.py:85-87).  The agent's next observation is computed by the
+ * next mm_step_obs, as in the reference (neither method observes). */
+int mm_agent_place(const mm_state *st, int env, int agent, int x, int y, int direction, int reset, void *stream);
 
 /*
  * K2 -- fused step + observation.  Replaces Maze.step / single_agent_step (maze.py:74-163) and

@@ -10,7 +10,7 @@ EXPORTS = [
     "mm_abi_version", "mm_source_hash", "mm_error_string", "mm_last_cuda_error",
     "mm_sizeof_pool_grid", "mm_sizeof_pool_d2e", "mm_sizeof_pool_hdr", "mm_sizeof_env_grid", "mm_sizeof_env_hdr",
     "mm_sizeof_env_episode", "mm_sizeof_agent_a", "mm_sizeof_agent_b", "mm_sizeof_finalize_scratch", "mm_sizeof_generate_scratch",
-    "mm_init_state", "mm_load_layouts", "mm_generate", "mm_generate_ex", "mm_generate_masked", "mm_reset", "mm_step_obs",
+    "mm_init_state", "mm_load_layouts", "mm_generate", "mm_generate_ex", "mm_generate_masked", "mm_reset", "mm_agent_place", "mm_step_obs",
     "mm_unpack_agents", "mm_unpack_envs", "mm_unpack_layout", "mm_unpack_pool", "mm_gae",
     "mm_policy_offsets", "mm_sizeof_policy_scratch", "mm_policy_forward", "mm_critic_forward", "mm_selftest_div", "mm_counter_add",
     "mm_wgrad_geometry", "mm_wgrad_tf32x3", "mm_linear_tf32x3", "mm_linear_f16x3", "mm_ppo_loss_geometry", "mm_ppo_heads_loss",
@@ -70,8 +70,9 @@ def lib():
         "mm_load_layouts": (i32, [st, i32, i32, vp, vp, vp, vp]),
         "mm_generate": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, i32, i32, vp, vp]),
         "mm_generate_ex": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, i32, i32, vp, i32, vp]),
-        "mm_generate_masked": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, i32, i32, vp, i32, vp, vp]),
+        "mm_generate_masked": (i32, [st, i32, i32, i32, i32, i32, i32, u64, u32, i32, i32, vp, i32, vp, i32, vp]),
         "mm_reset": (i32, [st, vp, vp, vp, vp]),
+        "mm_agent_place": (i32, [st, i32, i32, i32, i32, i32, i32, vp]),
         "mm_step_obs": (i32, [st, vp, vp, vp, vp, vp, i32, u64, vp, vp]),
         "mm_unpack_agents": (i32, [st, vp, vp]),
         "mm_unpack_envs": (i32, [st, vp, vp]),

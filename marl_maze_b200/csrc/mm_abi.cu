@@ -8,7 +8,7 @@ namespace mm {
 cudaError_t launch_step_obs(const StepParams& p, bool reset_only, cudaStream_t stream);
 cudaError_t launch_gae(const float*, const float*, const uint8_t*, const float*, float*, float*, int, int, double, double, cudaStream_t);
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty,
-                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, cudaStream_t stream);
+                            uint64_t seed, uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, int height_cells, cudaStream_t stream);
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
                           int, const uint64_t*, cudaStream_t);
 cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream);
@@ -26,6 +26,7 @@ cudaError_t launch_critic(const float* wts, const float* obs, int E, float* valu
 __global__ void k_load_layouts(ulonglong2*, ulonglong2*, uint4*, int, int, int, int, const uint8_t*, const int32_t*, uint16_t*);
 __global__ void k_init_state(uint4*, uint32_t*, uint4*, uint32_t*, int);
 __global__ void k_unpack_agents(const uint4*, const uint32_t*, const uint4*, const ulonglong2*, int, int, int32_t*);
+__global__ void k_agent_place(uint4*, uint32_t*, int, int, int, int, int);
 __global__ void k_unpack_envs(const uint4*, const uint32_t*, int, int32_t*);
 __global__ void k_unpack_grid(const ulonglong2*, const ulonglong2*, int, uint8_t*, uint8_t*);
 __global__ void k_unpack_pool_hdr(const uint4*, int, int32_t*);
@@ -114,21 +115,28 @@ int mm_load_layouts(const mm_state* st, int first, int n, const uint8_t* layouts
 }
 
 int mm_generate_masked(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
-                       int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, void* stream) {
+                       int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, int height_cells, void* stream) {
     if (!state_ok(st) || first < 0 || n < 0 || first + n > st->n_pool || side_lo < 4 || side_hi < side_lo || side_hi * 2 - 1 > st->smax || difficulty < 1 ||
-        id_mod < 0 || (n && !scratch) || max_blocks < 0)
+        id_mod < 0 || (n && !scratch) || max_blocks < 0 || height_cells < 0 || (height_cells > 0 && (height_cells < 4 || height_cells * 2 - 1 > st->smax)))
         return MM_ERR_BAD_ARG;
     if (n == 0) return MM_OK;
     return cuda_status(launch_generate(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks, only,
-                                       (cudaStream_t)stream));
+                                       height_cells, (cudaStream_t)stream));
 }
 int mm_generate_ex(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
                    int id_mod, int id_mul, void* scratch, int max_blocks, void* stream) {
-    return mm_generate_masked(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks, nullptr, stream);
+    return mm_generate_masked(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, max_blocks, nullptr, 0, stream);
 }
 int mm_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base,
                 int id_mod, int id_mul, void* scratch, void* stream) {
     return mm_generate_ex(st, first, n, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, scratch, 0, stream);
+}
+
+int mm_agent_place(const mm_state* st, int env, int agent, int x, int y, int direction, int reset, void* stream) {
+    if (!state_ok(st) || env < 0 || env >= st->n_envs || agent < 0 || agent > 1 || x < 0 || y < 0 || x >= st->smax || y >= st->smax || direction < 0 || direction > 3)
+        return MM_ERR_BAD_ARG;
+    k_agent_place<<<1, 1, 0, (cudaStream_t)stream>>>((uint4*)st->agent_a, (uint32_t*)st->agent_b, 2 * env + agent, x, y, direction, reset);
+    return cuda_status(cudaGetLastError());
 }
 
 int mm_reset(const mm_state* st, const uint8_t* reset_mask, float* obs, uint8_t* masks, void* stream) {

@@ -32,7 +32,7 @@ struct PhiloxStream {
 
 __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglong2* pool_d2e, uint4* pool_hdr, int first, int n, int rows, int smax,
                                                 int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed, uint32_t id_base, int id_mod, int id_mul,
-                                                uint16_t* scratch, const uint8_t* __restrict__ only) {
+                                                uint16_t* scratch, const uint8_t* __restrict__ only, int height_cells) {
     // grid-stride over mazes: a full grid for an inline build, a few blocks per SM for a background build that trickles along beside
     // other kernels (each thread's serial carve holds its residency slot for milliseconds)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -46,8 +46,11 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
     for (int y = 0; y < smax; y++) { open_rows[y] = 0; seen[y] = 0; dlo[y] = 0; dhi[y] = 0; }
     auto is_open = [&](int x, int y) { return (open_rows[y] >> (x + kPad)) & 1ull; };
 
-    const int S = rng.randint(side_lo, side_hi) * 2 - 1;  // maze.py:172
-    const int W = S, Hh = S;
+    // rand_sizes (maze.py:171-174): one draw, square.  height_cells > 0: Maze(default_size=[w, h]) with rand_sizes False (maze.py:26-27) -- every maze
+    // is 2w-1 wide and 2h-1 high and no size is drawn
+    const int W = height_cells > 0 ? side_lo * 2 - 1 : rng.randint(side_lo, side_hi) * 2 - 1;  // maze.py:172
+    const int Hh = height_cells > 0 ? height_cells * 2 - 1 : W;
+    const int S = max(W, Hh);
     int sx, sy;
     if (rand_start) { sx = rng.randint(0, (W - 1) / 2) * 2; sy = rng.randint(0, (Hh - 1) / 2) * 2; }  // maze.py:231-234
     else { sx = ((W / 2) % 2 == 0) ? W / 2 : W / 2 - 1; sy = 0; }
@@ -187,11 +190,11 @@ __global__ void __launch_bounds__(64) k_generate(ulonglong2* pool_grid, ulonglon
 }
 
 cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, int side_hi, int rand_start, int difficulty, uint64_t seed,
-                            uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, cudaStream_t stream) {
+                            uint32_t id_base, int id_mod, int id_mul, void* scratch, int max_blocks, const uint8_t* only, int height_cells, cudaStream_t stream) {
     int blocks = (n + 63) / 64;
     if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
     k_generate<<<blocks, 64, 0, stream>>>((ulonglong2*)st->pool_grid, (ulonglong2*)st->pool_d2e, (uint4*)st->pool_hdr, first, n,
-                                                 st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, (uint16_t*)scratch, only);
+                                                 st->smax + 2 * MM_PAD, st->smax, side_lo, side_hi, rand_start, difficulty, seed, id_base, id_mod, id_mul, (uint16_t*)scratch, only, height_cells);
     return cudaGetLastError();
 }
 

@@ -90,6 +90,20 @@ __global__ void k_unpack_agents(const uint4* agent_a, const uint32_t* agent_b, c
     o[17] = len;
 }
 
+// Agent.reset(x, y) (maze_agent.py:59-79; time_from_last_seen is deliberately kept) or Agent.move(x, y, direction) (maze_agent.py:85-87) of ONE agent: the
+// host-callable form of what K2's reset pass / step pass do for every agent.  One thread.
+__global__ void k_agent_place(uint4* agent_a, uint32_t* agent_b, int g, int x, int y, int dir, int reset) {
+    Agent a = unpack_agent(agent_a[g], agent_b[g]);
+    a.x = x; a.y = y;
+    if (reset) {
+        a.olsx = x; a.olsy = y; a.minx = a.maxx = x; a.miny = a.maxy = y;
+        a.dir = 2; a.mkv = 0; a.mem = 0; a.ke = a.oke = 0; a.exit_len = -1; a.has = a.team = 0; a.d2e = 0;
+    } else {
+        a.dir = dir & 3;
+    }
+    agent_a[g] = pack_agent(a);
+}
+
 __global__ void k_unpack_envs(const uint4* env_hdr, const uint32_t* env_episode, int E, int32_t* out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;

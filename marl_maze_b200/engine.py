@@ -111,16 +111,17 @@ class MazeEngine:
 
     def generate(self, seed: int, side_range=(13, 13), rand_start: bool = True, difficulty: int = 1, first: int = 0,
                  count: Optional[int] = None, id_base: int = 0, id_mod: int = 0, id_mul: int = 0, only: Optional[torch.Tensor] = None,
-                 max_blocks: int = 0):
+                 max_blocks: int = 0, height_cells: int = 0):
         """K1: fill pool entries [first, first+count) with freshly generated mazes (maze.py:170-273).  only: u8 [count], build slot i only where
-        only[i] != 0 (the incremental refill); max_blocks: cap on the thread blocks in flight (a background build on a side stream)."""
+        only[i] != 0 (the incremental refill); max_blocks: cap on the thread blocks in flight (a background build on a side stream); height_cells > 0:
+        rectangular mazes of (2 * side_range[0] - 1) x (2 * height_cells - 1) cells, Maze(default_size=[w, h]) with rand_sizes False."""
         n = self.P - first if count is None else count
         if only is not None:
             assert only.dtype == torch.uint8 and only.is_contiguous() and only.numel() == n and only.device == self.pool_hdr.device
         scratch = self._get_scratch(self.lib.mm_sizeof_generate_scratch(n, self.smax))
         _abi.check(self.lib.mm_generate_masked(C.byref(self.st), first, n, int(side_range[0]), int(side_range[1]), int(rand_start), int(difficulty),
                                                C.c_uint64(seed & (2**64 - 1)), C.c_uint32(id_base & 0xFFFFFFFF), int(id_mod), int(id_mul), _ptr(scratch),
-                                               int(max_blocks), _ptr(only), self._stream()), "mm_generate_masked")
+                                               int(max_blocks), _ptr(only), int(height_cells), self._stream()), "mm_generate_masked")
         self.launches += 1
 
     def consumed_slots(self) -> torch.Tensor:
@@ -157,6 +158,11 @@ class MazeEngine:
         _abi.check(self.lib.mm_reset(C.byref(self.st), _ptr(mask), _ptr(obs), _ptr(masks), self._stream()), "mm_reset")
         self.launches += 1
         return obs, masks
+
+    def place_agent(self, env: int, agent: int, x: int, y: int, direction: int = 2, reset: bool = False):
+        """Agent.reset(x, y) (reset=True) or Agent.move(x, y, direction) of one agent (maze_agent.py:59-87) on the packed device state."""
+        _abi.check(self.lib.mm_agent_place(C.byref(self.st), int(env), int(agent), int(x), int(y), int(direction), int(reset), self._stream()), "mm_agent_place")
+        self.launches += 1
 
     def step(self, actions: Optional[torch.Tensor], auto_reset: bool = True, obs: Optional[torch.Tensor] = None,
              masks: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None, done: Optional[torch.Tensor] = None,

@@ -36,13 +36,13 @@ class Maze:
             raise NotImplementedError("the reference (and the step kernel's lane pairing) is a two-agent game (README.md:34)")
         if sorted(a.tag for a in agents) != [2, 3] or agents[0].tag != 2:
             raise ValueError("agents must be tagged (2, 3) in that order (main.py:18-19)")
-        if not rand_sizes and default_size[0] != default_size[1]:
-            raise NotImplementedError("the batched generator builds square mazes; use rand_sizes or a square default_size")
         self.agents = agents
         self.max_timestep, self.difficulty, self.rand_start, self.rand_sizes = max_timestep, difficulty, rand_start, rand_sizes
         self.rand_range, self.default_size = list(rand_range), list(default_size)
         self.num_envs, self.device, self.seed, self.env_offset = int(num_envs), torch.device(device), int(seed), int(env_offset)
         self.side_range = (rand_range[0], rand_range[1]) if rand_sizes else (default_size[0], default_size[0])
+        # Maze(default_size=[w, h]) with rand_sizes False: every maze is 2w-1 by 2h-1 (maze.py:26-27); square default sizes keep the rand_sizes path
+        self.height_cells = default_size[1] if (not rand_sizes and default_size[0] != default_size[1]) else 0
         self.pool_episodes = pool_episodes or (64 if self.num_envs == 1 else 4)
         for i, agent in enumerate(self.agents):  # maze.py:40-42
             agent.maze = self
@@ -57,7 +57,7 @@ class Maze:
     # ------------------------------------------------------------------ engine / pool
     def _ensure_engine(self):
         if self.engine is None:
-            smax = self.side_range[1] * 2 - 1
+            smax = max(self.side_range[1], self.height_cells) * 2 - 1
             self.engine = MazeEngine(self.num_envs, smax=smax, max_timestep=self.max_timestep, pool_size=self.num_envs * self.pool_episodes,
                                      device=self.device, env_offset=self.env_offset, vision=tuple(a.vision_range for a in self.agents))
             self.refill_pool()
@@ -71,7 +71,8 @@ class Maze:
         if (self.env_offset + self.num_envs) * self.pool_episodes > 1 << 32:
             raise ValueError("(env_offset + num_envs) * pool_episodes must fit the 32-bit maze id")
         return dict(seed=(self.seed + _splitmix64(g)) & _M64 if g else self.seed & _M64, side_range=self.side_range, rand_start=self.rand_start,
-                    difficulty=self.difficulty, id_base=self.env_offset * self.pool_episodes, id_mod=self.num_envs, id_mul=self.pool_episodes)
+                    difficulty=self.difficulty, id_base=self.env_offset * self.pool_episodes, id_mod=self.num_envs, id_mul=self.pool_episodes,
+                    height_cells=self.height_cells)
 
     def _refill_mask(self):
         """The slots the next refill builds anew.  The reference builds ONE maze per reset (maze.py:57); a rollout draws its mazes from pool slots
@@ -111,6 +112,13 @@ class Maze:
         self._obs, self._masks = eng.reset(mask, obs=obs, masks=masks)
         self.exit_found = False
         return self._emit(self._obs, self._masks)
+
+    def build_maze(self):
+        """Maze.build_maze() (maze.py:170-218): every env gets its next maze.  The reference's grid and agents are separate python objects; here a
+        maze's working copy and its agents are one device state, so taking a new maze also places the agents on shortest_path[0:2] -- i.e. this is
+        reset() without the return value (the reference only ever calls build_maze from reset, maze.py:57).  Generation itself is K1
+        (csrc/mm_generate.cu): get_neighbors / set_start / set_end / set_key / get_shortest_path (maze.py:220-273) are stages of that kernel."""
+        self.reset()
 
     def step(self, action, auto_reset: Optional[bool] = None, **out):
         eng = self._ensure_engine()

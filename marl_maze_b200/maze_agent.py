@@ -28,6 +28,15 @@ class Agent:
         self.env = 0
         self.average_exit = 5000
 
+    # ---- the reference's two state setters (maze_agent.py:59-87), on the packed device state of env `self.env` ----------------------------
+    def reset(self, x, y):
+        """Agent.reset(x, y): position, facing south, flags / memory / route / bounding box cleared; time_from_last_seen kept (maze_agent.py:59-79)."""
+        self.maze._ensure_engine().place_agent(self.env, self._index, x, y, 2, reset=True)
+
+    def move(self, x, y, direction):
+        """Agent.move(x, y, direction) (maze_agent.py:85-87)."""
+        self.maze._ensure_engine().place_agent(self.env, self._index, x, y, direction, reset=False)
+
     # ---- behaviour -----------------------------------------------------------------------------------------------
     def get_action(self, obs, mask):
         """(action, probability of that action) -- maze_agent.py:81-83."""

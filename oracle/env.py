@@ -40,6 +40,8 @@ def load_lib():
         "omaze_new": (vp, [i32] * 8),
         "omaze_free": (None, [vp]),
         "omaze_set_vision": (None, [vp, i32, i32]),
+        "omaze_agent_reset": (None, [vp, i32, i32, i32]),
+        "omaze_agent_move": (None, [vp, i32, i32, i32, i32]),
         "obatch_set_vision": (None, [vp, i32, i32]),
         "omaze_seed": (None, [vp, u64]),
         "omaze_seed_philox": (None, [vp, u64, u32]),
@@ -94,6 +96,12 @@ class OracleMaze:
         if getattr(self, "_own", False) and self.h:
             self.lib.omaze_free(self.h)
             self.h = None
+
+    def agent_reset(self, a: int, x: int, y: int):   # Agent.reset(x, y), maze_agent.py:59-79
+        self.lib.omaze_agent_reset(self.h, a, x, y)
+
+    def agent_move(self, a: int, x: int, y: int, direction: int):   # Agent.move(x, y, direction), maze_agent.py:85-87
+        self.lib.omaze_agent_move(self.h, a, x, y, direction)
 
     def seed(self, s: int):  # == random.seed(s) before Maze.reset()
         self.lib.omaze_seed(self.h, s)

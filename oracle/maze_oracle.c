@@ -526,6 +526,9 @@ static void reset_agents(OMaze *m, float *obs, uint8_t *masks) {
     }
 }
 void omaze_reset(OMaze *m, float *obs, uint8_t *masks) { omaze_build(m); reset_agents(m, obs, masks); }
+/* the reference's two public agent setters, for tests of the host surface: Agent.reset(x, y) maze_agent.py:59-79, Agent.move(x, y, direction) :85-87 */
+void omaze_agent_reset(OMaze *m, int a, int x, int y) { agent_reset(&m->agents[a], x, y); }
+void omaze_agent_move(OMaze *m, int a, int x, int y, int direction) { m->agents[a].x = x; m->agents[a].y = y; m->agents[a].direction = direction; }
 void omaze_reset_injected(OMaze *m, int width, int height, const uint8_t *layout, int p0x, int p0y, int p1x, int p1y,
                           int ex, int ey, int kx, int ky, int spl, float *obs, uint8_t *masks) {
     omaze_inject(m, width, height, layout, p0x, p0y, p1x, p1y, ex, ey, kx, ky, spl);

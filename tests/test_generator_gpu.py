@@ -45,6 +45,41 @@ def test_generator_matches_oracle_philox(cfg):
         _check_tree_properties(g)
 
 
+@pytest.mark.parametrize("wh", [(6, 11), (13, 5), (4, 27), (20, 9)], ids=lambda v: f"{2 * v[0] - 1}x{2 * v[1] - 1}")
+def test_rectangular_mazes_match_oracle_and_step(wh):
+    """Maze(default_size=[w, h]) with rand_sizes False (maze.py:26-27,170-178): rectangular mazes.  K1 against the oracle's generator under the same Philox
+    stream (no size draw in this mode), then K2 stepping those mazes against the oracle, every field."""
+    import torch
+    from marl_maze_b200 import MazeEngine
+    from oracle import OracleBatch
+    w, h = wh
+    E, K, max_t = 64, 2, 90
+    smax = 2 * max(w, h) - 1
+    eng = MazeEngine(E, smax=smax, max_timestep=max_t, pool_size=E * K)
+    seed, id_base = 4242, 9
+    eng.generate(seed, side_range=(w, w), rand_start=True, difficulty=2, id_base=id_base, height_cells=h)
+    o = OracleMaze(max_timestep=10, difficulty=2, rand_start=True, rand_sizes=False, default_size=(w, h))
+    ob = OracleBatch(E, E * K, max_timestep=max_t, threads=4)
+    for p in range(E * K):
+        g = eng.pool_maze(p)
+        o.seed_philox(seed, id_base + p); o.build(); m = o.maze()
+        assert (g["width"], g["height"]) == (m["width"], m["height"]) == (2 * w - 1, 2 * h - 1)
+        assert np.array_equal(g["layout"], m["layout"]), f"maze {p} layout"
+        assert (g["start"], g["path1"], g["end"], g["key"], g["shortest_path_len"]) == (m["start"], m["path1"], m["end"], m["key"], m["shortest_path_len"]), p
+        _check_tree_properties(g)
+        ob.set_pool_maze(p, m)
+    oo, om = ob.reset_all(); go, gm = eng.reset()
+    assert np.array_equal(go.cpu().numpy().view(np.uint32), oo.view(np.uint32)) and np.array_equal(gm.cpu().numpy(), om)
+    rng = (np.arange(E, dtype=np.uint64) + 3) * np.uint64(0x9E3779B97F4A7C15)
+    for t in range(200):
+        act = ob.guided_actions(rng, p_follow=0.8, p_mark=0.3)
+        go, gm, gr, gd = eng.step(torch.from_numpy(act).to(eng.device))
+        oo, om, orr, od = ob.step(act)
+        assert np.array_equal(go.cpu().numpy().view(np.uint32), oo.view(np.uint32)), t
+        assert np.array_equal(gm.cpu().numpy(), om) and np.array_equal(gr.cpu().numpy(), orr) and np.array_equal(gd.cpu().numpy(), od), t
+    assert np.array_equal(eng.agents(), ob.agents()) and ob.errors() == 0
+
+
 def test_generated_pool_steps_bit_exact_vs_oracle():
     """End to end without any injected data: K1 fills the pool, K2 steps it; the oracle generates the same mazes itself."""
     import torch

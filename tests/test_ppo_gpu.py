@@ -195,6 +195,31 @@ def test_graphed_update_equals_eager_update(tmp_path, faithful):
         assert sa["actor_loss"] == sb["actor_loss"] and sa["critic_loss"] == sb["critic_loss"]
 
 
+def test_agent_reset_and_move_setters_match_oracle(tmp_path):
+    """Agent.reset(x, y) / Agent.move(x, y, direction) (maze_agent.py:59-87) and Maze.build_maze() on the device state: after the same calls on the
+    oracle, the next steps' observations, masks and agent state agree."""
+    from oracle import OracleMaze
+    brain, agents, maze = _make(1, tmp_path)
+    maze.build_maze()                                  # == reset() without the return value
+    m = maze._pool()
+    o = OracleMaze(max_timestep=120)
+    o.reset_injected(dict(layout=m["layout"], path0=m["path0"], path1=m["path1"], end=m["end"], key=m["key"], shortest_path_len=m["shortest_path_len"]))
+    path = maze.shortest_path
+    stop = [[4, 0], [4, 0]]
+    for k in range(3):
+        maze.step(stop); o.step([4, 0, 4, 0])
+    (x, y), (x2, y2) = path[min(4, len(path) - 1)], path[min(6, len(path) - 1)]
+    agents[0].move(x, y, 1); o.agent_move(0, x, y, 1)
+    agents[1].reset(x2, y2); o.agent_reset(1, x2, y2)
+    assert (agents[0].x, agents[0].y, agents[0].direction) == (x, y, 1) and (agents[1].x, agents[1].y, agents[1].direction) == (x2, y2, 2)
+    for k in range(4):
+        obs, masks, r, d = maze.step(stop)
+        oo, om, orr, od = o.step([4, 0, 4, 0])
+        assert np.array_equal(np.asarray(obs, np.float32).view(np.uint32), oo.view(np.uint32)), k
+        assert np.array_equal(np.asarray(masks, np.uint8), om) and r == orr and d == od
+        assert np.array_equal(maze.engine.agents()[0][:, :17], o.agents()[:, :17])   # (column 17, len(exit_route), is a stack in the reference: move() leaves it stale)
+
+
 def test_incremental_refill_rebuilds_consumed_slots_only(tmp_path):
     """The reference builds one maze per reset (maze.py:57).  Between two rollouts the pool refill rebuilds exactly the slots (env e, episode k) an
     episode started on -- k < env_episode[e] -- with the new refill's seed; the other slots keep their (unseen) mazes."""
