@@ -29,7 +29,15 @@ constexpr int TM_OFF_QH = 0, TM_OFF_QL = TM_Q_BYTES, TM_OFF_KH = 2 * TM_Q_BYTES,
               TM_OFF_VL = TM_OFF_VH + TM_KV_BYTES, TM_OFF_TOK = TM_OFF_VL + TM_KV_BYTES, TM_TILE_BYTES = TM_OFF_TOK + 24 * TM_EMB * 4;
 static_assert(TM_TILE_BYTES % 16 == 0, "16-byte aligned tiles");
 constexpr int TM_MAP_FLOATS = 60 * TM_TOK * 5;                  // [60][23][4] + [60][23]
-constexpr int TM_SMEM_BYTES = TM_MAP_FLOATS * 4 + TM_WARPS * TM_TILE_BYTES;
+// Rows a warp carries through phase A together: every map element fetched from shared memory serves TM_ROWS rows (240 of the ~445 shared-memory
+// wavefronts per row are those fetches); phase B runs one row at a time on the row's own tile.  Measured (profiles/r03d_token_rows_variants.jsonl): 2 rows
+// x 8 warps 0.305 ms, 2 x 4 warps x 2 blocks 0.298, 3 x 6 warps 0.366, 4 x 4 warps 0.452 against 0.290 for one row x 8 warps x 2 blocks -- the second
+// tile per warp halves the resident warps and the lost latency hiding costs more than the saved wavefronts.  Default 1.
+#ifndef MM_TOKM_ROWS
+#define MM_TOKM_ROWS 1
+#endif
+constexpr int TM_ROWS = MM_TOKM_ROWS;
+constexpr int TM_SMEM_BYTES = TM_MAP_FLOATS * 4 + TM_WARPS * TM_ROWS * TM_TILE_BYTES;
 
 struct TokOffsets { int tokm, tokb, proj_col, proj_dim; };
 
@@ -81,15 +89,14 @@ __global__ void __launch_bounds__(TM_WARPS * 32, MM_TOKM_MINBLOCKS) k_tokens_mma
     float (*s_m)[TM_TOK][4] = reinterpret_cast<float (*)[TM_TOK][4]>(tm_smem);                     // [60][23][4]
     float (*s_b)[TM_TOK] = reinterpret_cast<float (*)[TM_TOK]>(tm_smem + 60 * TM_TOK * 16);       // [60][23]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* tile = tm_smem + TM_MAP_FLOATS * 4 + w * TM_TILE_BYTES;
+    uint8_t* tiles = tm_smem + TM_MAP_FLOATS * 4 + w * TM_ROWS * TM_TILE_BYTES;
     for (int i = threadIdx.x; i < 60 * TM_TOK * 4; i += blockDim.x) (&s_m[0][0][0])[i] = wts[o.tokm + i];
     for (int i = threadIdx.x; i < 60 * TM_TOK; i += blockDim.x) (&s_b[0][0])[i] = wts[o.tokb + i];
-    for (int i = lane; i < TM_TILE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);   // padding rows / columns stay zero
+    for (int i = lane; i < TM_ROWS * TM_TILE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0u, 0u, 0u, 0u);   // padding rows / columns stay zero
     __syncthreads();
     const bool on = lane < TM_TOK;
     const int a = on ? lane : 0;
     const int c0 = (int)wts[o.proj_col + a], nd = (int)wts[o.proj_dim + a];
-    const uint32_t t_u32 = (uint32_t)__cvta_generic_to_shared(tile);
     const int g = lane >> 2, t4 = lane & 3;
     // ldmatrix row addresses.  A (queries, x4): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15) of an m16 tile.
     const uint32_t q_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * TM_PITCH + (lane >> 4) * 16);
@@ -98,54 +105,85 @@ __global__ void __launch_bounds__(TM_WARPS * 32, MM_TOKM_MINBLOCKS) k_tokens_mma
     // B of the context (values, x4.trans, one n8 tile of the embedding): matrices (tokens 0-7), (8-15), (16-23), (16-23 again, unused)
     const uint32_t v_off = (uint32_t)(((lane & 7) + min(lane >> 3, 2) * 8) * TM_PITCH);
 #pragma unroll 1
-    for (int row = blockIdx.x * TM_WARPS + w; row < nrows; row += gridDim.x * TM_WARPS) {
-        // ---------------- phase A: lane = token
-        float x[4];
+    for (int row0 = (blockIdx.x * TM_WARPS + w) * TM_ROWS; row0 < nrows; row0 += gridDim.x * TM_WARPS * TM_ROWS) {
+        // ---------------- phase A: lane = token, TM_ROWS rows per map fetch
+        float x[TM_ROWS][4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) x[c] = (c < nd) ? obs[(size_t)row * kObs + c0 + c] : 0.f;
-        auto affine = [&](int j) {
+        for (int r = 0; r < TM_ROWS; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) x[r][c] = (c < nd && row0 + r < nrows) ? obs[(size_t)(row0 + r) * kObs + c0 + c] : 0.f;
+        auto affine = [&](int j, float* out) {   // out[r] = (M_a x_a + b_a)[j] of row r
             const float4 m = *reinterpret_cast<const float4*>(&s_m[j][a][0]);
-            return fmaf(x[3], m.w, fmaf(x[2], m.z, fmaf(x[1], m.y, fmaf(x[0], m.x, s_b[j][a]))));
+            const float b = s_b[j][a];
+#pragma unroll
+            for (int r = 0; r < TM_ROWS; r++) out[r] = fmaf(x[r][3], m.w, fmaf(x[r][2], m.z, fmaf(x[r][1], m.y, fmaf(x[r][0], m.x, b))));
         };
-        {
-            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int d = 0; d < TM_KQ / 2; d++) tm_split2(affine(20 + 2 * d), affine(21 + 2 * d), hi[d], lo[d]);   // key
+        for (int part = 0; part < 2; part++) {   // keys (map rows 20-29) -> K tiles, queries (30-39) -> Q tiles
+            uint32_t hi[TM_ROWS][8], lo[TM_ROWS][8];
 #pragma unroll
-            for (int d = TM_KQ / 2; d < 8; d++) hi[d] = lo[d] = 0u;
-            if (on) {
-                uint4* ph = reinterpret_cast<uint4*>(tile + TM_OFF_KH + a * TM_PITCH);
-                uint4* pl = reinterpret_cast<uint4*>(tile + TM_OFF_KL + a * TM_PITCH);
-                ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            for (int d = 0; d < 8; d++) {
+                if (d < TM_KQ / 2) {
+                    float v0[TM_ROWS], v1[TM_ROWS];
+                    affine(20 + 10 * part + 2 * d, v0); affine(21 + 10 * part + 2 * d, v1);
+#pragma unroll
+                    for (int r = 0; r < TM_ROWS; r++) tm_split2(v0[r], v1[r], hi[r][d], lo[r][d]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < TM_ROWS; r++) hi[r][d] = lo[r][d] = 0u;
+                }
             }
-#pragma unroll
-            for (int d = 0; d < TM_KQ / 2; d++) tm_split2(affine(30 + 2 * d), affine(31 + 2 * d), hi[d], lo[d]);   // query
             if (on) {
-                uint4* ph = reinterpret_cast<uint4*>(tile + TM_OFF_QH + a * TM_PITCH);
-                uint4* pl = reinterpret_cast<uint4*>(tile + TM_OFF_QL + a * TM_PITCH);
-                ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-        }
-        {
-            uint32_t hi[12], lo[12];
 #pragma unroll
-            for (int d = 0; d < TM_EMB / 2; d++) tm_split2(affine(40 + 2 * d), affine(41 + 2 * d), hi[d], lo[d]);   // value
-            hi[10] = hi[11] = lo[10] = lo[11] = 0u;
-            if (on) {
-                uint4* ph = reinterpret_cast<uint4*>(tile + TM_OFF_VH + a * TM_PITCH);
-                uint4* pl = reinterpret_cast<uint4*>(tile + TM_OFF_VL + a * TM_PITCH);
-#pragma unroll
-                for (int i = 0; i < 3; i++) { ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]); pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]); }
+                for (int r = 0; r < TM_ROWS; r++) {
+                    uint8_t* tile = tiles + r * TM_TILE_BYTES;
+                    uint4* ph = reinterpret_cast<uint4*>(tile + (part ? TM_OFF_QH : TM_OFF_KH) + a * TM_PITCH);
+                    uint4* pl = reinterpret_cast<uint4*>(tile + (part ? TM_OFF_QL : TM_OFF_KL) + a * TM_PITCH);
+                    ph[0] = make_uint4(hi[r][0], hi[r][1], hi[r][2], hi[r][3]); ph[1] = make_uint4(hi[r][4], hi[r][5], hi[r][6], hi[r][7]);
+                    pl[0] = make_uint4(lo[r][0], lo[r][1], lo[r][2], lo[r][3]); pl[1] = make_uint4(lo[r][4], lo[r][5], lo[r][6], lo[r][7]);
+                }
             }
         }
-        if (on) {
-            float4* pt = reinterpret_cast<float4*>(tile + TM_OFF_TOK + a * TM_EMB * 4);
 #pragma unroll
-            for (int d4 = 0; d4 < TM_EMB / 4; d4++) pt[d4] = make_float4(affine(4 * d4), affine(4 * d4 + 1), affine(4 * d4 + 2), affine(4 * d4 + 3));
+        for (int i = 0; i < 3; i++) {   // values (map rows 40-59), 8 columns = one 16-byte chunk at a time; the last chunk holds 4 values + padding
+            uint32_t hi[TM_ROWS][4], lo[TM_ROWS][4];
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                if (4 * i + d < TM_EMB / 2) {
+                    float v0[TM_ROWS], v1[TM_ROWS];
+                    affine(40 + 8 * i + 2 * d, v0); affine(41 + 8 * i + 2 * d, v1);
+#pragma unroll
+                    for (int r = 0; r < TM_ROWS; r++) tm_split2(v0[r], v1[r], hi[r][d], lo[r][d]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < TM_ROWS; r++) hi[r][d] = lo[r][d] = 0u;
+                }
+            }
+            if (on) {
+#pragma unroll
+                for (int r = 0; r < TM_ROWS; r++) {
+                    uint8_t* tile = tiles + r * TM_TILE_BYTES;
+                    reinterpret_cast<uint4*>(tile + TM_OFF_VH + a * TM_PITCH)[i] = make_uint4(hi[r][0], hi[r][1], hi[r][2], hi[r][3]);
+                    reinterpret_cast<uint4*>(tile + TM_OFF_VL + a * TM_PITCH)[i] = make_uint4(lo[r][0], lo[r][1], lo[r][2], lo[r][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int d4 = 0; d4 < TM_EMB / 4; d4++) {   // the token itself (map rows 0-19), fp32: the residual
+            float t0[TM_ROWS], t1[TM_ROWS], t2[TM_ROWS], t3[TM_ROWS];
+            affine(4 * d4, t0); affine(4 * d4 + 1, t1); affine(4 * d4 + 2, t2); affine(4 * d4 + 3, t3);
+            if (on) {
+#pragma unroll
+                for (int r = 0; r < TM_ROWS; r++) reinterpret_cast<float4*>(tiles + r * TM_TILE_BYTES + TM_OFF_TOK + a * TM_EMB * 4)[d4] = make_float4(t0[r], t1[r], t2[r], t3[r]);
+            }
         }
         __syncwarp();
+#pragma unroll 1
+        for (int r = 0; r < TM_ROWS; r++) {
+        const int row = row0 + r;
+        if (row >= nrows) break;
+        uint8_t* tile = tiles + r * TM_TILE_BYTES;
+        const uint32_t t_u32 = (uint32_t)__cvta_generic_to_shared(tile);
         // ---------------- phase B: scores S[32 x 24] = Q K^T (three fp16 products), rows = query tokens
         float sc[2][3][4];
 #pragma unroll
@@ -227,7 +265,8 @@ __global__ void __launch_bounds__(TM_WARPS * 32, MM_TOKM_MINBLOCKS) k_tokens_mma
                 }
             }
         }
-        __syncwarp();  // the tiles are rewritten by the warp's next row
+        }
+        __syncwarp();  // the tiles are rewritten by the warp's next rows
     }
 }
 
@@ -238,7 +277,7 @@ cudaError_t launch_tokens_mma(const float* wts, const float* obs, int R, float* 
         if (e != cudaSuccess) { configured.retract(); return e; }
     }
     TokOffsets o{off_tokm, off_tokb, off_col, off_dim};
-    const int blocks = (R + TM_WARPS - 1) / TM_WARPS;
+    const int blocks = (R + TM_WARPS * TM_ROWS - 1) / (TM_WARPS * TM_ROWS);
     k_tokens_mma<<<blocks < 148 * MM_TOKM_MINBLOCKS ? blocks : 148 * MM_TOKM_MINBLOCKS, TM_WARPS * 32, TM_SMEM_BYTES, stream>>>(obs, wts, o, x0, R);
     return cudaGetLastError();
 }

@@ -101,6 +101,10 @@ __device__ __forceinline__ void tf_tma_load_2d_mc(void* dst, const CUtensorMap* 
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
                  : "memory");
 }
+// ask the L2 for a box of a tensor map ahead of its use (no shared memory, no completion to wait for)
+__device__ __forceinline__ void tf_tma_prefetch_l2(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tf_commit_mc(uint64_t* bar, uint16_t mask) {   // arrive on the barrier at this offset in every CTA of the mask
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
@@ -272,6 +276,12 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                         mbar_expect_tx(&a_full[sa], TF_A_BYTES);
                         tma_load_2d(hlo + sa * TF_A_BYTES, &maps.a, kb * TF_BK, m0, &a_full[sa]);
                     }
+                }
+                // The next tile's activation blocks can only be LOADED once this tile's head MMAs are done (the landing slots alias the lo plane), which
+                // exposes their HBM latency at every tile start: ask the L2 for them now, while layers 1-2 of this tile run.
+                if (pair + pair_stride < n_pairs && elect_one()) {
+                    const int m1 = ((pair + pair_stride) * TF_CLUSTER + (int)crank) * TF_BM;
+                    for (int kb = 0; kb < kTfNKB0; kb++) tf_tma_prefetch_l2(&maps.a, kb * TF_BK, m1);
                 }
             }
 #ifdef MM_TF_PROFILE
