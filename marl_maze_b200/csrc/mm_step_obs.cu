@@ -96,7 +96,8 @@ struct LaneCtx {
     bool mk;          // this agent marked its (pre-move) cell this step
     int px, py;       // pre-move cell
     bool want_reset;
-    bool have_d2e;    // phase 1 put this agent's dir-to-exit row in flight (only agents that already know the exit need it for certain)
+    bool have_d2e;    // phase 1 put this agent's dir-to-exit row in flight (an agent that knows the exit and moved ALONG its route)
+    bool d2e_known;   // phase 1 already knows the dir-to-exit of the new cell without reading the field (see k2_phase1)
     float* stage;     // this warp's 32 x 65-float staging area in shared memory (doubles as the landing zone of the window rows)
     uint64_t* bar;    // this warp's mbarrier (MM_K2_BULK: completion of the window bulk copies)
 };
@@ -122,6 +123,12 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
     bool mk = false;      // this agent marked its (pre-move) cell this step
     int px = 0, py = 0;   // pre-move cell
     bool want_reset = false;
+    // dir-to-exit of the cell the agent ends this step on, for an agent that knows the exit (R2 in DESIGN.md: the exit route is the tree path).  It needs
+    // the field only when it moved ALONG its route (the next cell's direction is new information).  Stepping off the route -- any other move, also away
+    // from the exit cell itself -- leads to a cell whose path to the exit goes straight back: direction = the reverse of the move.  Not moving keeps the
+    // stored direction.  (Every agent that knew the exit used to fetch a 32-byte sector of the field every step: 64 MB of DRAM reads per 1 Mi-maze launch
+    // in reset steady state, where most agents know the exit.)
+    bool d2e_fetch = false, d2e_known = valid && me.ke;
 
     if (kResetOnly) {
         want_reset = valid && (p.reset_mask == nullptr || p.reset_mask[e] != 0);
@@ -157,7 +164,10 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
             } else {
                 if (me.ke) {  // exit_route pop/push == walking along / against the tree path to the exit (maze.py:148-154)
                     const bool at_end_pre = (me.x == ex && me.y == ey);
-                    me.exit_len += (!at_end_pre && nd == me.d2e) ? -1 : 1;
+                    const bool along = !at_end_pre && nd == me.d2e;
+                    me.exit_len += along ? -1 : 1;
+                    if (along) { d2e_fetch = true; d2e_known = false; }
+                    else me.d2e = (nd + 2) & 3;
                 }
                 me.x = nx; me.y = ny; me.dir = nd;
                 cand_key = keyp && nx == kx && ny == ky;
@@ -207,11 +217,12 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
             // the dir-to-exit row is consumed only by an agent that knows the exit at the END of this step; one that does not know it yet
             // and learns it during the observation (a sighting, a shared route) fetches the row then -- rare -- instead of every
             // agent fetching a 32-byte sector every step
-            if (me.ke) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + me.y) : "memory");
+            if (d2e_fetch) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s1), "l"(p.pool_d2e + (size_t)pidx * p.smax + me.y) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    c.have_d2e = !kResetOnly && valid && me.ke;
+    c.have_d2e = !kResetOnly && valid && d2e_fetch;
+    c.d2e_known = !kResetOnly && d2e_known;
     c.me = me; c.t = t; c.keyp = keyp; c.err = err; c.pidx = pidx; c.W = W; c.Hh = Hh; c.ex = ex; c.ey = ey; c.kx = kx; c.ky = ky;
     c.reward = reward; c.done = done; c.mk = mk; c.px = px; c.py = py; c.want_reset = want_reset;
 }
@@ -414,8 +425,9 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
         }
 
         // dir-to-exit of the current cell, for whoever knows the exit now (own sighting, or a route shared by the other agent)
-        if (act && me.ke && !(pass == 0 && !kResetOnly && c.have_d2e)) dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
-        const int d2e_here = (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
+        const bool d2e_from_phase1 = pass == 0 && !kResetOnly && c.d2e_known;   // stored / derived in phase 1: no field access at all
+        if (act && me.ke && !d2e_from_phase1 && !(pass == 0 && !kResetOnly && c.have_d2e)) dd = __ldg(&p.pool_d2e[(size_t)pidx * p.smax + y]);
+        const int d2e_here = d2e_from_phase1 ? me.d2e : (int)(((dd.y >> (x + kPad)) & 1ull) << 1 | ((dd.x >> (x + kPad)) & 1ull));
         if (act) me.d2e = d2e_here;
         // next_move_to_exit (maze_agent.py:113-118): exit_route[-1] == dir-to-exit of the current cell
         const uint32_t nm = (s_ke && !at_end) ? (1u << ((d2e_here - f) & 3)) : 0xfu;
