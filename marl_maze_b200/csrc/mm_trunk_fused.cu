@@ -57,7 +57,13 @@ static_assert((2 * TF_WSTAGES + 2 * TF_ASLOTS + 2 * TF_OPS + 3) * 8 + 4 <= 512, 
 constexpr int TF_BIAS_FLOATS = 3 * TF_N + 8;                      // three trunk biases + the six head biases
 constexpr uint32_t TF_SMEM_BYTES = TF_BIAS_OFF + TF_BIAS_FLOATS * 4 + 1024 /*alignment slack*/;
 static_assert(TF_SMEM_BYTES <= 232448, "one CTA per SM");
-constexpr int TF_EPI_WARPS = 8, TF_THREADS = 64 + 32 * TF_EPI_WARPS + 32;   // + the activation-tile producer warp
+// splitter / epilogue warps: 2 or 4 per TMEM lane quarter.  The three epilogues are serial with the MMAs (the next layer needs the whole operand and reuses
+// the accumulator columns): with 8 warps an epilogue took ~3.1 kclk of ~48 kclk per tile, bound by its own latencies (two warps per scheduler)
+#ifndef MM_TF_EPI_WARPS
+#define MM_TF_EPI_WARPS 8
+#endif
+constexpr int TF_EPI_WARPS = MM_TF_EPI_WARPS, TF_WPQ = TF_EPI_WARPS / 4, TF_THREADS = 64 + 32 * TF_EPI_WARPS + 32;   // + the activation-tile producer warp
+static_assert(TF_EPI_WARPS == 8 || TF_EPI_WARPS == 16, "two or four epilogue warps per lane quarter");
 // TMEM: D columns 0..271 | hi plane of the activations 272..407 (136 columns = 272 fp16 k-elements) | layer-0 operand ring 408 + 32 * stage
 constexpr uint32_t TF_TMEM_COLS = 512, TF_TMEM_H_COL = 272, TF_TMEM_A_COL = 408;
 static_assert(TF_TMEM_A_COL + 32 * TF_OPS <= TF_TMEM_COLS, "operand ring fits");
@@ -80,6 +86,9 @@ __device__ __forceinline__ void tf_tmem_st8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
                  "r"(v[6]), "r"(v[7])
                  : "memory");
+}
+__device__ __forceinline__ void tf_tmem_st4(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 __device__ __forceinline__ void tf_tmem_ld32_nowait(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -375,21 +384,22 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                 const int sa = ait % TF_ASLOTS, os = oit % TF_OPS;
                 const float4* rowp = reinterpret_cast<const float4*>(hlo + sa * TF_A_BYTES + arow * 128);
                 TF_PROF_WAIT(0, mbar_wait(&a_full[sa], (ait / TF_ASLOTS) & 1));
-                float4 av[4];
+                constexpr int kC = 8 / TF_WPQ;   // float4 chunks of the 32-column block per warp of the quarter
+                float4 av[kC];
 #pragma unroll
-                for (int c = 0; c < 4; c++) av[c] = rowp[(c + 4 * whalf) ^ (arow & 7)];
+                for (int c = 0; c < kC; c++) av[c] = rowp[(c + kC * whalf) ^ (arow & 7)];
                 tf_arrive(&a_free[sa]);
-                uint32_t hi[8], lo[8];
+                uint32_t hi[2 * kC], lo[2 * kC];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < kC; c++) {
                     tf_split2(av[c].x, av[c].y, hi[2 * c], lo[2 * c]);
                     tf_split2(av[c].z, av[c].w, hi[2 * c + 1], lo[2 * c + 1]);
                 }
                 TF_PROF_WAIT(1, mbar_wait(&op_free[os], ((oit / TF_OPS) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = t_lane + TF_TMEM_A_COL + (uint32_t)(os * 32);
-                tf_tmem_st8(ta + 8 * whalf, hi);
-                tf_tmem_st8(ta + 16 + 8 * whalf, lo);
+                if (TF_WPQ == 2) { tf_tmem_st8(ta + 8 * whalf, hi); tf_tmem_st8(ta + 16 + 8 * whalf, lo); }
+                else { tf_tmem_st4(ta + 4 * whalf, hi); tf_tmem_st4(ta + 16 + 4 * whalf, lo); }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 tf_arrive(&op_full[os]);
@@ -401,12 +411,13 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const float scale = __ldg(args.acc_scale[layer]);
                 const float* sb = s_bias + layer * TF_N;
-                const int c_lo = whalf ? 5 : 0, n_c = whalf ? 4 : 5;
+                // the nine 32-column chunks over the quarter's warps: 5 + 4, or 3 + 2 + 2 + 2
+                const int c_lo = TF_WPQ == 2 ? (whalf ? 5 : 0) : (whalf ? 1 + 2 * whalf : 0), n_c = TF_WPQ == 2 ? (whalf ? 4 : 5) : (whalf ? 2 : 3);
                 uint32_t v0[32], v1[32];
                 tf_tmem_ld32_nowait(t_lane + (uint32_t)(c_lo * 32), v0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 5; i++) {
+                for (int i = 0; i < (TF_WPQ == 2 ? 5 : 3); i++) {
                     if (i < n_c) {
                         uint32_t* cur = (i & 1) ? v1 : v0;
                         uint32_t* nxt = (i & 1) ? v0 : v1;
