@@ -180,16 +180,50 @@ class PPO:
     def get_action(self, obs, action_mask):
         """One agent's action from ONE observation (PPO.py:170-186) -- the reference's single-env interface, kept for
         Agent.get_action / viewers.  The batched rollout does not come through here (it uses the fused kernel)."""
+        if self.device.type == "cuda":
+            return self._get_action_kernel(obs, action_mask)
         with torch.no_grad():
             move_logits, mark_logits = self.actor(obs)
-            mask = torch.as_tensor(action_mask, dtype=torch.bool, device=self.device).reshape(-1)
-            dist = torch.distributions.Categorical(logits=torch.where(mask[:5], move_logits, torch.tensor(-float("inf"), device=self.device)))
-            move = dist.sample()
-            p = torch.sigmoid(mark_logits) if bool(mask[5]) else torch.zeros(1, 1, device=self.device)
-            mark = torch.bernoulli(p)
-            p = p if mark == 1 else 1 - p
-            log_prob = dist.log_prob(move) + torch.log(p)
+            return self._sample_action(move_logits, mark_logits, action_mask)
+
+    @staticmethod
+    def _sample_action(move_logits, mark_logits, action_mask):
+        """The reference's draw (PPO.py:175-186) from the six logits of one observation: masked categorical move, Bernoulli mark (probability 0 when the
+        mark action is masked), joint log-prob.  Logits [1,5] / [1,1] on any device; the generator of that device decides."""
+        dev = move_logits.device
+        mask = torch.as_tensor(action_mask, dtype=torch.bool, device=dev).reshape(-1)
+        dist = torch.distributions.Categorical(logits=torch.where(mask[:5], move_logits, torch.tensor(-float("inf"), device=dev)))
+        move = dist.sample()
+        p = torch.sigmoid(mark_logits) if bool(mask[5]) else torch.zeros(1, 1, device=dev)
+        mark = torch.bernoulli(p)
+        p = p if mark == 1 else 1 - p
+        log_prob = dist.log_prob(move) + torch.log(p)
         return [int(move.item()), float(mark.item())], log_prob
+
+    def _get_action_kernel(self, obs, action_mask):
+        """get_action on the GPU without the ~60 small launches of the autograd modules: the six logits of the one observation come from the K4 kernels
+        (mm_policy_forward at one env, this agent's row; weights re-packed only when the actor changed), travel to a pinned host buffer, and the
+        draw is the reference's own sequence of torch calls (Categorical.sample, bernoulli: PPO.py:175-184) on the host -- as in the reference,
+        which runs on the CPU, the global torch CPU generator decides the action."""
+        a1 = getattr(self, "_act1", None)
+        if a1 is None:
+            run = PolicyRunner(self.actor, self.critic, 1, self.device, seed=self.seed)
+            a1 = self._act1 = dict(run=run, key=None, h_obs=torch.zeros(1, 2, 65, pin_memory=True), d_obs=torch.zeros(1, 2, 65, device=self.device),
+                                   d_masks=torch.ones(1, 2, 6, dtype=torch.uint8, device=self.device), d_logits=torch.zeros(1, 2, 6, device=self.device),
+                                   h_logits=torch.zeros(1, 2, 6, pin_memory=True), d_act=torch.zeros(1, 2, 2, dtype=torch.uint8, device=self.device),
+                                   d_logp=torch.zeros(1, device=self.device))
+            a1["h_obs_np"] = a1["h_obs"].numpy()
+        key = (getattr(self, "_weights_version", 0),) + tuple(p._version for p in self.actor.parameters())
+        if a1["key"] != key:     # optimiser steps (eager: tensor versions; graph replays: _weights_version), load_state_dict, load_parameters
+            a1["run"].refresh(); a1["key"] = key
+        a1["h_obs_np"][0, 0, :] = obs.detach().cpu().numpy().reshape(-1) if torch.is_tensor(obs) else obs
+        a1["d_obs"].copy_(a1["h_obs"], non_blocking=True)
+        a1["run"].forward(a1["d_obs"], a1["d_masks"], actions_out=a1["d_act"], logp=a1["d_logp"], logits=a1["d_logits"], want_value=False)
+        a1["h_logits"].copy_(a1["d_logits"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        with torch.no_grad():
+            lg = a1["h_logits"][0, 0].clone()
+            return self._sample_action(lg[:5].view(1, 5), lg[5:6].view(1, 1), action_mask)
 
     # ------------------------------------------------------------------ update-side helpers (autograd)
     def get_log_probs(self, i, batch_obs, batch_actions, batch_masks):
@@ -301,6 +335,7 @@ class PPO:
             return self._update(batch)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+            self._weights_version = getattr(self, "_weights_version", 0) + 1   # graph replays change the parameters without touching tensor versions
 
     # minibatches of at most this many env-steps replay their optimiser step as a CUDA graph (launch-bound regime: at the reference's own
     # configuration an optimiser step is ~150 small launches, 7.5 ms eager against < 1 ms of GPU work); larger ones are compute-bound

@@ -10,6 +10,7 @@
 //                joint log-prob per env (sum over the two agents, PPO.py:118,121)
 //   k_critic   : centralised critic [E,130] -> 64 -> 64 -> 1
 // Weights arrive as ONE flat fp32 buffer laid out by mm_policy_offsets() (host packs it from the state_dict).
+#include <cuda_fp16.h>
 #include "mm_env.cuh"
 #include "mm_policy_heads.cuh"
 
@@ -594,52 +595,273 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ h, cons
 }
 
 // ------------------------------------------------------------------------------------------------ critic
-// 130 -> 64 -> 64 -> 1.  One warp handles 4 envs at a time; lane j owns hidden neurons j and j+32, weights are read from the
-// TRANSPOSED copies ([k][neuron]: a warp reads 2 x 128 contiguous bytes per k, L1-resident), inputs are broadcast from shared.
-constexpr int kCrEnvs = 4;
-__global__ void __launch_bounds__(128) k_critic(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ value, int E) {
-    const PolicyOffsets o = policy_offsets();
-    __shared__ float s_in[4][kCrEnvs][132], s_h[4][kCrEnvs][kCH];
-    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e0 = (blockIdx.x * 4 + wl) * kCrEnvs;
-    if (e0 >= E) return;
-    const int ne = min(kCrEnvs, E - e0);
-    for (int i = lane; i < kCrEnvs * 130; i += 32) { const int e = i / 130, k = i - e * 130; s_in[wl][e][k] = e < ne ? obs[(size_t)(e0 + e) * 130 + k] : 0.f; }
-    __syncwarp();
-    float a0[kCrEnvs], a1[kCrEnvs];
+// 130 -> 64 -> 64 -> 1 (networks.py:84-104).
+// Third generation: both hidden layers on the warp-level tensor path (mma.sync m16n8k16, fp16 operands, fp32 accumulation) with the same
+// error-compensated split as the trunk (x ~ hi + lo: hi.hi + lo.hi + hi.lo, ~2^-22 relative per product).  Why not SIMT: a warp-wide 16-byte shared-memory
+// read returns 512 bytes through a 128-byte/clock pipe, so any register tiling that fits (lane = neuron pair x 4 envs: 76 us per 65 536 envs; lane = env x
+// 64 neurons from broadcast weight quads: 68 us, kept under -DMM_CRITIC_SIMT) is bound by that pipe at ~1/3 of the FMA rate; on the tensor path a weight
+// fragment (16 bytes per lane) feeds 6 HMMAs.
+// One warp = 32 environments (two m16 tiles).  Layer 0's A fragments are read straight from the fp32 observation rows (float2 per lane: 130 is even, a
+// 32-byte sector serves the four lanes of a row group), scaled by 2^8 and split in registers; the accumulator layout of an m16n8 tile IS the A layout of
+// the next k16 step, so layer 1's operand (relu(acc + b), scaled by 2^4) never leaves the registers; the 64 -> 1 output layer is an fp32 dot product on the
+// accumulator fragments, reduced over the lane quad.  Weights: every block builds the B fragments (hi | lo fp16 of 2^e W, e from the layer's largest
+// |w|) in its shared memory once -- 52 KB, persistent blocks of 16 warps, one per SM.  Domain: |obs| < 255, hidden activations < 4094 (fp16 range after the
+// scaling); the reference's observations lie in [-1, 2].
+#ifdef MM_CRITIC_SIMT
+constexpr int kCrIn = 130, kCrWarps = 8, kCrPitch = 131;
+constexpr int kCrWFloats = kCrIn * kCH + kCH * kCH + 3 * kCH + 4;            // W0t, W1t, b0, b1, w2, b2 (+ padding)
+constexpr int kCrSmemBytes = (kCrWFloats + kCrWarps * 32 * kCrPitch) * 4;
+
+// acc[n] = b[n] + sum_k x[k] W[k][n], k ascending; x[k] read from the lane's tile row, W as 16-byte broadcast quads
+template <int K>
+__device__ __forceinline__ void critic_layer(float (&acc)[kCH], const float* __restrict__ xrow, const float4* __restrict__ w4, const float* __restrict__ b) {
 #pragma unroll
-    for (int e = 0; e < kCrEnvs; e++) { a0[e] = wts[o.c0_b + lane]; a1[e] = wts[o.c0_b + lane + 32]; }
-    const float* w0 = wts + o.c0_wt;
+    for (int n = 0; n < kCH; n++) acc[n] = b[n];
 #pragma unroll 2
-    for (int k = 0; k < 130; k++) {
-        const float wa = w0[k * kCH + lane], wb = w0[k * kCH + lane + 32];
+    for (int k = 0; k < K; k++) {
+        const float x = xrow[k];
 #pragma unroll
-        for (int e = 0; e < kCrEnvs; e++) { const float x = s_in[wl][e][k]; a0[e] = fmaf(x, wa, a0[e]); a1[e] = fmaf(x, wb, a1[e]); }
-    }
-#pragma unroll
-    for (int e = 0; e < kCrEnvs; e++) { s_h[wl][e][lane] = fmaxf(a0[e], 0.f); s_h[wl][e][lane + 32] = fmaxf(a1[e], 0.f); }
-    __syncwarp();
-#pragma unroll
-    for (int e = 0; e < kCrEnvs; e++) { a0[e] = wts[o.c1_b + lane]; a1[e] = wts[o.c1_b + lane + 32]; }
-    const float* w1 = wts + o.c1_wt;
-#pragma unroll 4
-    for (int k = 0; k < kCH; k++) {
-        const float wa = w1[k * kCH + lane], wb = w1[k * kCH + lane + 32];
-#pragma unroll
-        for (int e = 0; e < kCrEnvs; e++) { const float x = s_h[wl][e][k]; a0[e] = fmaf(x, wa, a0[e]); a1[e] = fmaf(x, wb, a1[e]); }
-    }
-    const float v0 = wts[o.c2_w + lane], v1 = wts[o.c2_w + lane + 32], vb = wts[o.c2_b];
-#pragma unroll
-    for (int e = 0; e < kCrEnvs; e++) {
-        float part = fmaf(fmaxf(a0[e], 0.f), v0, fmaxf(a1[e], 0.f) * v1);
-#pragma unroll
-        for (int sft = 16; sft; sft >>= 1) part += __shfl_xor_sync(kFull, part, sft);
-        if (lane == 0 && e < ne) value[e0 + e] = part + vb;
+        for (int j = 0; j < kCH / 4; j++) {
+            const float4 w = w4[k * (kCH / 4) + j];
+            acc[4 * j] = fmaf(x, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+        }
     }
 }
 
+__global__ void __launch_bounds__(kCrWarps * 32, 1) k_critic(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ value, int E) {
+    extern __shared__ __align__(16) float cr_smem[];
+    const PolicyOffsets o = policy_offsets();
+    float* s_w0 = cr_smem;                       // [130][64]
+    float* s_w1 = s_w0 + kCrIn * kCH;            // [64][64]
+    float* s_b0 = s_w1 + kCH * kCH;
+    float* s_b1 = s_b0 + kCH;
+    float* s_w2 = s_b1 + kCH;
+    float* s_b2 = s_w2 + kCH;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = cr_smem + kCrWFloats + w * 32 * kCrPitch;
+    for (int i = threadIdx.x; i < kCrIn * kCH / 4; i += blockDim.x) reinterpret_cast<float4*>(s_w0)[i] = reinterpret_cast<const float4*>(wts + o.c0_wt)[i];
+    for (int i = threadIdx.x; i < kCH * kCH / 4; i += blockDim.x) reinterpret_cast<float4*>(s_w1)[i] = reinterpret_cast<const float4*>(wts + o.c1_wt)[i];
+    if (threadIdx.x < kCH) { s_b0[threadIdx.x] = wts[o.c0_b + threadIdx.x]; s_b1[threadIdx.x] = wts[o.c1_b + threadIdx.x]; s_w2[threadIdx.x] = wts[o.c2_w + threadIdx.x]; }
+    if (threadIdx.x == 0) s_b2[0] = wts[o.c2_b];
+    __syncthreads();
+    const int ntiles = (E + 31) >> 5;
+    // tile t belongs to block t % gridDim.x; inside the block the warps take the block's tiles in turn
+#pragma unroll 1
+    for (int t = blockIdx.x + w * gridDim.x; t < ntiles; t += kCrWarps * gridDim.x) {
+        const int e0 = t << 5;
+        const int ne = min(32, E - e0);
+        // stage [ne][130] contiguous floats as [32][131]: float2 granules never straddle an environment (130 is even)
+        const float2* src = reinterpret_cast<const float2*>(obs + (size_t)e0 * kCrIn);
+        __syncwarp();
+#pragma unroll 5
+        for (int i = lane; i < 32 * (kCrIn / 2); i += 32) {
+            const int e = i / (kCrIn / 2), k2 = i - e * (kCrIn / 2);
+            const float2 v = e < ne ? __ldg(src + i) : make_float2(0.f, 0.f);
+            tile[e * kCrPitch + 2 * k2] = v.x; tile[e * kCrPitch + 2 * k2 + 1] = v.y;
+        }
+        __syncwarp();
+        float* xrow = tile + lane * kCrPitch;
+        float acc[kCH];
+        critic_layer<kCrIn>(acc, xrow, reinterpret_cast<const float4*>(s_w0), s_b0);
+#pragma unroll
+        for (int n = 0; n < kCH; n++) xrow[n] = fmaxf(acc[n], 0.f);   // the lane's own row: no other lane reads it
+        critic_layer<kCH>(acc, xrow, reinterpret_cast<const float4*>(s_w1), s_b1);
+        float v = s_b2[0];
+#pragma unroll
+        for (int n = 0; n < kCH; n++) v = fmaf(fmaxf(acc[n], 0.f), s_w2[n], v);
+        if (lane < ne) value[e0 + lane] = v;
+    }
+}
+#else
+#ifndef MM_CRITIC_WARPS
+#define MM_CRITIC_WARPS 16
+#endif
+constexpr int kCrIn = 130, kCrWarps = MM_CRITIC_WARPS;
+constexpr int kCrKS0 = (kCrIn + 15) / 16, kCrKS1 = kCH / 16, kCrNT = kCH / 8;      // 9 and 4 k16 steps, 8 n8 tiles
+constexpr float kCrXScale = 256.f, kCrHScale = 16.f;
+constexpr int kCrSmemBytes = (kCrKS0 + kCrKS1) * kCrNT * 32 * 16 + (3 * kCH + 4 + 2 * kCrWarps) * 4;
+
+__device__ __forceinline__ void cr_split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h2 = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ void cr_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// largest |w| of a weight matrix -> the power of two that puts it in [256, 512) (exact scaling; hi and lo stay normal fp16 numbers).
+// (Staging the fp32 weights in shared memory first was measured: no faster at 65 536 envs -- the prologue is not bound by these L2 reads -- and
+// 6 % slower at 1 Mi envs, where the 49 KB it takes from L1 cost observation-row hits.)
+__device__ __forceinline__ float cr_block_scale(const float* __restrict__ w, int n, float* s_red) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, sft));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) m = fmaxf(m, s_red[i]);
+    int ex;
+    frexpf(fmaxf(m, 1e-30f), &ex);                 // m = f 2^ex, f in [0.5, 1)
+    const int e = max(-14, min(24, 9 - ex));        // m 2^e in [256, 512)
+    return exp2f((float)e);
+}
+// B fragments of W [64][K] (row = output neuron) for the k16 steps of one layer: per (step, n8 tile, lane)
+// {hi b0, hi b1, lo b0, lo b1}
+__device__ __forceinline__ void cr_build_frags(uint4* dst, const float* __restrict__ w, int K, int ksteps, float scale) {
+    for (int i = threadIdx.x; i < ksteps * kCrNT * 32; i += blockDim.x) {
+        const int lane = i & 31, nt = (i >> 5) % kCrNT, ks = (i >> 5) / kCrNT;
+        const int n = 8 * nt + (lane >> 2), k0 = 16 * ks + 2 * (lane & 3);
+        const float* r = w + n * K;
+        const float w0 = k0 < K ? r[k0] * scale : 0.f, w1 = k0 + 1 < K ? r[k0 + 1] * scale : 0.f;
+        const float w8 = k0 + 8 < K ? r[k0 + 8] * scale : 0.f, w9 = k0 + 9 < K ? r[k0 + 9] * scale : 0.f;
+        uint4 f;
+        cr_split2(w0, w1, f.x, f.z); cr_split2(w8, w9, f.y, f.w);
+        dst[i] = f;
+    }
+}
+
+__global__ void __launch_bounds__(kCrWarps * 32, 1) k_critic(const float* __restrict__ obs, const float* __restrict__ wts, float* __restrict__ value, int E) {
+    extern __shared__ __align__(16) uint8_t cr_smem[];
+    const PolicyOffsets o = policy_offsets();
+    uint4* s_f0 = reinterpret_cast<uint4*>(cr_smem);                    // [9][8][32]
+    uint4* s_f1 = s_f0 + kCrKS0 * kCrNT * 32;                           // [4][8][32]
+    float* s_b0 = reinterpret_cast<float*>(s_f1 + kCrKS1 * kCrNT * 32);
+    float* s_b1 = s_b0 + kCH;
+    float* s_w2 = s_b1 + kCH;
+    float* s_misc = s_w2 + kCH;                                          // b2, 1 / (x scale * w0 scale), 1 / (h scale * w1 scale)
+    float* s_red = s_misc + 4;                                           // [2][warps]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    {
+        const float sc0 = cr_block_scale(wts + o.c0_w, kCH * kCrIn, s_red);
+        const float sc1 = cr_block_scale(wts + o.c1_w, kCH * kCH, s_red + kCrWarps);
+        cr_build_frags(s_f0, wts + o.c0_w, kCrIn, kCrKS0, sc0);
+        cr_build_frags(s_f1, wts + o.c1_w, kCH, kCrKS1, sc1);
+        if (threadIdx.x < kCH) { s_b0[threadIdx.x] = wts[o.c0_b + threadIdx.x]; s_b1[threadIdx.x] = wts[o.c1_b + threadIdx.x]; s_w2[threadIdx.x] = wts[o.c2_w + threadIdx.x]; }
+        if (threadIdx.x == 0) { s_misc[0] = wts[o.c2_b]; s_misc[1] = 1.f / (kCrXScale * sc0); s_misc[2] = 1.f / (kCrHScale * sc1); }
+    }
+    __syncthreads();
+    const float inv0 = s_misc[1], inv1 = s_misc[2], b2 = s_misc[0];
+    const int ntiles = (E + 31) >> 5;
+#pragma unroll 1
+    for (int t = blockIdx.x + w * gridDim.x; t < ntiles; t += kCrWarps * gridDim.x) {
+        const int e0 = t << 5;
+        float acc[2][kCrNT][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < kCrNT; nt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[mt][nt][i] = 0.f;
+        // ---------------- layer 0: [32 x 130] x [130 x 64]; the next k16 step's observation columns are in flight while this step's HMMAs issue
+        const float* xbase = obs + (size_t)(e0 + g) * kCrIn + 2 * t4;   // row e0 + 16 mt + 8 rr + g = a compile-time offset from this one
+        float2 xn[2][2][2];   // [m tile][column half][row half]
+        auto fetch = [&](int ks) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++) {
+                        const int col = 16 * ks + 8 * hf + 2 * t4;
+                        xn[mt][hf][rr] = (col < kCrIn && e0 + g + 16 * mt + 8 * rr < E)
+                                             ? __ldg(reinterpret_cast<const float2*>(xbase + (16 * mt + 8 * rr) * kCrIn + 16 * ks + 8 * hf)) : make_float2(0.f, 0.f);
+                    }
+        };
+        fetch(0);
+#pragma unroll 1
+        for (int ks = 0; ks < kCrKS0; ks++) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++)
+                        cr_split2(xn[mt][hf][rr].x * kCrXScale, xn[mt][hf][rr].y * kCrXScale, ah[mt][2 * hf + rr], al[mt][2 * hf + rr]);
+            if (ks + 1 < kCrKS0) fetch(ks + 1);
+#pragma unroll
+            for (int nt = 0; nt < kCrNT; nt++) {
+                const uint4 b = s_f0[(ks * kCrNT + nt) * 32 + lane];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    cr_mma(acc[mt][nt], al[mt], b.x, b.y);
+                    cr_mma(acc[mt][nt], ah[mt], b.z, b.w);
+                    cr_mma(acc[mt][nt], ah[mt], b.x, b.y);
+                }
+            }
+        }
+        // ---------------- layers 1 and 2, one m16 tile at a time: relu(acc + b0) becomes the A fragments in registers
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            asm volatile("" ::: "memory");   // the second tile re-reads the weight fragments instead of keeping all 128 words of them live across both
+            uint32_t hh[kCrKS1][4], hl[kCrKS1][4];
+#pragma unroll
+            for (int nt = 0; nt < kCrNT; nt++) {
+                const float2 bb = *reinterpret_cast<const float2*>(s_b0 + 8 * nt + 2 * t4);
+                const float h0 = fmaxf(fmaf(acc[mt][nt][0], inv0, bb.x), 0.f) * kCrHScale, h1 = fmaxf(fmaf(acc[mt][nt][1], inv0, bb.y), 0.f) * kCrHScale;
+                const float h2 = fmaxf(fmaf(acc[mt][nt][2], inv0, bb.x), 0.f) * kCrHScale, h3 = fmaxf(fmaf(acc[mt][nt][3], inv0, bb.y), 0.f) * kCrHScale;
+                cr_split2(h0, h1, hh[nt >> 1][2 * (nt & 1)], hl[nt >> 1][2 * (nt & 1)]);            // row g
+                cr_split2(h2, h3, hh[nt >> 1][2 * (nt & 1) + 1], hl[nt >> 1][2 * (nt & 1) + 1]);    // row g + 8
+            }
+            float a1[kCrNT][4];
+#pragma unroll
+            for (int nt = 0; nt < kCrNT; nt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) a1[nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < kCrKS1; ks++) {
+                asm volatile("" ::: "memory");   // at most one k step's fragments in flight (the compiler otherwise hoists all 32 loads and spills the accumulators)
+#pragma unroll
+                for (int nt = 0; nt < kCrNT; nt++) {
+                    const uint4 b = s_f1[(ks * kCrNT + nt) * 32 + lane];
+                    cr_mma(a1[nt], hl[ks], b.x, b.y);
+                    cr_mma(a1[nt], hh[ks], b.z, b.w);
+                    cr_mma(a1[nt], hh[ks], b.x, b.y);
+                }
+            }
+            float v0 = 0.f, v1 = 0.f;   // rows g and g + 8
+#pragma unroll
+            for (int nt = 0; nt < kCrNT; nt++) {
+                const float2 bb = *reinterpret_cast<const float2*>(s_b1 + 8 * nt + 2 * t4);
+                const float2 ww = *reinterpret_cast<const float2*>(s_w2 + 8 * nt + 2 * t4);
+                v0 = fmaf(fmaxf(fmaf(a1[nt][0], inv1, bb.x), 0.f), ww.x, v0); v0 = fmaf(fmaxf(fmaf(a1[nt][1], inv1, bb.y), 0.f), ww.y, v0);
+                v1 = fmaf(fmaxf(fmaf(a1[nt][2], inv1, bb.x), 0.f), ww.x, v1); v1 = fmaf(fmaxf(fmaf(a1[nt][3], inv1, bb.y), 0.f), ww.y, v1);
+            }
+            v0 += __shfl_xor_sync(kFull, v0, 1); v0 += __shfl_xor_sync(kFull, v0, 2);
+            v1 += __shfl_xor_sync(kFull, v1, 1); v1 += __shfl_xor_sync(kFull, v1, 2);
+            if (t4 == 0) {
+                const int e = e0 + 16 * mt + g;
+                if (e < E) value[e] = v0 + b2;
+                if (e + 8 < E) value[e + 8] = v1 + b2;
+            }
+        }
+    }
+}
+#endif
+
 cudaError_t launch_critic(const float* wts, const float* obs, int E, float* value, cudaStream_t stream) {
-    k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
+    static PerDeviceFlag configured;
+    static int n_sm[kMaxDevices] = {};
+    const int dslot = current_device_slot();
+    if (configured.first_time()) {
+        cudaError_t e = cudaFuncSetAttribute(k_critic, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrSmemBytes);
+        int dev = 0;
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm[dslot], cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) { configured.retract(); return e; }
+    }
+    const int ntiles = (E + 31) / 32;
+    const int blocks = (ntiles + kCrWarps - 1) / kCrWarps;
+    k_critic<<<blocks < n_sm[dslot] ? blocks : n_sm[dslot], kCrWarps * 32, kCrSmemBytes, stream>>>(obs, wts, value, E);
     return cudaGetLastError();
 }
 
@@ -696,7 +918,7 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
         cudaError_t e = cudaEventRecord(ev_fork, stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev_fork, 0);
         if (e != cudaSuccess) return e;
-        k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, side>>>(obs, wts, value, E);
+        if ((e = launch_critic(wts, obs, E, value, side)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
     }
     { cudaError_t e = launch_tokens_any(wts, obs, R, x0, stream); if (e != cudaSuccess) return e; }
@@ -728,7 +950,7 @@ cudaError_t launch_policy(const float* wts, const float* obs, const uint8_t* mas
     if (overlap) {
         cudaError_t e = cudaStreamWaitEvent(stream, ev_join, 0);
         if (e != cudaSuccess) return e;
-    } else if (value) k_critic<<<(E + 4 * kCrEnvs - 1) / (4 * kCrEnvs), 128, 0, stream>>>(obs, wts, value, E);
+    } else if (value) { cudaError_t e = launch_critic(wts, obs, E, value, stream); if (e != cudaSuccess) return e; }
     return cudaGetLastError();
 }
 

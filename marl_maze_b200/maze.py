@@ -123,20 +123,46 @@ class Maze:
     def step(self, action, auto_reset: Optional[bool] = None, **out):
         eng = self._ensure_engine()
         if self.num_envs == 1 and not torch.is_tensor(action):
-            a = torch.tensor([[int(action[0][0]), int(action[0][1])], [int(action[1][0]), int(action[1][1])]], dtype=torch.uint8).view(1, 2, 2)
-            action = a.to(self.device)
+            io = self._single_io()   # the reference's list interface: the four action bytes travel through one pinned buffer, no allocation per step
+            h = io["h_act_np"]
+            h[0], h[1], h[2], h[3] = int(action[0][0]), int(action[0][1]), int(action[1][0]), int(action[1][1])
+            io["d_act"].copy_(io["h_act"], non_blocking=True)
+            action = io["d_act"]
         elif torch.is_tensor(action) and (action.dtype != torch.uint8 or not action.is_contiguous() or action.device.type != self.device.type):
             action = action.to(device=self.device, dtype=torch.uint8).reshape(self.num_envs, 2, 2).contiguous()  # e.g. the float [E,2,2] of PPO.get_batch
         auto = (self.num_envs > 1) if auto_reset is None else auto_reset
         self._obs, self._masks, r, d = eng.step(action, auto_reset=auto, **out)
         if self.num_envs == 1:
-            o, m = self._emit(self._obs, self._masks)
-            return o, m, float(r.item()), bool(d.item())
+            o, m = self._emit(self._obs, self._masks, r, d)
+            io = self._io
+            return o, m, float(io["h_rew_np"][0]), bool(io["h_done_np"][0])
         return self._obs, self._masks, r, d
 
-    def _emit(self, obs, masks):
+    def _single_io(self):
+        """Pinned host mirrors of ONE environment's step inputs / outputs (num_envs == 1: the reference's python-list interface).  A step is then one
+        small host-to-device copy, the kernel, four small device-to-host copies and ONE stream synchronisation."""
+        io = getattr(self, "_io", None)
+        if io is None:
+            pin = self.device.type == "cuda"
+            mk = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, pin_memory=pin)
+            io = dict(h_act=mk(1, 2, 2, dtype=torch.uint8), h_obs=mk(2, 65, dtype=torch.float32), h_masks=mk(2, 6, dtype=torch.uint8),
+                      h_rew=mk(1, dtype=torch.float32), h_done=mk(1, dtype=torch.uint8))
+            io["d_act"] = torch.zeros(1, 2, 2, dtype=torch.uint8, device=self.device)
+            for k in ("act", "obs", "masks", "rew", "done"):
+                io[f"h_{k}_np"] = io[f"h_{k}"].numpy()
+            io["h_act_np"] = io["h_act_np"].reshape(-1)   # a view: the four action bytes
+            self._io = io
+        return io
+
+    def _emit(self, obs, masks, reward=None, done=None):
         if self.num_envs == 1:
-            return obs[0].tolist(), [[bool(v) for v in row] for row in masks[0].tolist()]
+            io = self._single_io()
+            io["h_obs"].copy_(obs[0], non_blocking=True); io["h_masks"].copy_(masks[0], non_blocking=True)
+            if reward is not None:
+                io["h_rew"].copy_(reward.reshape(1), non_blocking=True); io["h_done"].copy_(done.reshape(1), non_blocking=True)
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+            return io["h_obs_np"].tolist(), [[bool(v) for v in row] for row in io["h_masks_np"].tolist()]
         return obs, masks
 
     def is_valid_cell(self, x, y):

@@ -274,3 +274,43 @@ def test_fused_update_tracks_autograd_update(tmp_path, faithful):
     cos = float((da @ db) / (da.norm() * db.norm()))
     assert cos > (0.999 if faithful else 0.98), cos
     assert far < (2e-3 if faithful else 0.15) * total, (far, total)
+
+
+def test_get_action_kernel_path_equals_the_module_path(tmp_path):
+    """PPO.get_action on a GPU asks the K4 kernels for the six logits of ONE observation (PPO._get_action_kernel) and draws on the host like the
+    reference (PPO.py:170-186).  Same torch seed => the same action and the same log-prob as the autograd modules followed by the same draw; a changed
+    actor (in-place optimiser-style step, load_state_dict) is picked up by the next call."""
+    brain, agents, maze = _make(1, tmp_path)
+    obs, masks = maze.reset()
+    rng = np.random.default_rng(1)
+
+    def module_path(o, m, seed):
+        with torch.no_grad():
+            mv, mk = brain.actor(torch.tensor(o, dtype=torch.float32, device="cuda"))
+        torch.manual_seed(seed)
+        return brain._sample_action(mv.cpu(), mk.cpu(), m), (mv.cpu(), mk.cpu())
+
+    def check(n, seed0):
+        nonlocal obs, masks
+        for k in range(n):
+            i = k % 2
+            (a_ref, lp_ref), (mv, mk) = module_path(obs[i], masks[i], seed0 + k)
+            torch.manual_seed(seed0 + k)
+            a, lp = brain.get_action(obs[i], masks[i])
+            lg = brain._act1["h_logits"][0, 0]
+            assert torch.allclose(lg[:5], mv.view(-1), rtol=1e-5, atol=8e-6) and torch.allclose(lg[5:], mk.view(-1), rtol=1e-5, atol=8e-6)
+            assert a == a_ref and masks[i][a[0]] and torch.allclose(lp, lp_ref, rtol=1e-5, atol=2e-6)
+            act = [[int(rng.choice([j for j in range(5) if masks[q][j]])), int(rng.integers(0, 2)) if masks[q][5] else 0] for q in range(2)]
+            obs, masks, r, d = maze.step(act)
+            if d:
+                obs, masks = maze.reset()
+
+    check(30, 100)
+    with torch.no_grad():   # an in-place step on every parameter, as an optimiser does
+        for p_ in brain.actor.parameters():
+            p_.add_(0.01 * torch.randn_like(p_))
+    check(10, 200)
+    brain._weights_version = getattr(brain, "_weights_version", 0)  # attribute exists / is an int
+    sd = {k: v + 0.01 for k, v in brain.actor.state_dict().items()}
+    brain.actor.load_state_dict(sd)
+    check(10, 300)

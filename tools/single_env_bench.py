@@ -1,6 +1,8 @@
 """BASELINE config[0]: the reference's own use -- ONE maze, two agents, the policy asked for one action at a time through the
 reference's interface (Maze.reset / Agent.get_action / Maze.step with python lists, the loop of maze.py:477-493) -- on this framework.
-It is launch- and synchronisation-bound by construction (every step returns python lists); the batched path is the product.
+It is launch- and synchronisation-bound by construction (every step returns python lists); the batched path is the product.  Per step: two
+get_action calls (each: one pinned copy in, tokens + fused trunk at one env, six logits back, the reference's draw on the host) and one Maze.step
+(four action bytes in, the step kernel, observation / masks / reward / done back through pinned mirrors, one synchronisation).
     python tools/single_env_bench.py [--steps 3000]"""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
