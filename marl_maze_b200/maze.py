@@ -160,9 +160,18 @@ class Maze:
             io["h_obs"].copy_(obs[0], non_blocking=True); io["h_masks"].copy_(masks[0], non_blocking=True)
             if reward is not None:
                 io["h_rew"].copy_(reward.reshape(1), non_blocking=True); io["h_done"].copy_(done.reshape(1), non_blocking=True)
+            brain = self.agents[0].brain
+            bdev = getattr(brain, "device", None)   # torch.device("cuda") and torch.device("cuda:0") do not compare equal
+            pre = (bool(getattr(self, "_prefetch_policy", False)) and bdev is not None and bdev.type == obs.device.type == "cuda"
+                   and bdev.index in (None, obs.device.index) and obs.is_contiguous())
+            if pre:     # a get_action loop (maze.py:477-493): both agents' logits ride along with the observation (PPO._prefetch_logits)
+                brain._prefetch_logits(obs)
             if self.device.type == "cuda":
                 torch.cuda.current_stream(self.device).synchronize()
-            return io["h_obs_np"].tolist(), [[bool(v) for v in row] for row in io["h_masks_np"].tolist()]
+            rows = io["h_obs_np"].tolist()
+            if pre:
+                brain._commit_logits(rows)
+            return rows, [[bool(v) for v in row] for row in io["h_masks_np"].tolist()]
         return obs, masks
 
     def is_valid_cell(self, x, y):

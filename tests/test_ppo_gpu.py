@@ -290,14 +290,17 @@ def test_get_action_kernel_path_equals_the_module_path(tmp_path):
         torch.manual_seed(seed)
         return brain._sample_action(mv.cpu(), mk.cpu(), m), (mv.cpu(), mk.cpu())
 
+    hits = 0
+
     def check(n, seed0):
-        nonlocal obs, masks
+        nonlocal obs, masks, hits
         for k in range(n):
             i = k % 2
             (a_ref, lp_ref), (mv, mk) = module_path(obs[i], masks[i], seed0 + k)
             torch.manual_seed(seed0 + k)
             a, lp = brain.get_action(obs[i], masks[i])
-            lg = brain._act1["h_logits"][0, 0]
+            lg = brain._act1["last_logits"]
+            hits += brain._act1["cache"] is not None and obs[i] in brain._act1["cache"][0]
             assert torch.allclose(lg[:5], mv.view(-1), rtol=1e-5, atol=8e-6) and torch.allclose(lg[5:], mk.view(-1), rtol=1e-5, atol=8e-6)
             assert a == a_ref and masks[i][a[0]] and torch.allclose(lp, lp_ref, rtol=1e-5, atol=2e-6)
             act = [[int(rng.choice([j for j in range(5) if masks[q][j]])), int(rng.integers(0, 2)) if masks[q][5] else 0] for q in range(2)]
@@ -306,6 +309,7 @@ def test_get_action_kernel_path_equals_the_module_path(tmp_path):
                 obs, masks = maze.reset()
 
     check(30, 100)
+    assert hits >= 25 and maze._prefetch_policy   # after the first call the logits arrive with the observation (PPO._prefetch_logits)
     with torch.no_grad():   # an in-place step on every parameter, as an optimiser does
         for p_ in brain.actor.parameters():
             p_.add_(0.01 * torch.randn_like(p_))
