@@ -384,6 +384,10 @@ def run_ours(args):
     if not args.no_extra_legs:
         ppo_leg = ppo_iteration_leg(torch, dist, world, rank, local, args)
 
+    single = None
+    if rank == 0 and world == 1 and not args.no_extra_legs:
+        single = single_env_leg(torch, local, seconds=2.0)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -423,6 +427,8 @@ def run_ours(args):
             line["strong"] = strong
         if ppo_leg is not None:
             line["rollout" if world == 1 else "train_iter"] = ppo_leg
+        if single is not None:
+            line["single_env"] = single
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -483,6 +489,33 @@ def ppo_iteration_leg(torch, dist, world, rank, local, args):
     except Exception:
         pass
     return out
+
+
+def single_env_leg(torch, local, seconds=2.0):
+    """BASELINE config[0] on this framework: ONE maze, the reference's python-list interface (Maze.reset / Agent.get_action per agent / Maze.step, the
+    loop of maze.py:477-493), main.py's settings, randomly initialised networks of the reference architecture.  Host-timed (every call returns python
+    objects); cpu_baseline.python_reference.config1_policy_rollout is the unmodified reference in the same loop on this box's CPU."""
+    from marl_maze_b200.PPO import PPO
+    from marl_maze_b200.maze import Maze
+    from marl_maze_b200.maze_agent import Agent
+    dev = f"cuda:{local}"
+    brain = PPO(agent_amount=2, batch_size=15000, lr=0.00014, verbose=False, model_path=None, device=dev)
+    agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
+    maze = Maze(agents=agents, max_timestep=MAX_T, rand_sizes=True, rand_range=[12, 13], rand_start=True, difficulty=1, default_size=[4, 4], num_envs=1, seed=0, device=dev)
+    obs, masks = maze.reset()
+    n = 0
+    for budget in (0.3, seconds):   # warm-up, then the timed loop
+        torch.cuda.synchronize(); t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < budget:
+            action = [agent.get_action(obs[i], masks[i])[0] for i, agent in enumerate(agents)]
+            obs, masks, reward, done = maze.step(action)
+            n += 1
+            if done:
+                obs, masks = maze.reset()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    return {"what": "config[0]: 1 maze (side 23-25), 2 agents, Agent.get_action per agent + Maze.step through python lists; one stream synchronisation per env step "
+                    "(both agents' logits are fetched behind the step kernel)", "env_steps": n, "seconds": round(dt, 3),
+            "agent_steps_per_s": 2.0 * n / dt, "unit": "agent-steps/s", "timed": "host clock"}
 
 
 def main():

@@ -97,7 +97,11 @@ size_t mm_sizeof_env_episode(int n_envs) { return (size_t)n_envs * 4; }
 size_t mm_sizeof_agent_a(int n_envs) { return (size_t)n_envs * 2 * 16; }
 size_t mm_sizeof_agent_b(int n_envs) { return (size_t)n_envs * 2 * 4; }
 size_t mm_sizeof_finalize_scratch(int n, int smax) { return (size_t)n * smax * smax * 2; }
-size_t mm_sizeof_generate_scratch(int n, int smax) { return (size_t)n * smax * smax * 2; }
+#ifdef MM_K1_V1
+size_t mm_sizeof_generate_scratch(int n, int smax) { return (size_t)n * smax * smax * 2; }   // DFS stack / BFS queue of the first-generation kernel
+#else
+size_t mm_sizeof_generate_scratch(int, int) { return 16; }   // the generator keeps all working state in shared memory (mm_generate.cu); the argument stays in the ABI
+#endif
 
 int mm_init_state(const mm_state* st, void* stream) {
     if (!state_ok(st)) return MM_ERR_BAD_ARG;

@@ -39,7 +39,19 @@ constexpr int TF_BM = 128, TF_BK = 32, TF_N = 264, TF_N0 = 128, TF_N1 = 144, TF_
 #endif
 constexpr int TF_CLUSTER = MM_TF_CLUSTER;
 static_assert(TF_CLUSTER == 1 || TF_CLUSTER == 2, "cluster of one or two CTAs");
-constexpr int TF_WSTAGES = MM_TF_WSTAGES, TF_ASLOTS = 4, TF_OPS = 3;
+// MM_TF_ADEDICATED = 1: the fp32 landing slots of layer 0 get shared memory of their own (taken from the weight ring: build with MM_TF_WSTAGES 6 and
+// MM_TF_ASLOTS 2, or 7 and 1) instead of aliasing the lo plane, so the activation producer loads the NEXT tile's first blocks while this tile's layers
+// 1-3 run instead of waiting for the head MMAs (5.2 of 48 kclk per tile were that wait).
+#ifndef MM_TF_STAGGER_CLK
+#define MM_TF_STAGGER_CLK 0
+#endif
+#ifndef MM_TF_ADEDICATED
+#define MM_TF_ADEDICATED 0
+#endif
+#ifndef MM_TF_ASLOTS
+#define MM_TF_ASLOTS 4
+#endif
+constexpr int TF_WSTAGES = MM_TF_WSTAGES, TF_ASLOTS = MM_TF_ASLOTS, TF_OPS = 3;
 constexpr uint32_t TF_WROW = 64;                                  // fp16 weight rows of one k-block: 32 x 2 bytes, SWIZZLE_64B
 constexpr uint32_t TF_WHALF = TF_N1 * TF_WROW;                    // 9216: one of (hi, lo) of a stage, sized for the wider half
 constexpr uint32_t TF_W_BYTES = 2 * TF_WHALF;                     // 18432
@@ -48,9 +60,10 @@ constexpr int TF_HKB = 9;                                         // 264 columns
 constexpr uint32_t TF_H_KB_BYTES = TF_BM * 64;                    // 8192
 constexpr uint32_t TF_H_PLANE = TF_HKB * TF_H_KB_BYTES;           // 73728: the lo plane
 constexpr uint32_t TF_A_BYTES = TF_BM * TF_BK * 4;                // 16384: fp32 landing slot (layer 0), 128-byte rows, SWIZZLE_128B
-static_assert(TF_ASLOTS * TF_A_BYTES <= TF_H_PLANE, "landing slots alias the lo plane");
+static_assert(MM_TF_ADEDICATED || TF_ASLOTS * TF_A_BYTES <= TF_H_PLANE, "landing slots alias the lo plane");
 static_assert(TF_H_OFF % 1024 == 0, "swizzle atoms need 1024-byte alignment");
-constexpr uint32_t TF_RING_BYTES = TF_H_OFF + TF_H_PLANE;         // 221184
+constexpr uint32_t TF_A_OFF = MM_TF_ADEDICATED ? TF_H_OFF + TF_H_PLANE : TF_H_OFF;   // landing slots: behind the lo plane, or aliasing it
+constexpr uint32_t TF_RING_BYTES = TF_H_OFF + TF_H_PLANE + (MM_TF_ADEDICATED ? TF_ASLOTS * TF_A_BYTES : 0u);   // 221184
 constexpr uint32_t TF_BAR_OFF = TF_RING_BYTES;
 constexpr uint32_t TF_BIAS_OFF = TF_BAR_OFF + 512;
 static_assert((2 * TF_WSTAGES + 2 * TF_ASLOTS + 2 * TF_OPS + 3) * 8 + 4 <= 512, "barriers fit in front of the biases");
@@ -229,6 +242,11 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
     const int pair0 = blockIdx.x / TF_CLUSTER, pair_stride = gridDim.x / TF_CLUSTER;
     const int n_pairs = (args.n_tiles + TF_CLUSTER - 1) / TF_CLUSTER;
     if (TF_CLUSTER > 1) tf_cluster_sync();   // the peer's barriers are initialised before anything of ours can land on them
+#if MM_TF_STAGGER_CLK > 0
+    // All CTAs walk the same layer sequence in lockstep, so the chip's L2 sees every layer-0 phase (weights + the fp32 activation stream: ~31 B/clk/SM)
+    // at once and every layer-1/2 phase (20 B/clk/SM) at once.  Every other cluster starts MM_TF_STAGGER_CLK clocks late to interleave the phases.
+    if ((blockIdx.x / TF_CLUSTER) & 1) { const long long t0 = clock64(); while (clock64() - t0 < (long long)MM_TF_STAGGER_CLK) { } }
+#endif
 
     if (warp == 0) {
         {  // ===== weight producer (whole warp loops, one elected lane issues)
@@ -276,14 +294,14 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
                 const int m0 = (pair * TF_CLUSTER + (int)crank) * TF_BM;
                 // The landing slots alias the lo plane: the previous tile's head MMAs (the 4th d_full completion of that tile) must be done.  A parity
                 // wait only tells two consecutive phases apart and this warp can be several phases behind: it follows all four completions in order.
-                if (t_local)
+                if (!MM_TF_ADEDICATED && t_local)
                     for (int i = 0; i < 4; i++) TF_PROF_WAIT(0, mbar_wait(d_full, (4 * (t_local - 1) + i) & 1));
                 for (int kb = 0; kb < kTfNKB0; kb++, ait++) {
                     const int sa = ait % TF_ASLOTS;
                     TF_PROF_WAIT(1, mbar_wait(&a_free[sa], ((ait / TF_ASLOTS) & 1) ^ 1));
                     if (elect_one()) {
                         mbar_expect_tx(&a_full[sa], TF_A_BYTES);
-                        tma_load_2d(hlo + sa * TF_A_BYTES, &maps.a, kb * TF_BK, m0, &a_full[sa]);
+                        tma_load_2d(smem + TF_A_OFF + sa * TF_A_BYTES, &maps.a, kb * TF_BK, m0, &a_full[sa]);
                     }
                 }
                 // The next tile's activation blocks can only be LOADED once this tile's head MMAs are done (the landing slots alias the lo plane), which
@@ -382,7 +400,7 @@ __global__ void __cluster_dims__(TF_CLUSTER, 1, 1) __launch_bounds__(TF_THREADS,
             // ---- layer 0 main loop: fp32 landing slot -> fp16 hi / lo -> tensor memory
             for (int kb = 0; kb < kTfNKB0; kb++, ait++, oit++) {
                 const int sa = ait % TF_ASLOTS, os = oit % TF_OPS;
-                const float4* rowp = reinterpret_cast<const float4*>(hlo + sa * TF_A_BYTES + arow * 128);
+                const float4* rowp = reinterpret_cast<const float4*>(smem + TF_A_OFF + sa * TF_A_BYTES + arow * 128);
                 TF_PROF_WAIT(0, mbar_wait(&a_full[sa], (ait / TF_ASLOTS) & 1));
                 constexpr int kC = 8 / TF_WPQ;   // float4 chunks of the 32-column block per warp of the quarter
                 float4 av[kC];

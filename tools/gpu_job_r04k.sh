@@ -1,0 +1,8 @@
+#!/bin/bash
+# K1: parent-pointer carve (no stack, no tree walks)
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_generator_gpu.py tests/test_env_parity_gpu.py -x -q 2>&1 | tail -4
+timeout 300 python tools/k1_bench.py 2>&1 | tail -1 | tee -a gpurun_out/r04k_k1.jsonl
+timeout 300 python tools/k1_bench.py --mazes 393216 --side-half 13 2>&1 | tail -1 | tee -a gpurun_out/r04k_k1.jsonl
+timeout 300 python tools/k1_bench.py --mazes 262144 --side-half 13 --difficulty 4 2>&1 | tail -1 | tee -a gpurun_out/r04k_k1.jsonl
+
