@@ -166,7 +166,8 @@ int mm_gae(const float *reward, const float *value, const uint8_t *done, const f
  *            [64][64], c1_b, c2_w [64], c2_b [1], total, then l{0,1,2}_w{hi,lo}: the trunk weights split as w = hi + lo with hi = w
  *            truncated to TF32 -- only read by the tensor-core path).  proj_col[i] is the first obs column projection i reads: 0 for every i
  *            reproduces the reference's Projection.forward (networks.py:59-63); sum(FEATURE_DIMS[:i]) is the indexed variant.
- *   obs [E][2][65] f32, masks [E][2][6] u8, scratch: mm_sizeof_policy_scratch(E) bytes.
+ *   obs [E][2][65] f32 (8-byte aligned: the critic reads the rows as float2), masks [E][2][6] u8, scratch: mm_sizeof_policy_scratch(E) bytes;
+ *   weights and scratch 16-byte aligned (MM_ERR_BAD_ARG otherwise).
  *   actions_in == NULL: sample (Philox keyed by seed, counter, env_offset+env, agent) into actions_out [E][2][2] u8;
  *   actions_in != NULL: evaluate those actions instead (actions_out unused).
  *   logp [E] f32 = joint log-prob of both agents' actions (PPO.py:118,121); value [E] f32 (may be NULL); logits_out [E][2][6]

@@ -201,6 +201,7 @@ int mm_selftest_div(int amax, int bmax, uint64_t* mismatches, void* stream) {
 int mm_policy_offsets(int32_t* out) { return out ? policy_offsets_host(out) : MM_ERR_BAD_ARG; }
 int mm_critic_forward(const float* weights, const float* obs, int n_envs, float* value, void* stream) {
     if (!weights || !obs || !value || n_envs <= 0) return MM_ERR_BAD_ARG;
+    if (((uintptr_t)weights & 15) || ((uintptr_t)obs & 7)) return MM_ERR_BAD_ARG;   // 16-byte weight quads; the observation rows are read as float2
     return cuda_status(launch_critic(weights, obs, n_envs, value, (cudaStream_t)stream));
 }
 size_t mm_sizeof_policy_scratch(int n_envs) { return (size_t)n_envs * 2 * (460 + 2 * 264 + 16) * sizeof(float); }
@@ -208,7 +209,7 @@ int mm_policy_forward(const float* weights, const float* obs, const uint8_t* mas
                       uint8_t* actions_out, float* logp, float* value, float* logits_out, int env_offset, uint64_t seed, uint64_t counter, int flags,
                       const uint64_t* counter_dev, void* stream) {
     if (!weights || !obs || !masks || n_envs <= 0 || !scratch || !logp || (!actions_in && !actions_out)) return MM_ERR_BAD_ARG;
-    if (((uintptr_t)weights & 15) || ((uintptr_t)scratch & 15)) return MM_ERR_BAD_ARG;
+    if (((uintptr_t)weights & 15) || ((uintptr_t)scratch & 15) || ((uintptr_t)obs & 7)) return MM_ERR_BAD_ARG;
     return cuda_status(launch_policy(weights, obs, masks, n_envs, (float*)scratch, actions_in, actions_out, logp, value, logits_out, env_offset, seed,
                                      counter, flags, counter_dev, (cudaStream_t)stream));
 }
