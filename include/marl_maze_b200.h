@@ -258,12 +258,17 @@ int mm_segment_sum(const float *x, const int64_t *seg, int rows, int cols, int n
  * The 23-token embedding of K4 as a stand-alone pair (Projection + m_Attention, networks.py:58-65,75-82, and their backward).
  * weights: the K4 buffer layout (mm_policy_offsets); only tokm [60][23][4], tokb [60][23] (the per-token affine maps: rows 0-19 token,
  * 20-29 key, 30-39 query, 40-59 value), proj_col [23] and proj_dim [23] are read.
- *   mm_tokens_forward:  x0 [rows][460] = token + attention(token) for obs [rows][65].
+ *   mm_tokens_forward:  x0 [rows][460] = token + attention(token) for obs [rows][65] -- a function of the maps alone (this is the forward the backward
+ *                       below differentiates; second-generation kernel, mm_tokens_mma.cu).
+ *   mm_tokens_forward_full: the same values through the third-generation kernel the rollout uses (mm_tokens_proj.cu: keys / queries / values as
+ *                       tensor-path products of the token tile); it reads rows 0-19 of tokm / tokb AND att_q [10][20], att_k [10][20], att_v [20][20] of
+ *                       the full K4 weight buffer (policy.pack_weights), which must be consistent with the maps.
  *   mm_tokens_backward: part [mm_tokens_backward_blocks()][60][23][5] <- per-block partial sums of d loss / d tokm (first four of the
  *                       five) and d loss / d tokb (the fifth), given d_x0 [rows][460] = d loss / d x0; scratch:
  *                       mm_sizeof_tokens_backward_scratch(rows) bytes (the per-row key / query / value gradients, 3680 B per row).
  */
 int mm_tokens_forward(const float *weights, const float *obs, int rows, float *x0, void *stream);
+int mm_tokens_forward_full(const float *weights, const float *obs, int rows, float *x0, void *stream);
 int mm_tokens_backward_blocks(void);
 size_t mm_sizeof_tokens_backward_scratch(int rows);
 int mm_tokens_backward(const float *weights, const float *obs, const float *d_x0, int rows, void *scratch, float *part, void *stream);

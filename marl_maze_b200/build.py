@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarl_maze_b200.so")
-SOURCES = ["mm_abi.cu", "mm_step_obs.cu", "mm_pool.cu", "mm_gae.cu", "mm_generate.cu", "mm_policy.cu", "mm_policy_tc.cu", "mm_linear16.cu", "mm_trunk_fused.cu", "mm_tokens_mma.cu", "mm_update_tc.cu", "mm_update.cu"]
+SOURCES = ["mm_abi.cu", "mm_step_obs.cu", "mm_pool.cu", "mm_gae.cu", "mm_generate.cu", "mm_policy.cu", "mm_policy_tc.cu", "mm_linear16.cu", "mm_trunk_fused.cu", "mm_tokens_mma.cu", "mm_tokens_proj.cu", "mm_update_tc.cu", "mm_update.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC"]
 
 

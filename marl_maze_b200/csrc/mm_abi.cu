@@ -12,6 +12,7 @@ cudaError_t launch_generate(const mm_state* st, int first, int n, int side_lo, i
 cudaError_t launch_policy(const float*, const float*, const uint8_t*, int, float*, const uint8_t*, uint8_t*, float*, float*, float*, int, uint64_t, uint64_t,
                           int, const uint64_t*, cudaStream_t);
 cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream);
+cudaError_t launch_tokens_fwd_full(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream);
 cudaError_t launch_tokens_bwd(const float* wts, const float* obs, const float* dout, int R, float* dy40, float* part, cudaStream_t stream);
 size_t tokens_bwd_scratch_floats(int R);
 int tokens_bwd_blocks();
@@ -273,6 +274,10 @@ int mm_segment_sum(const float* x, const int64_t* seg, int rows, int cols, int n
 int mm_tokens_forward(const float* weights, const float* obs, int rows, float* x0, void* stream) {
     if (!weights || !obs || !x0 || rows <= 0 || ((uintptr_t)x0 & 15)) return MM_ERR_BAD_ARG;
     return cuda_status(launch_tokens_fwd(weights, obs, rows, x0, (cudaStream_t)stream));
+}
+int mm_tokens_forward_full(const float* weights, const float* obs, int rows, float* x0, void* stream) {
+    if (!weights || !obs || !x0 || rows <= 0 || ((uintptr_t)x0 & 15)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_tokens_fwd_full(weights, obs, rows, x0, (cudaStream_t)stream));
 }
 int mm_tokens_backward_blocks(void) { return tokens_bwd_blocks(); }
 size_t mm_sizeof_tokens_backward_scratch(int rows) { return rows > 0 ? tokens_bwd_scratch_floats(rows) * sizeof(float) : 0; }

@@ -285,13 +285,19 @@ __global__ void __launch_bounds__(kTokWarps * 32, MM_TOK_R_MINBLOCKS) k_tokens_r
     }
 }
 constexpr int kTokRSmem = (60 * kTok * 5 + kTokWarps * MM_TOK_ROWS * kTok * kTokTS) * (int)sizeof(float);
-// -DMM_TOK_MMA=0 keeps the SIMT token kernel (A/B runs); the default is the HMMA version (mm_tokens_mma.cu)
+// -DMM_TOK_MMA=0 keeps the SIMT token kernel, 1 the second generation (attention on HMMA, mm_tokens_mma.cu) for A/B runs; the default is the third
+// (keys / queries / values as tensor-path products of the token tile, mm_tokens_proj.cu)
 #ifndef MM_TOK_MMA
-#define MM_TOK_MMA 1
+#define MM_TOK_MMA 2
 #endif
 cudaError_t launch_tokens_mma(const float* wts, const float* obs, int R, float* x0, int off_tokm, int off_tokb, int off_col, int off_dim, cudaStream_t stream);
+cudaError_t launch_tokens_proj(const float* wts, const float* obs, int R, float* x0, int off_tokm, int off_tokb, int off_col, int off_dim, int off_q, int off_k, int off_v,
+                               cudaStream_t stream);
 static cudaError_t launch_tokens_any(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
-#if MM_TOK_MMA
+#if MM_TOK_MMA == 2   // third generation: keys / queries / values as tensor-path products of the token tile (mm_tokens_proj.cu)
+    const PolicyOffsets o = policy_offsets();
+    return launch_tokens_proj(wts, obs, R, x0, o.tokm, o.tokb, o.proj_col, o.proj_dim, o.att_q, o.att_k, o.att_v, stream);
+#elif MM_TOK_MMA
     const PolicyOffsets o = policy_offsets();
     return launch_tokens_mma(wts, obs, R, x0, o.tokm, o.tokb, o.proj_col, o.proj_dim, stream);
 #elif MM_TOK_ROWS >= 2
@@ -506,7 +512,17 @@ __global__ void __launch_bounds__(kTrThreads) k_tokens_bwd_reduce(const float* _
 
 int tokens_bwd_blocks() { return 148 * 4; }
 size_t tokens_bwd_scratch_floats(int R) { return (size_t)R * kTok * 40; }
-cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) { return launch_tokens_any(wts, obs, R, x0, stream); }
+// the stand-alone forward is a function of the per-token maps alone (its caller, update.TokenEmbed, fills only those blocks of the buffer and its backward
+// differentiates exactly this function): second-generation kernel.  _full: whatever the rollout uses, given the full weight buffer.
+cudaError_t launch_tokens_fwd(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) {
+#if MM_TOK_MMA
+    const PolicyOffsets o = policy_offsets();
+    return launch_tokens_mma(wts, obs, R, x0, o.tokm, o.tokb, o.proj_col, o.proj_dim, stream);
+#else
+    return launch_tokens_any(wts, obs, R, x0, stream);
+#endif
+}
+cudaError_t launch_tokens_fwd_full(const float* wts, const float* obs, int R, float* x0, cudaStream_t stream) { return launch_tokens_any(wts, obs, R, x0, stream); }
 cudaError_t launch_tokens_bwd(const float* wts, const float* obs, const float* dout, int R, float* dy40, float* part, cudaStream_t stream) {
     static PerDeviceFlag configured;
     if (configured.first_time()) {

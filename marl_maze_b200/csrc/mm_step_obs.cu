@@ -104,6 +104,33 @@ struct LaneCtx {
 
 __device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// L2 residency hints (MM_K2_L2HINT: bit 0 = state evict_last, bit 1 = streams evict_first).  Per step the kernel streams ~0.9 GB through a 126 MB L2 (window rows in, observations out: no reuse) and reads +
+// writes 56 B of agent / env state per env -- 59 MB at 1 Mi envs, the only data it touches again in the next launch.  State loads and stores carry an
+// evict_last policy, the window bulk copies and the observation bulk store evict_first, so that in an env-only stepping loop (BASELINE config[3]) the
+// state stays resident between launches: its 2 x 59 MB leave the DRAM traffic and the FIRST of the two dependent round trips (state -> window address)
+// becomes an L2 hit.
+#ifndef MM_K2_L2HINT
+#define MM_K2_L2HINT 0
+#endif
+__device__ __forceinline__ uint64_t k2_policy_evict_last() { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol; }
+__device__ __forceinline__ uint64_t k2_policy_evict_first() { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol; }
+__device__ __forceinline__ uint4 k2_ld_keep(const uint4* a, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t k2_ld_keep(const uint32_t* a, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void k2_st_keep(uint4* a, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void k2_st_keep(uint32_t* a, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+
 // Phase 1: load state, S1 (Maze.step / single_agent_step), reward/done, and put the window rows of the NEW position in flight.
 template <bool kResetOnly>
 __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const int lane) {
@@ -112,7 +139,11 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
     const bool valid = c.valid;
     uint4 H = make_uint4(0, 0, 0, 0), A = make_uint4(0, 0, 0, 0);
     uint32_t B = 0;
+#if MM_K2_L2HINT & 1
+    if (valid) { const uint64_t keep = k2_policy_evict_last(); H = k2_ld_keep(&p.env_hdr[e], keep); A = k2_ld_keep(&p.agent_a[g], keep); B = k2_ld_keep(&p.agent_b[g], keep); }
+#else
     if (valid) { H = p.env_hdr[e]; A = p.agent_a[g]; B = p.agent_b[g]; }
+#endif
     Agent me = unpack_agent(A, B);
     uint32_t t = H.x, keyp = H.z & 1u, err = (H.z >> 1) & 1u, pidx = H.w;
     int W = (H.z >> 8) & 0xff, Hh = (H.z >> 16) & 0xff;
@@ -209,7 +240,13 @@ __device__ __forceinline__ void k2_phase1(const StepParams& p, LaneCtx& c, const
             const ulonglong2* grid = (const ulonglong2*)(p.env_grid + (size_t)e * p.rows);
             const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(wbase_s + lane * 176), s1 = (uint32_t)__cvta_generic_to_shared(wbase_s + 32 * 176 + lane * 16);
 #if MM_K2_BULK
+#if MM_K2_L2HINT & 2
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], 176, [%2], %3;" ::"r"(s0), "l"(grid + me.y),
+                         "r"(k2_smem_u32(c.bar)), "l"(k2_policy_evict_first())
+                         : "memory");
+#else
             asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], 176, [%2];" ::"r"(s0), "l"(grid + me.y), "r"(k2_smem_u32(c.bar)) : "memory");
+#endif
 #else
 #pragma unroll
             for (int r = 0; r < 11; r++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16 * r), "l"(grid + me.y + r) : "memory");
@@ -510,11 +547,20 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
     // ---------------------------------------------------------------- state write-back
     if (!kResetOnly) err |= __shfl_xor_sync(kFull, err, 1);   // either agent's illegal move flags the env (agent 0's lane writes the header)
     if (valid && (!kResetOnly || want_reset)) {
+        const uint4 hdr_new = make_uint4(t, (uint32_t)ex | ((uint32_t)ey << 8) | ((uint32_t)kx << 16) | ((uint32_t)ky << 24),
+                                         keyp | (err << 1) | ((uint32_t)W << 8) | ((uint32_t)Hh << 16), pidx);
+#if MM_K2_L2HINT & 1
+        const uint64_t keep = k2_policy_evict_last();
+        k2_st_keep(&p.agent_a[g], pack_agent(me), keep);
+        k2_st_keep(&p.agent_b[g], me.time, keep);
+        if (a == 0) {
+            k2_st_keep(&p.env_hdr[e], hdr_new, keep);
+#else
         p.agent_a[g] = pack_agent(me);
         p.agent_b[g] = me.time;
         if (a == 0) {
-            p.env_hdr[e] = make_uint4(t, (uint32_t)ex | ((uint32_t)ey << 8) | ((uint32_t)kx << 16) | ((uint32_t)ky << 24),
-                                      keyp | (err << 1) | ((uint32_t)W << 8) | ((uint32_t)Hh << 16), pidx);
+            p.env_hdr[e] = hdr_new;
+#endif
             if (!kResetOnly) { p.reward[e] = reward; p.done[e] = (uint8_t)done; }
         }
     }
@@ -535,9 +581,15 @@ __device__ __forceinline__ void k2_phase2(const StepParams& p, LaneCtx& c, const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy STS above -> visible to the async proxy
         __syncwarp();
         if (lane == 0) {
+#if MM_K2_L2HINT & 2
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(p.obs + gbase * kObs),
+                         "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(32 * kObs * 4), "l"(k2_policy_evict_first())
+                         : "memory");
+#else
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.obs + gbase * kObs),
                          "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(32 * kObs * 4)
                          : "memory");
+#endif
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
         }
