@@ -134,3 +134,62 @@ def test_generator_regression_partial_maze_without_eligible_exit():
         assert (g["start"], g["path1"], g["end"], g["key"], g["shortest_path_len"]) == (m["start"], m["path1"], m["end"], m["key"], m["shortest_path_len"]), p
     g = eng.pool_maze(2)
     assert int((g["layout"] == 0).sum()) == 11 and g["layout"][g["end"][1], g["end"][0]] == 0
+
+
+@pytest.mark.parametrize("cfg", [dict(side=(13, 13), difficulty=1, height_cells=0), dict(side=(25, 25), difficulty=4, height_cells=0),
+                                 dict(side=(4, 9), difficulty=2, height_cells=0), dict(side=(6, 6), difficulty=3, height_cells=11),
+                                 dict(side=(27, 27), difficulty=1, height_cells=0)])
+def test_dir_to_exit_field_leads_every_open_cell_to_the_exit(cfg):
+    """K1 builds the dir-to-exit field from the carve's own parent pointers (tree rooted at the start) by turning the start -> exit path around.  A perfect
+    maze is a tree, so the field is fully determined: from EVERY open cell, following it must walk open cells only, never revisit one, and end on the exit;
+    the exit's own entry and every wall's entry are 0."""
+    from marl_maze_b200 import MazeEngine
+    n = 48
+    smax = max(cfg["side"][1], cfg["height_cells"]) * 2 - 1
+    eng = MazeEngine(4, smax=smax, max_timestep=100, pool_size=n)
+    eng.generate(99, side_range=cfg["side"], rand_start=True, difficulty=cfg["difficulty"], id_base=5, height_cells=cfg["height_cells"])
+    for p in range(n):
+        g = eng.pool_maze(p)
+        lay, d2e = np.asarray(g["layout"]), np.asarray(g["d2e"])
+        H, W = lay.shape
+        ex, ey = g["end"]
+        assert d2e[ey, ex] == 0 and (d2e[lay != 0] == 0).all()
+        dist = -np.ones((H, W), np.int64); dist[ey, ex] = 0
+        for y0 in range(H):
+            for x0 in range(W):
+                if lay[y0, x0] != 0 or dist[y0, x0] >= 0:
+                    continue
+                chain, x, y = [], x0, y0
+                while dist[y, x] < 0:
+                    assert lay[y, x] == 0 and (x, y) not in chain and len(chain) <= H * W, (p, x0, y0)
+                    chain.append((x, y))
+                    k = int(d2e[y, x]); x, y = x + (k == 1) - (k == 3), y + (k == 2) - (k == 0)
+                    assert 0 <= x < W and 0 <= y < H, (p, x0, y0)
+                for i, (cx, cy) in enumerate(reversed(chain)):
+                    dist[cy, cx] = dist[y, x] + 1 + i
+        sx, sy = g["start"]
+        assert dist[sy, sx] + 1 == g["shortest_path_len"]
+
+
+def test_masked_generation_ragged_counts_and_sparse_masks():
+    """mm_generate_masked compacts the consumed slots warp-wide before carving: slot counts that are not multiples of 32, an all-zero mask, a single slot
+    and a random mask must rebuild exactly the masked slots (the oracle's maze under the new seed) and leave every other slot untouched."""
+    import torch
+    from marl_maze_b200 import MazeEngine
+    n, side = 1000 + 77, (7, 9)
+    eng = MazeEngine(4, smax=side[1] * 2 - 1, max_timestep=100, pool_size=n)
+    eng.generate(11, side_range=side, rand_start=True, difficulty=2, id_base=3)
+    grid0, hdr0 = eng.pool_grid.clone(), eng.pool_hdr.clone()
+    rng = np.random.default_rng(5)
+    masks = [np.zeros(n, np.uint8), np.eye(1, n, n - 1, dtype=np.uint8)[0], (rng.random(n) < 0.17).astype(np.uint8), (rng.random(n) < 0.9).astype(np.uint8)]
+    o = OracleMaze(max_timestep=10, difficulty=2, rand_start=True, rand_sizes=True, rand_range=side, default_size=(4, 4))
+    for it, mk in enumerate(masks):
+        seed = 100 + it
+        eng.generate(seed, side_range=side, rand_start=True, difficulty=2, id_base=3, only=torch.from_numpy(mk).cuda())
+        same = (eng.pool_grid.view(n, -1) == grid0.view(n, -1)).all(1).cpu().numpy() & (eng.pool_hdr.view(n, -1) == hdr0.view(n, -1)).all(1).cpu().numpy()
+        assert same[mk == 0].all(), it                                       # untouched slots: bit-identical
+        for p in list(np.flatnonzero(mk)[:12]) + list(np.flatnonzero(mk)[-3:]):
+            g = eng.pool_maze(int(p))
+            o.seed_philox(seed, 3 + int(p)); o.build(); m = o.maze()
+            assert np.array_equal(g["layout"], m["layout"]) and g["start"] == m["start"] and g["end"] == m["end"] and g["key"] == m["key"], (it, p)
+        grid0, hdr0 = eng.pool_grid.clone(), eng.pool_hdr.clone()

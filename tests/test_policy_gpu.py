@@ -144,3 +144,45 @@ def test_kat5_reference_checkpoint_through_mm_policy_forward(tc):
     fin = np.isfinite(want)
     got = logp.cpu().numpy()
     assert np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], want[fin], **TOL)
+
+
+@pytest.mark.parametrize("faithful", [True, False])
+def test_token_kernels_full_and_maps_only_agree_with_float64(faithful):
+    """mm_tokens_forward (second generation: everything from the folded per-token maps -- the forward the update differentiates) and
+    mm_tokens_forward_full (third generation, the rollout's: keys / queries / values as tensor-path products with att_q / att_k / att_v) are the same
+    function of a consistently packed weight buffer: both within 1e-6 (of the largest element) of the float64 modules (Projection + m_Attention, networks.py:58-65,75-82),
+    ragged row counts included."""
+    import copy
+    from marl_maze_b200 import _abi
+    from marl_maze_b200.policy import pack_weights
+    actor, critic, _, _ = _nets(7, faithful)
+    w = pack_weights(actor, critic, "cuda")
+    L = _abi.lib(); st = torch.cuda.current_stream().cuda_stream
+    a64 = copy.deepcopy(actor).double()
+    rng = np.random.default_rng(11)
+    for R in (1, 33, 2051):
+        obs = torch.from_numpy((rng.random((R, 65)) * 2 - 0.5).astype(np.float32)).cuda()
+        with torch.no_grad():
+            ref = a64.attention(a64.projection(obs.double()))
+        for fn in (L.mm_tokens_forward, L.mm_tokens_forward_full):
+            x0 = torch.full((R, 460), float("nan"), device="cuda")
+            _abi.check(fn(w.data_ptr(), obs.data_ptr(), R, x0.data_ptr(), st), "tokens")
+            err, scale = float((x0.double() - ref).abs().max()), max(1.0, float(ref.abs().max()))
+            assert err < 1e-6 * scale, (R, fn.__name__, err, scale)
+
+
+def test_critic_kernel_ragged_env_counts_against_float64():
+    """mm_critic_forward (3xFP16 mma.sync, 32 envs per warp) at env counts that do not fill a warp tile, against the float64 module."""
+    import copy
+    from marl_maze_b200.policy import PolicyRunner
+    actor, critic, _, _ = _nets(9)
+    W = [l.weight.detach().double() for l in critic.layers]; B = [l.bias.detach().double() for l in critic.layers]
+    c64 = lambda x: torch.relu(torch.relu(x.reshape(-1, 130) @ W[0].t() + B[0]) @ W[1].t() + B[1]) @ W[2].t() + B[2]   # networks.py:96-102 in float64
+    rng = np.random.default_rng(2)
+    for E in (1, 15, 33, 4099):
+        run = PolicyRunner(actor, critic, E, "cuda")
+        obs = torch.from_numpy((rng.random((E, 2, 65)) * 2 - 0.5).astype(np.float32)).cuda()
+        val = run.values(obs)
+        with torch.no_grad():
+            ref = c64(obs.double()).reshape(-1)
+        assert torch.allclose(val.double(), ref, rtol=1e-5, atol=2e-6), (E, float((val.double() - ref).abs().max()))
