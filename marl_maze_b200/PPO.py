@@ -97,6 +97,7 @@ class PPO:
         self.fused_update = fused_update  # actor trunk + heads + clipped surrogate, fwd and bwd, as hand-written tcgen05 3xTF32 kernels (update.py)
         self.prefetch_pool = prefetch_pool  # build the next rollout's maze pool in the background during the update (off by default: it only moves
                                             # the ~13 ms carve from the rollout to the update, and hurts when rollouts follow each other directly)
+        self.batched_values = os.environ.get("MARL_MAZE_BATCHED_VALUES", "1") != "0"   # critic once per rollout over the whole buffer (see get_batch)
         self.use_cuda_graph = use_cuda_graph  # replay the T-step rollout (6 launches per step) as one captured CUDA graph from the 2nd rollout on
         self._buf = None
         self._graph = None
@@ -146,9 +147,16 @@ class PPO:
 
         def body():  # launches only: no allocation, no host sync -> capturable
             for t in range(T):  # PPO.py:108-141, one iteration = one step of every env
-                pol.forward(obs[t], masks[t], actions_out=actions[t], logp=logp[t], value=values[t], counter=t + 1)
+                pol.forward(obs[t], masks[t], actions_out=actions[t], logp=logp[t], value=None if self.batched_values else values[t],
+                            want_value=not self.batched_values, counter=t + 1)
                 eng.step(actions[t], auto_reset=True, obs=obs[t + 1], masks=masks[t + 1], reward=reward[t], done=done[t])
-            pol.values(obs[T], values[T])  # V(s_T) bootstraps the episodes still open at the horizon
+            if self.batched_values:
+                # Nothing in the loop reads V(s_t) (PPO.py:116 only records it for the advantages): the critic runs ONCE over all (T + 1) E observation
+                # pairs of the rollout buffer -- V(s_T) included, which bootstraps the episodes still open at the horizon -- instead of as a forked
+                # side-stream launch in every step (128 block prologues and 128 fork / join edges of the captured graph less)
+                pol.values(obs.view((T + 1) * E, 2, 65), values.view((T + 1) * E))
+            else:
+                pol.values(obs[T], values[T])  # V(s_T) bootstraps the episodes still open at the horizon
             _gae(reward, values[:T], done, values[T], self.discount_rate, self.lam, out=adv)
             pol.bump(T)                    # next rollout / replay continues the sampling stream
 
