@@ -109,6 +109,9 @@ __device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_
 // evict_last policy, the window bulk copies and the observation bulk store evict_first, so that in an env-only stepping loop (BASELINE config[3]) the
 // state stays resident between launches: its 2 x 59 MB leave the DRAM traffic and the FIRST of the two dependent round trips (state -> window address)
 // becomes an L2 hit.
+#ifndef MM_K2_PREFETCH_WARPS
+#define MM_K2_PREFETCH_WARPS 0
+#endif
 #ifndef MM_K2_L2HINT
 #define MM_K2_L2HINT 0
 #endif
@@ -612,6 +615,21 @@ __global__ void __launch_bounds__(kThreads, kGroups == 2 ? MM_K2_MINBLOCKS2 : MM
     extern __shared__ __align__(16) float s_obs[];  // [kGroups][kThreads][65]
     const int tid = threadIdx.x, lane = tid & 31;
     LaneCtx c[kGroups];
+#if MM_K2_PREFETCH_WARPS > 0
+    // A warp's first act is a DRAM round trip for its agent / env state, with nothing else to do while it waits (24 % of the kernel's stall samples sit on
+    // the first use of that load).  Blocks are dispatched in index order as residency slots free up, so the warp MM_K2_PREFETCH_WARPS groups further on starts
+    // about one block lifetime from now: ask the L2 for ITS state lines now (7 lines per warp: 4 of agent_a, 1 of agent_b, 2 of env_hdr).
+    if (!kResetOnly) {
+        const long long gp = ((long long)blockIdx.x * kGroups * kThreads + (tid & ~31)) + (long long)MM_K2_PREFETCH_WARPS * 32;   // first agent of that warp
+        if (gp < 2ll * p.E) {
+            const void* a = nullptr;
+            if (lane < 4) a = &p.agent_a[gp + 8 * lane];
+            else if (lane == 4) a = &p.agent_b[gp];
+            else if (lane < 7) a = &p.env_hdr[(gp >> 1) + 8 * (lane - 5)];
+            if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    }
+#endif
 #pragma unroll
     for (int gi = 0; gi < kGroups; gi++) {
         c[gi].g = ((long long)blockIdx.x * kGroups + gi) * kThreads + tid;
