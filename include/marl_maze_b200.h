@@ -253,6 +253,9 @@ int mm_ppo_heads_loss(const float *h2, const float *head_w, const float *head_b,
  */
 int mm_segment_sum_blocks(int rows);
 int mm_segment_sum(const float *x, const int64_t *seg, int rows, int cols, int n_seg, float *part, void *stream);
+/* the gather itself: out [rows][cols] <- src[seg[r]][:] for src [n_src <= 8][cols] (cols a multiple of 4, n_src * cols * 4 <= 48 KB; seg values are
+ * clamped to [0, n_src)); src and out 16-byte aligned */
+int mm_gather_rows(const float *src, const int64_t *seg, int rows, int cols, int n_src, float *out, void *stream);
 
 /*
  * The 23-token embedding of K4 as a stand-alone pair (Projection + m_Attention, networks.py:58-65,75-82, and their backward).

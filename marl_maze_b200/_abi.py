@@ -14,7 +14,7 @@ EXPORTS = [
     "mm_unpack_agents", "mm_unpack_envs", "mm_unpack_layout", "mm_unpack_pool", "mm_gae",
     "mm_policy_offsets", "mm_sizeof_policy_scratch", "mm_policy_forward", "mm_critic_forward", "mm_selftest_div", "mm_counter_add",
     "mm_wgrad_geometry", "mm_wgrad_tf32x3", "mm_linear_tf32x3", "mm_linear_f16x3", "mm_ppo_loss_geometry", "mm_ppo_heads_loss",
-    "mm_segment_sum_blocks", "mm_segment_sum", "mm_tokens_forward", "mm_tokens_forward_full", "mm_tokens_backward_blocks", "mm_tokens_backward", "mm_sizeof_tokens_backward_scratch",
+    "mm_segment_sum_blocks", "mm_segment_sum", "mm_gather_rows", "mm_tokens_forward", "mm_tokens_forward_full", "mm_tokens_backward_blocks", "mm_tokens_backward", "mm_sizeof_tokens_backward_scratch",
 ]
 
 
@@ -95,7 +95,7 @@ def lib():
         "mm_tokens_backward": (i32, [vp, vp, vp, i32, vp, vp, vp]),
         "mm_sizeof_tokens_backward_scratch": (sz, [i32]),
         "mm_segment_sum_blocks": (i32, [i32]),
-        "mm_segment_sum": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+        "mm_segment_sum": (i32, [vp, vp, i32, i32, i32, vp, vp]), "mm_gather_rows": (i32, [vp, vp, i32, i32, i32, vp, vp]),
         "mm_ppo_heads_loss": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]),
     }
     for name in EXPORTS:

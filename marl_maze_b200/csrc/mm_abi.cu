@@ -271,6 +271,11 @@ int mm_segment_sum(const float* x, const int64_t* seg, int rows, int cols, int n
     return cuda_status(launch_segment_sum(x, (const long long*)seg, rows, cols, n_seg, part, (cudaStream_t)stream));
 }
 
+int mm_gather_rows(const float* src, const int64_t* seg, int rows, int cols, int n_src, float* out, void* stream) {
+    if (!src || !seg || !out || rows <= 0 || cols <= 0 || (cols & 3) || n_src < 1 || n_src > 8 || ((uintptr_t)src & 15) || ((uintptr_t)out & 15)) return MM_ERR_BAD_ARG;
+    return cuda_status(launch_gather_rows(src, (const long long*)seg, rows, cols, n_src, out, (cudaStream_t)stream));
+}
+
 int mm_tokens_forward(const float* weights, const float* obs, int rows, float* x0, void* stream) {
     if (!weights || !obs || !x0 || rows <= 0 || ((uintptr_t)x0 & 15)) return MM_ERR_BAD_ARG;
     return cuda_status(launch_tokens_fwd(weights, obs, rows, x0, (cudaStream_t)stream));

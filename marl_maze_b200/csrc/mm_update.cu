@@ -180,6 +180,33 @@ __global__ void __launch_bounds__(SS_THREADS) k_segment_sum(const float* __restr
     }
 }
 
+// out[r][:] = src[seg[r]][:] for a handful (<= 8) of source rows: the forward of the gather whose adjoint is k_segment_sum (the embedding of each agent row
+// from the few distinct embeddings, update._ActorTrunkLoss).  The source rows sit in shared memory; a warp writes one 16-byte-per-lane stripe of a row per
+// instruction with streaming stores -- the kernel is nothing but its rows x cols x 4 bytes of HBM writes (torch's index_select ran at a third of that rate).
+constexpr int GR_THREADS = 256;
+__global__ void __launch_bounds__(GR_THREADS) k_gather_rows(const float* __restrict__ src, const long long* __restrict__ seg, int rows, int cols, int n_src,
+                                                            float* __restrict__ out) {
+    extern __shared__ __align__(16) float gr_src[];   // [n_src][cols]
+    for (int i = threadIdx.x; i < n_src * cols / 4; i += GR_THREADS) reinterpret_cast<float4*>(gr_src)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    __syncthreads();
+    const int c4n = cols / 4, w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GR_THREADS / 32;
+    for (long long r = (long long)blockIdx.x * nw + w; r < rows; r += (long long)gridDim.x * nw) {
+        int sg = (int)__ldg(&seg[r]);
+        sg = sg < 0 ? 0 : sg >= n_src ? n_src - 1 : sg;   // never read outside the staged rows
+        const float4* s4 = reinterpret_cast<const float4*>(gr_src + (size_t)sg * cols);
+        float4* o4 = reinterpret_cast<float4*>(out + (size_t)r * cols);
+        for (int c = lane; c < c4n; c += 32) __stcs(&o4[c], s4[c]);
+    }
+}
+
+cudaError_t launch_gather_rows(const float* src, const long long* seg, int rows, int cols, int n_src, float* out, cudaStream_t stream) {
+    if (n_src < 1 || n_src > SS_MAX_SEG || (cols & 3) || rows <= 0 || cols <= 0 || (size_t)n_src * cols * 4 > 48 * 1024) return cudaErrorInvalidValue;
+    const int want = 148 * 8, nw = GR_THREADS / 32;
+    const long long need = ((long long)rows + nw - 1) / nw;
+    k_gather_rows<<<(int)(need < want ? need : want), GR_THREADS, (size_t)n_src * cols * 4, stream>>>(src, seg, rows, cols, n_src, out);
+    return cudaGetLastError();
+}
+
 int segment_sum_blocks(int rows) {
     const int want = 148 * 8;
     return rows < want ? (rows > 0 ? rows : 1) : want;

@@ -21,6 +21,7 @@ cudaError_t launch_wgrad_tc(const float* dz, const float* h, int R, int n_out, i
 void wgrad_geometry(int R, int n_out, int k_in, int* slabs, int* ld, int* kb_per, int* out_rows, int* transposed);
 int segment_sum_blocks(int rows);
 cudaError_t launch_segment_sum(const float* x, const long long* seg, int rows, int cols, int n_seg, float* part, cudaStream_t stream);
+cudaError_t launch_gather_rows(const float* src, const long long* seg, int rows, int cols, int n_src, float* out, cudaStream_t stream);
 struct HeadArgs;
 cudaError_t launch_linear_tc_ex(const float* x, const float* w_hi, const float* w_lo, int n_rows_w, const float* bias, float* y, int ldy, int M, int K, int mode,
                                 const uint32_t* gate, uint32_t* gate_out, const float* head_w, const float* head_b, const HeadArgs* heads, cudaStream_t stream);

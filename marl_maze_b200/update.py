@@ -56,6 +56,18 @@ def segment_sum(x: torch.Tensor, seg: torch.Tensor, n_seg: int) -> torch.Tensor:
     return part.sum(0)
 
 
+def gather_rows(src: torch.Tensor, inv: torch.Tensor) -> torch.Tensor:
+    """src[inv] for src [U <= 8, cols] f32 and inv [rows] int64 (mm_gather_rows: the source rows from shared memory, streaming stores at HBM write speed);
+    anything else falls to index_select."""
+    if not (src.is_cuda and src.dtype == torch.float32 and inv.dtype == torch.int64 and src.dim() == 2 and 1 <= src.shape[0] <= 8 and src.shape[1] % 4 == 0
+            and src.shape[0] * src.shape[1] * 4 <= 48 * 1024 and inv.dim() == 1 and inv.numel() > 0):
+        return src.index_select(0, inv)
+    src, inv = src.contiguous(), inv.contiguous()
+    out = torch.empty(inv.numel(), src.shape[1], device=src.device, dtype=torch.float32)
+    _abi.check(_abi.lib().mm_gather_rows(_ptr(src), _ptr(inv), inv.numel(), src.shape[1], src.shape[0], _ptr(out), _stream(src)), "mm_gather_rows")
+    return out
+
+
 class GatherRows(torch.autograd.Function):
     """src[inv] for a handful (<= 8) of distinct source rows; the backward is mm_segment_sum instead of a scatter-add into those rows."""
 
@@ -63,7 +75,7 @@ class GatherRows(torch.autograd.Function):
     def forward(ctx, src, inv):
         ctx.save_for_backward(inv)
         ctx.n = src.shape[0]
-        return src.index_select(0, inv)
+        return gather_rows(src.detach(), inv)
 
     @staticmethod
     def backward(ctx, g):
@@ -249,7 +261,7 @@ class _ActorTrunkLoss(torch.autograd.Function):
     def forward(ctx, x0, inv, w0, b0, w1, b1, w2, b2, wh, bh, sp, masks, actions, old_logp, adv, clip, scale):
         """x0 [2E,460], inv None -- or x0 = the few DISTINCT embedding rows [U<=8,460] and inv [2E] the row of each agent (Actor.embed_parts)."""
         src = x0.detach().contiguous()
-        x0 = src if inv is None else src.index_select(0, inv)
+        x0 = src if inv is None else gather_rows(src, inv)
         if FWD_FP16:   # forward GEMMs: 3xFP16, two CTAs per SM (the data / weight gradients below need TF32's exponent range)
             h0, bits0 = linear_f16(x0, sp["fwd16"][0], b0, want_bits=True)
             h1, bits1 = linear_f16(h0, sp["fwd16"][1], b1, want_bits=True)

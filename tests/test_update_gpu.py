@@ -325,3 +325,14 @@ def test_fused_critic_loss_matches_autograd():
     assert abs(float(loss.detach()) - float(ref_loss.detach())) < 1e-5 * float(ref_loss.detach())
     for (name, p), (_, q) in zip(critic.named_parameters(), ref.named_parameters()):
         assert _rel(p.grad, q.grad) < 2e-5, (name, _rel(p.grad, q.grad))
+
+
+def test_gather_rows_equals_index_select():
+    """mm_gather_rows (the forward of the embedding gather whose adjoint is mm_segment_sum): a pure copy, bit-identical to index_select, for ragged row
+    counts and every legal number of source rows."""
+    from marl_maze_b200.update import gather_rows
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for U, rows, cols in ((1, 1, 460), (4, 33, 460), (8, 100_003, 460), (5, 4097, 264), (3, 70_001, 64)):
+        src = torch.randn(U, cols, device="cuda", generator=g)
+        inv = torch.randint(0, U, (rows,), device="cuda", generator=g)
+        assert torch.equal(gather_rows(src, inv), src.index_select(0, inv)), (U, rows, cols)
