@@ -15,6 +15,9 @@
 
 namespace mm {
 
+#ifndef MM_UL_PREFETCH
+#define MM_UL_PREFETCH 1
+#endif
 #ifndef MM_UL_MINBLOCKS
 #define MM_UL_MINBLOCKS 3
 #endif
@@ -41,15 +44,30 @@ __global__ void __launch_bounds__(UL_WARPS * 32, MM_UL_MINBLOCKS) k_ppo_heads_lo
     }
     const bool tail = lane < UL_HID - 8 * 32;  // lanes 0-7 own a 9th column
     const int wglobal = blockIdx.x * UL_WARPS + warp, wstride = gridDim.x * UL_WARPS;
-    for (int e = wglobal; e < a.E; e += wstride) {
-        float hv[2][UL_CPL], l[2][6];
+    // the two activation rows of an env are fetched one env ahead: the warp has nothing else in flight while it waits for them (12 warps per SM)
+    float hn[2][UL_CPL];
+    auto fetch = [&](int e) {
 #pragma unroll
         for (int ag = 0; ag < 2; ag++) {
             const float* hr = a.h2 + (size_t)(2 * e + ag) * UL_HID;
 #pragma unroll
-            for (int i = 0; i < 8; i++) hv[ag][i] = __ldg(hr + lane + 32 * i);
-            hv[ag][8] = tail ? __ldg(hr + lane + 256) : 0.f;
+            for (int i = 0; i < 8; i++) hn[ag][i] = e < a.E ? __ldg(hr + lane + 32 * i) : 0.f;
+            hn[ag][8] = (tail && e < a.E) ? __ldg(hr + lane + 256) : 0.f;
         }
+    };
+    fetch(wglobal);
+    for (int e = wglobal; e < a.E; e += wstride) {
+        float hv[2][UL_CPL], l[2][6];
+#if !MM_UL_PREFETCH
+        fetch(e);
+#endif
+#pragma unroll
+        for (int ag = 0; ag < 2; ag++)
+#pragma unroll
+            for (int i = 0; i < UL_CPL; i++) hv[ag][i] = hn[ag][i];
+#if MM_UL_PREFETCH
+        fetch(e + wstride);
+#endif
 #pragma unroll
         for (int ag = 0; ag < 2; ag++)
 #pragma unroll
