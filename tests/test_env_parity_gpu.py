@@ -298,3 +298,53 @@ def test_illegal_actions_follow_the_stated_convention():
         _assert_obs_equal(g[0].cpu().numpy()[keep], o[0][keep], f"after illegal step +{t}")
         assert np.array_equal(g[1].cpu().numpy()[keep], o[1][keep])
     assert np.array_equal(eng.envs()[:, 6] != 0, kind != 0)
+
+
+def test_full_size_config4_sampled_envs_bit_exact_and_global_invariants():
+    """BASELINE config[3] at its FULL size -- 1 Mi mazes of side 49 (4x the default area), two pool mazes per env built by K1, uniform mask-legal actions
+    sampled in the kernel, auto-reset on -- checked two ways: (1) 1 024 environments spread over the whole batch (first / last warps, block boundaries,
+    random ones) are replayed by the oracle on the SAME mazes (generated by the oracle itself from the maze keys) with the recorded actions: observations
+    (bit patterns), masks, rewards, dones and the unpacked agent state must be identical at every one of 160 steps, resets included (max_timestep 64);
+    (2) size-independent properties of the whole batch: no error flag, every sampled action legal under the previous masks, every observation finite with a
+    one-hot facing and a one-hot agent id, rewards in {0, 0.5, 1}, a done either a joint exit (reward 1) or the truncation."""
+    E, S, max_t, T, n_s = 1 << 20, 49, 64, 160, 1024
+    seed, base = 4242, 17
+    eng = _engine(E, smax=S, max_timestep=max_t, pool_size=2 * E)
+    eng.generate(seed, side_range=(25, 25), rand_start=True, difficulty=1, id_base=base)
+    rng = np.random.default_rng(0)
+    pick = np.unique(np.concatenate([np.arange(0, 40), np.arange(E - 40, E), np.arange(63, 66), np.arange(4095, 4098), rng.integers(0, E, n_s)]))[:n_s]
+    n_s = len(pick)
+    ob = OracleBatch(n_s, 2 * n_s, max_timestep=max_t, threads=8)
+    o = OracleMaze(max_timestep=10, difficulty=1, rand_start=True, rand_sizes=True, rand_range=(25, 25), default_size=(4, 4))
+    for k in range(2):
+        for i, e in enumerate(pick):
+            o.seed_philox(seed, base + int(e) + k * E); o.build(); ob.set_pool_maze(i + k * n_s, o.maze())
+    idx = torch.from_numpy(pick).to(eng.device)
+    o_obs, o_masks = ob.reset_all()
+    g_obs, g_masks = eng.reset()
+    _assert_obs_equal(g_obs[idx].cpu().numpy(), o_obs, "reset")
+    assert np.array_equal(g_masks[idx].cpu().numpy(), o_masks)
+    act_out = torch.zeros(E, 2, 2, dtype=torch.uint8, device=eng.device)
+    prev_masks = g_masks.clone()
+    n_done = n_exit = 0
+    for t in range(T):
+        g_obs, g_masks, g_r, g_d = eng.step(None, auto_reset=True, action_seed=11, actions_out=act_out)
+        # (2) whole-batch properties
+        mv = act_out[:, :, 0].long()
+        assert bool(torch.gather(prev_masks[:, :, :5], 2, mv.unsqueeze(-1)).all()) and bool((act_out[:, :, 1] <= prev_masks[:, :, 5]).all()), t
+        assert bool(torch.isfinite(g_obs).all()) and bool((g_obs[:, :, 0:4].sum(-1) == 1).all()) and bool((g_obs[:, :, 63:65].sum(-1) == 1).all()), t
+        assert bool(((g_r == 0) | (g_r == 0.5) | (g_r == 1)).all()), t
+        # a finished env either solved the maze (reward 1) or ran into the truncation; the oracle comparison below pins which
+        assert bool((g_d.bool() | (g_r != 1)).all()), t
+        n_done += int(g_d.sum()); n_exit += int((g_r == 1).sum())
+        prev_masks.copy_(g_masks)
+        # (1) sampled envs against the oracle
+        act = act_out[idx].cpu().numpy()
+        o_obs, o_masks, o_r, o_d = ob.step(act, auto_reset=True)
+        assert np.array_equal(g_d[idx].cpu().numpy(), o_d), f"done differs at step {t}"
+        assert np.array_equal(g_r[idx].cpu().numpy(), o_r), f"reward differs at step {t}"
+        _assert_obs_equal(g_obs[idx].cpu().numpy(), o_obs, f"step {t}")
+        assert np.array_equal(g_masks[idx].cpu().numpy(), o_masks), f"masks differ at step {t}"
+    assert np.array_equal(eng.agents()[pick], ob.agents())
+    assert int(eng.envs()[:, 6].sum()) == 0 and ob.errors() == 0
+    assert n_done >= 2 * E          # every env was truncated at least twice in 160 steps of max_timestep 64

@@ -318,3 +318,37 @@ def test_get_action_kernel_path_equals_the_module_path(tmp_path):
     sd = {k: v + 0.01 for k, v in brain.actor.state_dict().items()}
     brain.actor.load_state_dict(sd)
     check(10, 300)
+
+
+def test_full_size_config3_rollout_properties_and_sampled_parity(tmp_path):
+    """BASELINE config[2] at its FULL size: 65 536 mazes x 2 agents, T = 128 (8.4 M env-steps), main.py's maze settings.  Size-independent properties of the
+    whole rollout (every recorded action legal under its recorded mask, finite log-probs / values / advantages, episode bookkeeping consistent) and, on
+    4 096 sampled (t, env) rows, the kernel policy against the autograd modules (joint log-prob and value, 1e-5 relative) plus the GAE of 64 sampled
+    environments against the oracle's restatement of PPO.get_GAEs bootstrapped at the horizon."""
+    from oracle import ppo_oracle as po
+    from marl_maze_b200.PPO import PPO
+    from marl_maze_b200.maze import Maze
+    from marl_maze_b200.maze_agent import Agent
+    E, T = 65536, 128
+    brain = PPO(agent_amount=2, batch_size=E * T - 5, lr=0.00014, epochs=1, verbose=False, model_path=None, horizon=T)
+    agents = (Agent("RED", brain, None, None, 2), Agent("BLUE", brain, None, None, 3))
+    Maze(agents=agents, max_timestep=1200, rand_sizes=True, rand_range=[12, 13], rand_start=True, num_envs=E, seed=1)
+    for rollout in range(2):        # the second one is the captured CUDA graph
+        b_obs, b_act, b_logp, b_sp, ep_lens, b_masks, b_advs, b_vals = brain.get_batch()
+        N = E * T
+        assert b_obs.shape == (N, 2, 65) and b_logp.shape == (N,)
+        legal = torch.gather(b_masks[:, :, :5], 2, b_act[:, :, :1].long())
+        assert bool(legal.all()) and bool((b_act[:, :, 1] <= b_masks[:, :, 5].float()).all())
+        assert bool(torch.isfinite(b_logp).all()) and bool(torch.isfinite(b_vals).all()) and bool(torch.isfinite(b_advs).all()) and bool((b_logp <= 0).all())
+        assert brain.last_stats["env_steps"] == N and len(ep_lens) == len(b_sp) == brain.last_stats["episodes"]
+        g = torch.Generator(device="cuda").manual_seed(rollout)
+        rows = torch.randint(0, N, (4096,), device="cuda", generator=g)
+        with torch.no_grad():
+            lp = brain.joint_log_probs(b_obs[rows], b_act[rows], b_masks[rows])
+            v = brain.get_state_values(b_obs[rows])
+        assert torch.allclose(lp, b_logp[rows], rtol=1e-5, atol=2e-6) and torch.allclose(v, b_vals[rows], rtol=1e-5, atol=2e-6)
+        buf = brain._buf
+        envs = torch.randint(0, E, (64,), generator=torch.Generator().manual_seed(rollout)).tolist()
+        r, vals, d, adv = (buf[k].cpu().numpy() for k in ("reward", "values", "done", "adv"))
+        want = po.gae_fixed_horizon(r[:, envs], vals[:T][:, envs], d[:, envs].astype(bool), vals[T][envs], brain.discount_rate, brain.lam)
+        assert np.array_equal(adv[:, envs].view(np.uint32), want.view(np.uint32)), "GAE of the sampled envs differs from the oracle"

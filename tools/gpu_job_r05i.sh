@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests/test_ppo_gpu.py -q -x -k "full_size" ) 2>&1 | tail -25
