@@ -154,7 +154,10 @@ class PPO:
                 # Nothing in the loop reads V(s_t) (PPO.py:116 only records it for the advantages): the critic runs ONCE over all (T + 1) E observation
                 # pairs of the rollout buffer -- V(s_T) included, which bootstraps the episodes still open at the horizon -- instead of as a forked
                 # side-stream launch in every step (128 block prologues and 128 fork / join edges of the captured graph less)
-                pol.values(obs.view((T + 1) * E, 2, 65), values.view((T + 1) * E))
+                rows_per_call = max(1, (1 << 28) // E)          # the C ABI counts environments in an int
+                for t0 in range(0, T + 1, rows_per_call):
+                    t1 = min(T + 1, t0 + rows_per_call)
+                    pol.values(obs[t0:t1].view((t1 - t0) * E, 2, 65), values[t0:t1].view((t1 - t0) * E))
             else:
                 pol.values(obs[T], values[T])  # V(s_T) bootstraps the episodes still open at the horizon
             _gae(reward, values[:T], done, values[T], self.discount_rate, self.lam, out=adv)
