@@ -73,7 +73,7 @@ size_t mm_sizeof_env_episode(int n_envs);
 size_t mm_sizeof_agent_a(int n_envs);
 size_t mm_sizeof_agent_b(int n_envs);
 size_t mm_sizeof_finalize_scratch(int n, int smax);
-size_t mm_sizeof_generate_scratch(int n, int smax);
+size_t mm_sizeof_generate_scratch(int n, int smax); /* 16: the generator keeps its working state in shared memory; the scratch argument of mm_generate* stays in the ABI (a non-NULL device pointer to that many bytes) */
 
 /* Agent.__init__ state for every agent (maze_agent.py:16-57): x=y=0, facing south, exit_len=-1, empty memory. */
 int mm_init_state(const mm_state *st, void *stream);
