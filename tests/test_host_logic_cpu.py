@@ -92,3 +92,32 @@ def test_checkpoint_written_here_loads_in_the_reference(tmp_path):
     assert np.array_equal(np.asarray(d["mv"], np.float32), mv.numpy()) and np.array_equal(np.asarray(d["mk"], np.float32), mk.numpy())
     assert np.array_equal(np.asarray(d["v"], np.float32), v.numpy())
     assert d["lr"] == pytest.approx(0.00014 * 0.997 ** 2, rel=1e-12) and d["clr"] == pytest.approx(0.00014 * 0.997 ** 2, rel=1e-12) and d["step"] == 1.0
+
+
+def test_sample_action_is_the_reference_draw_bit_for_bit():
+    """PPO._sample_action (the host-side draw of PPO.get_action on a GPU, and the whole of it on a CPU) against the reference's own lines
+    (PPO.py:175-186: masked Categorical, sigmoid / Bernoulli mark, joint log-prob) evaluated with torch.distributions on the same logits and the same
+    generator state: identical actions and bit-identical log-probs, for every mask pattern that leaves a legal move."""
+    from marl_maze_b200.PPO import PPO
+    g = torch.Generator().manual_seed(0)
+    n = 0
+    for trial in range(300):
+        mv = torch.randn(1, 5, generator=g) * (0.1 + trial % 7)
+        mk = torch.randn(1, 1, generator=g) * 3
+        mask = [bool(v) for v in (torch.rand(6, generator=g) < 0.6).tolist()]
+        if not any(mask[:5]):
+            mask[trial % 5] = True
+        torch.manual_seed(1000 + trial)
+        m = torch.tensor(mask)
+        dist = torch.distributions.Categorical(logits=torch.where(m[:5], mv, torch.tensor(-float("inf"))))
+        move = dist.sample()
+        p = torch.sigmoid(mk) if mask[5] else torch.zeros(1, 1)
+        mark = torch.bernoulli(p)
+        p = p if mark == 1 else 1 - p
+        want = ([int(move.item()), float(mark.item())], dist.log_prob(move) + torch.log(p))
+        torch.manual_seed(1000 + trial)
+        got = PPO._sample_action(mv, mk, mask)
+        assert got[0] == want[0] and mask[got[0][0]] and (mask[5] or got[0][1] == 0.0), (trial, got, want)
+        assert torch.equal(got[1].reshape(-1), want[1].reshape(-1)), (trial, got[1], want[1])
+        n += 1
+    assert n == 300
